@@ -1,0 +1,220 @@
+/*
+ * kin_b200.h -- C ABI of libkin_b200.so, the B200 (sm_100a) backend for the data-parallel hot
+ * path of HiroIshida/Kinematics.jl: batched forward kinematics, geometric / Euler-rate Jacobians
+ * and the sphere-vs-box-SDF collision cost + gradient.
+ *
+ * The reference has NO FFI on this path (it is plain Julia); the functions below are
+ * what a `CUDABackend` Julia module binds with `ccall` (julia/CUDABackend.jl) and
+ * what the Python host mirror binds with ctypes.  Each entry point names the reference function
+ * it replaces (paths relative to the reference's src/).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative KinStatus otherwise; the text of the last
+ *     error on the calling thread is kin_last_error().  Nothing throws, nothing calls exit().
+ *   - ids are 1-BASED exactly as the reference assigns them: links / joints in URDF document
+ *     order (load_urdf.jl:22-32), appended links after them (mechanism.jl:239-243); boxes in
+ *     UnionSDF.sdfs order (sdf.jl:84-95); spheres in sscc.sphere_links order (collision.jl:41-48).
+ *   - 4x4 matrices are COLUMN-MAJOR, i.e. the memory of the reference's `Transform.mat`
+ *     (transform.jl:3-5), so Julia passes `pose.mat` by reference unchanged.
+ *   - a "configuration" is the reference's `angles` vector of set_joint_angles
+ *     (mechanism.jl:223-231): the n_joints control-joint values in the caller's `joints` order,
+ *     followed by (x, y, theta) of the planar base when the model was created with_base.
+ *   - batched arrays come in two layouts (KinLayout).  With n_dof = n_joints (+3), for batch N:
+ *       KIN_LAYOUT_SOA  batch index fastest:   q[c*ld + n],  T[(l*12+k)*ld + n], ...
+ *                       = Julia Array of size (N, n_dof), (N, 12, L), (N, rows, cols, n_req), (N, n_dof, S)
+ *       KIN_LAYOUT_AOS  one contiguous record per configuration: q[n*n_dof + c], T[(n*L + l)*12 + k], ...
+ *                       = Julia Array of size (n_dof, N), (3, 4, L, N), (rows, cols, n_req, N), (n_dof, S, N)
+ *                         i.e. the per-configuration arrays of the reference stacked along a last axis
+ *                         (xi of planning.jl:58 is exactly (n_dof, n_wp)).
+ *     `ld` (batch_stride) is the SoA distance between consecutive components, >= N; 0 means N.
+ *   - a transform is written as 3x4 column-major (k = col*3 + row: R columns then t); the constant
+ *     bottom row of the reference's 4x4 is not materialised.
+ *   - a Jacobian block is (rows, cols) column-major with rows = 3 or 6 and cols = n_dof, columns
+ *     in the caller's `joints` order then the 3 base columns (algorithm.jl:83-106).
+ *   - collision gradients are (n_dof, n_spheres) column-major per configuration (collision.jl:91).
+ *   - all device pointers are caller-owned; calls are asynchronous and ordered on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - a KinModel is immutable after creation except through kin_model_set_boxes /
+ *     kin_model_set_spheres (which must not race with launches that use the model); concurrent
+ *     kin_eval calls on different streams are allowed.  One model per device.
+ */
+#ifndef KIN_B200_H
+#define KIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KIN_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define KIN_API __attribute__((visibility("default")))
+#else
+#define KIN_API
+#endif
+
+typedef enum {
+    KIN_OK = 0,
+    KIN_ERR_INVALID_ARGUMENT = -1,
+    KIN_ERR_CUDA = -2,
+    KIN_ERR_LIMIT = -3,       /* model exceeds a compiled-in limit (KIN_MAX_*) */
+    KIN_ERR_NO_DEVICE = -4,
+    KIN_ERR_ALLOC = -5
+} KinStatus;
+
+typedef enum { KIN_F64 = 0, KIN_F32 = 1 } KinPrecision;
+typedef enum { KIN_LAYOUT_SOA = 0, KIN_LAYOUT_AOS = 1 } KinLayout;
+typedef enum { KIN_JOINT_FIXED = 0, KIN_JOINT_REVOLUTE = 1, KIN_JOINT_PRISMATIC = 2 } KinJointType;
+/* sdf.jl:34-41,116-119 is a forward difference (eps 1e-7) on the argmin box; KIN_GRAD_ANALYTIC is
+ * the closed form of the same box (an extension, off by default). */
+typedef enum { KIN_GRAD_FD = 0, KIN_GRAD_ANALYTIC = 1 } KinGradMode;
+/* collision.jl:76,90 reuses ONE 3 x n_dof Jacobian scratch across the spheres of a call and
+ * get_jacobian! (algorithm.jl:91-96) only overwrites relevant columns, so a sphere inherits the
+ * columns of joints that do not move it from the previous non-truncated sphere.
+ * KIN_SCRATCH_REFERENCE reproduces that bit for bit in sphere order; KIN_SCRATCH_CLEAN zeroes
+ * them (the mathematically correct gradient). */
+typedef enum { KIN_SCRATCH_REFERENCE = 0, KIN_SCRATCH_CLEAN = 1 } KinScratchMode;
+
+#define KIN_MAX_LINKS 512
+#define KIN_MAX_JOINTS 32          /* control joints (bitmask width), base columns excluded */
+#define KIN_MAX_SPHERES 512
+#define KIN_MAX_BOXES 128
+
+typedef struct KinModel KinModel;
+
+/*
+ * Flattened mechanism: what load_urdf.jl:20-80 + mechanism.jl:147-181 hold as Link / Joint
+ * objects, as tables indexed by link (0-based position i <-> reference link id i+1).
+ * All pointers are HOST memory and are copied; they may be freed after kin_model_create.
+ */
+typedef struct {
+    int32_t n_links;
+    const int32_t *parent_link;   /* [n_links] 1-based id of the parent link, -1 for the root (Link.plink_id) */
+    const int32_t *joint_type;    /* [n_links] KinJointType of the link's parent joint (root: fixed) */
+    const double *joint_pose;     /* [n_links][16] column-major Joint.pose (mechanism.jl:79), root: ignored */
+    const double *joint_axis;     /* [n_links][3]  unit axis in the joint frame (fixed: ignored) */
+    const int32_t *q_index;       /* [n_links] 0-based column of the configuration that drives the parent
+                                     joint (position in the caller's `joints` vector), or -1: the joint is
+                                     not controlled and sits at default_angle (Mechanism.angles) */
+    const double *default_angle;  /* [n_links] */
+    int32_t n_joints;             /* number of control joints D (length of `joints`) */
+    int32_t with_base;            /* Mechanism.with_base: 3 extra columns (x, y, theta), transform.jl:33-37 */
+
+    /* swept-sphere table: SweptSphereCollisionChecker (collision.jl:32-49). A sphere is a link
+     * attached to sphere_link through a fixed joint of pure translation sphere_center. */
+    int32_t n_spheres;
+    const int32_t *sphere_link;   /* [n_spheres] 1-based link id of the parent link */
+    const double *sphere_center;  /* [n_spheres][3] in the parent link frame */
+    const double *sphere_radius;  /* [n_spheres] */
+
+    /* UnionSDF of boxes (sdf.jl:48-114): world pose and full widths; a single BoxSDF is n_boxes = 1 */
+    int32_t n_boxes;
+    const double *box_pose;       /* [n_boxes][16] column-major world pose (BoxSDF.pose) */
+    const double *box_width;      /* [n_boxes][3] full extents (BoxSDF.width) */
+} KinModelDesc;
+
+/*
+ * One batched evaluation.  Any output pointer may be NULL, then that part is skipped.
+ * What is computed per configuration:
+ *   T_out     get_transform(m, link) for each fk_links[i]          (algorithm.jl:1-37)
+ *   J_out     get_jacobian(m, link, joints, with_rot; rpy_jac)     (algorithm.jl:83-114) for each jac_links[i]
+ *   vals_out  compute_coll_dists[_and_grads]!                      (collision.jl:51-58, 67-94)
+ *   grads_out                                                      (collision.jl:67-94)
+ *   argmin_out  UnionSDF.min_idx_cache per sphere, 1-based         (sdf.jl:112)
+ */
+typedef struct {
+    int32_t precision;         /* KinPrecision: element type of q and of every floating output */
+    int32_t layout;            /* KinLayout of q and of every output */
+    int64_t n;                 /* batch size N */
+    int64_t batch_stride;      /* SoA only: ld (>= n), 0 => n */
+    const void *q;             /* DEVICE: configurations, n_dof = n_joints (+3) per configuration */
+
+    int32_t n_fk_links;        /* 0 => no FK output */
+    const int32_t *fk_links;   /* HOST [n_fk_links] 1-based link ids, output order */
+    void *T_out;               /* DEVICE 12 * n_fk_links per configuration */
+
+    int32_t n_jac_links;
+    const int32_t *jac_links;  /* HOST [n_jac_links] 1-based link ids */
+    int32_t with_rot;          /* rows = with_rot ? 6 : 3 */
+    int32_t rpy_jac;           /* rows 4:6 = Euler-rate map (algorithm.jl:56-63) instead of the axis */
+    int32_t keep_irrelevant;   /* 1 => get_jacobian! semantics: columns of joints that do not move the
+                                  link are NOT written (caller's buffer keeps its values); 0 => zeros */
+    void *J_out;               /* DEVICE rows * n_dof * n_jac_links per configuration */
+
+    double truncation_dist;    /* collision.jl:68; +inf => never truncate */
+    int32_t grad_mode;         /* KinGradMode */
+    int32_t scratch_mode;      /* KinScratchMode */
+    void *vals_out;            /* DEVICE n_spheres per configuration */
+    void *grads_out;           /* DEVICE n_dof * n_spheres per configuration; NULL => dists only */
+    int32_t *argmin_out;       /* DEVICE n_spheres int32 per configuration, or NULL */
+    double vals_offset;        /* subtracted from every value written to vals_out: planning.jl:66
+                                  (`dists .- margin`); 0 for the plain collision call */
+
+    void *stream;              /* cudaStream_t */
+} KinCall;
+
+KIN_API const char *kin_last_error(void);
+KIN_API int kin_abi_version(void);
+
+/* load_urdf.jl:20-80 / mechanism.jl:147-181 -> device tables on the CURRENT cuda device */
+KIN_API int kin_model_create(const KinModelDesc *desc, KinModel **out);
+KIN_API int kin_model_destroy(KinModel *model);
+/* add_coll_links (collision.jl:39-49): replaces the whole sphere table */
+KIN_API int kin_model_set_spheres(KinModel *model, int32_t n_spheres, const int32_t *sphere_link,
+                          const double *sphere_center, const double *sphere_radius);
+/* UnionSDF / BoxSDF poses after the obstacle moved (sdf.jl:14-32): replaces the whole box table */
+KIN_API int kin_model_set_boxes(KinModel *model, int32_t n_boxes, const double *box_pose, const double *box_width);
+KIN_API int kin_model_n_dof(const KinModel *model);      /* n_joints (+3) */
+KIN_API int kin_model_n_spheres(const KinModel *model);
+KIN_API int kin_model_n_boxes(const KinModel *model);
+
+/* The fused entry point: FK + Jacobians + collision in one pass over the batch. */
+KIN_API int kin_eval(KinModel *model, const KinCall *call);
+
+/* Same call with HOST q / outputs (pageable or pinned): the library stages chunks through its own
+ * device and pinned buffers on internal streams (H2D, kernel and D2H of consecutive chunks overlap)
+ * and returns when every output is in host memory.  `stream` is ignored. */
+KIN_API int kin_eval_host(KinModel *model, const KinCall *call);
+
+/* Convenience wrappers with the names of SURVEY 8b; each fills a KinCall and calls kin_eval. */
+/* get_transform, algorithm.jl:1 */
+KIN_API int kin_fk_links(KinModel *model, int32_t precision, int32_t layout, const void *q, int64_t n,
+                 const int32_t *link_ids, int32_t n_req, void *T_out, void *stream);
+/* get_transform + get_jacobian, algorithm.jl:1,108 */
+KIN_API int kin_fk_jacobian(KinModel *model, int32_t precision, int32_t layout, const void *q, int64_t n,
+                    const int32_t *link_ids, int32_t n_req, int32_t with_rot, int32_t rpy_jac,
+                    void *T_out, void *J_out, void *stream);
+/* compute_coll_dists! / compute_coll_dists_and_grads!, collision.jl:51,67 */
+KIN_API int kin_collision(KinModel *model, int32_t precision, int32_t layout, const void *q, int64_t n,
+                  double truncation_dist, int32_t grad_mode, int32_t scratch_mode,
+                  void *vals_out, void *grads_out, int32_t *argmin_out, void *stream);
+
+/* BoxSDF / UnionSDF call and gradient! at arbitrary points (sdf.jl:34-41, 67-74, 108-119): for a
+ * union of n_boxes boxes (HOST tables, same format as KinModelDesc), pts (DEVICE, N points x 3
+ * components in `layout`) -> vals_out[N], grads_out (3 per point in `layout`, nullable),
+ * argmin_out[N] (1-based box index, nullable). */
+KIN_API int kin_sdf_points(int32_t n_boxes, const double *box_pose, const double *box_width, int32_t precision,
+                   int32_t layout, const void *pts, int64_t n, int32_t grad_mode, void *vals_out,
+                   void *grads_out, int32_t *argmin_out, void *stream);
+
+/* Diagnostics for bench.py / tests: kernel launches issued by this library since load, and the
+ * static resources of the kernel a call would use (registers / thread, dynamic shared memory bytes /
+ * CTA, threads / CTA, CTAs in the grid).  */
+KIN_API int64_t kin_launch_count(void);
+KIN_API int kin_query_launch(KinModel *model, const KinCall *call, int32_t *regs, int32_t *smem_bytes,
+                     int32_t *block, int32_t *grid);
+
+/* Host-only (no device needed): compile the kinematic program a call with these requests would run
+ * and copy its tables out; the CPU test-suite interprets them against the oracle.  header_out
+ * receives the ProgHeader of csrc/kin_program.h as int32 words. */
+KIN_API int kin_program_dump(const KinModelDesc *desc, const int32_t *fk_links, int32_t n_fk,
+                             const int32_t *jac_links, int32_t n_jac, int32_t want_coll, int32_t want_stale,
+                             int32_t *header_out, int32_t header_cap, int32_t *ints_out, int32_t ints_cap,
+                             double *reals_out, int32_t reals_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KIN_B200_H */

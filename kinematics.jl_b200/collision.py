@@ -1,0 +1,77 @@
+"""SweptSphereCollisionChecker and compute_coll_dists[_and_grads] (collision.jl:1-103) on the B200
+backend."""
+from __future__ import annotations
+
+import uuid
+
+import numpy as np
+
+from . import lib as _lib
+from .algorithm import _check_joints
+from .device import current_q, device_model, evaluate
+from .mechanism import Link, Mechanism, SphereMetaData, add_new_link
+from .transform import Transform
+
+
+class SweptSphereCollisionChecker:         # collision.jl:32-37
+    def __init__(self, mech: Mechanism):
+        self.mech = mech
+        self.sphere_links, self.sphere_radii = [], []
+        self._parents, self._centers = [], []
+
+
+def add_coll_links(sscc: SweptSphereCollisionChecker, coll_link: Link, centers=None, radii=None):
+    """collision.jl:39-49.  The reference obtains (centers, radius) from scikit-robot's swept-sphere fit
+    of the link's collision mesh (collision.jl:16-30); meshes are not available offline, so the table is
+    passed in (``centers`` (k, 3) in the link frame, ``radii`` scalar or (k,))."""
+    if centers is None:
+        raise _lib.KinError("add_coll_links: swept-sphere generation from meshes is out of scope (SURVEY 8f-4); "
+                            "pass centers= and radii=")
+    centers = np.asarray(centers, dtype=np.float64).reshape(-1, 3)
+    radii = np.broadcast_to(np.asarray(radii, dtype=np.float64), (len(centers),))
+    for c, r in zip(centers, radii):
+        new_link = Link("sphere_" + str(uuid.uuid1()), link_type="CollSphere",
+                        geometric_meta_data=SphereMetaData(r, Transform()))
+        add_new_link(sscc.mech, new_link, coll_link, c)
+        sscc.sphere_links.append(new_link)
+        sscc.sphere_radii.append(float(r))
+        sscc._parents.append(coll_link.id)
+        sscc._centers.append(c.copy())
+
+
+def _prepare(sscc, joints, sdf):
+    m = sscc.mech
+    _check_joints(m, joints)
+    dm = device_model(m)
+    dm.set_spheres(sscc._parents, sscc._centers, sscc.sphere_radii)
+    poses, widths = sdf.world_boxes()
+    dm.set_boxes(poses, widths)
+    return m, dm
+
+
+def compute_coll_dists(sscc, joints, sdf, layout=None, dtype=None, return_argmin=False):
+    """collision.jl:51-65: ``vals[i] = sdf(centre_i) - r_i``.  single -> ndarray (S,); batch -> tensor (N, S)."""
+    m, dm = _prepare(sscc, joints, sdf)
+    Q, ql, N = current_q(m, dtype)
+    out = evaluate(dm, Q, ql, N, layout=layout, collision=True, with_grads=False, want_argmin=return_argmin)
+    vals = out["vals"][0].double().cpu().numpy() if m._single else out["vals"]
+    if return_argmin:
+        return vals, (out["argmin"][0].cpu().numpy() if m._single else out["argmin"])
+    return vals
+
+
+def compute_coll_dists_and_grads(sscc, joints, sdf, truncation_dist=np.inf, grad_mode=_lib.GRAD_FD,
+                                 scratch_mode=_lib.SCRATCH_REFERENCE, layout=None, dtype=None, return_argmin=False,
+                                 vals_offset=0.0):
+    """collision.jl:67-103.  single -> (vals (S,), grads (n_dof, S)); batch -> (N, S), (N, n_dof, S).
+    ``scratch_mode`` defaults to the reference's behaviour (one Jacobian scratch shared by all spheres,
+    collision.jl:76,90); ``SCRATCH_CLEAN`` gives the gradient with the untouched columns zeroed."""
+    m, dm = _prepare(sscc, joints, sdf)
+    Q, ql, N = current_q(m, dtype)
+    out = evaluate(dm, Q, ql, N, layout=layout, collision=True, with_grads=True, truncation_dist=truncation_dist,
+                   grad_mode=grad_mode, scratch_mode=scratch_mode, want_argmin=return_argmin, vals_offset=vals_offset)
+    if m._single:
+        res = (out["vals"][0].double().cpu().numpy(), out["grads"][0].double().cpu().numpy())
+        return res + (out["argmin"][0].cpu().numpy(),) if return_argmin else res
+    res = (out["vals"], out["grads"])
+    return res + (out["argmin"],) if return_argmin else res

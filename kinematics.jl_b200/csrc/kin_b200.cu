@@ -1,0 +1,533 @@
+// kin_b200.cu -- C ABI of libkin_b200.so (include/kin_b200.h): model handles, program cache,
+// launch configuration and the host-staged variant.  The kernel itself is kin_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/kin_b200.h"
+#include "kin_kernels.cuh"
+#include "kin_model.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return KIN_ERR_CUDA;
+}
+#define CUDA_TRY(expr)                                          \
+    do {                                                        \
+        cudaError_t e__ = (expr);                               \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #expr);   \
+    } while (0)
+
+struct DeviceProgram {
+    kin::Program prog;
+    int32_t *d_int = nullptr;
+    double *d_r64 = nullptr;
+    float *d_r32 = nullptr;
+    // launch configuration per (precision, layout)
+    int block[2][2] = {{0, 0}, {0, 0}}, occ[2][2] = {{0, 0}, {0, 0}}, regs[2][2] = {{0, 0}, {0, 0}};
+    size_t smem[2][2] = {{0, 0}, {0, 0}};
+};
+
+struct HostStage {          // resources of kin_eval_host, created on first use
+    static constexpr int kStreams = 3;
+    cudaStream_t stream[kStreams] = {nullptr, nullptr, nullptr};
+    void *buf[kStreams] = {nullptr, nullptr, nullptr};
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct KinModel {
+    kin::HostModel hm;
+    int device = 0, n_sm = 0;
+    std::mutex mu;
+    std::map<std::vector<int>, DeviceProgram *> cache;
+    HostStage stage;
+};
+
+namespace {
+
+void free_program(DeviceProgram *p) {
+    if (!p) return;
+    cudaFree(p->d_int); cudaFree(p->d_r64); cudaFree(p->d_r32);
+    delete p;
+}
+
+void clear_cache(KinModel *m) {
+    for (auto &kv : m->cache) free_program(kv.second);
+    m->cache.clear();
+}
+
+int load_spheres(kin::HostModel &hm, int32_t n, const int32_t *link, const double *center, const double *radius) {
+    if (n < 0 || n > KIN_MAX_SPHERES) return fail(KIN_ERR_LIMIT, "n_spheres exceeds KIN_MAX_SPHERES");
+    if (n > 0 && (!link || !center || !radius)) return fail(KIN_ERR_INVALID_ARGUMENT, "null sphere table");
+    hm.n_sph = n;
+    hm.sph_link.assign(n, 0); hm.sph_c.assign(3 * (size_t)n, 0.0); hm.sph_r.assign(n, 0.0);
+    for (int s = 0; s < n; ++s) {
+        if (link[s] < 1 || link[s] > hm.n_links) return fail(KIN_ERR_INVALID_ARGUMENT, "sphere_link id out of range");
+        hm.sph_link[s] = link[s] - 1;
+        for (int k = 0; k < 3; ++k) hm.sph_c[3 * s + k] = center[3 * s + k];
+        hm.sph_r[s] = radius[s];
+    }
+    return KIN_OK;
+}
+
+int load_boxes(kin::HostModel &hm, int32_t n, const double *pose, const double *width) {
+    if (n < 0 || n > KIN_MAX_BOXES) return fail(KIN_ERR_LIMIT, "n_boxes exceeds KIN_MAX_BOXES");
+    if (n > 0 && (!pose || !width)) return fail(KIN_ERR_INVALID_ARGUMENT, "null box table");
+    hm.n_box = n;
+    hm.box_inv.resize(n); hm.box_half.assign(3 * (size_t)n, 0.0);
+    for (int b = 0; b < n; ++b) {
+        kin::Xf P = kin::Xf::from_colmajor16(pose + 16 * b), inv;
+        // inv(tf) = (-R' t, R')  (transform.jl:62-65)
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) inv.r[r * 3 + c] = P.r[c * 3 + r];
+        for (int r = 0; r < 3; ++r)
+            inv.p[r] = (-inv.r[r * 3 + 0]) * P.p[0] + (-inv.r[r * 3 + 1]) * P.p[1] + (-inv.r[r * 3 + 2]) * P.p[2];
+        hm.box_inv[b] = inv;
+        for (int k = 0; k < 3; ++k) hm.box_half[3 * b + k] = 0.5 * width[3 * b + k];   // sdf.jl:68
+    }
+    return KIN_OK;
+}
+
+int host_model_from_desc(const KinModelDesc *d, kin::HostModel &hm) {
+    if (d->n_links <= 0 || d->n_links > KIN_MAX_LINKS) return fail(KIN_ERR_LIMIT, "n_links out of range (KIN_MAX_LINKS)");
+    if (d->n_joints < 0 || d->n_joints > KIN_MAX_JOINTS) return fail(KIN_ERR_LIMIT, "n_joints out of range (KIN_MAX_JOINTS)");
+    if (!d->parent_link || !d->joint_type || !d->joint_pose || !d->joint_axis || !d->q_index || !d->default_angle)
+        return fail(KIN_ERR_INVALID_ARGUMENT, "null mechanism table");
+    const int L = d->n_links;
+    hm.n_links = L; hm.n_joints = d->n_joints; hm.with_base = d->with_base ? 1 : 0;
+    hm.parent.resize(L); hm.jtype.resize(L); hm.qidx.resize(L); hm.pose.resize(L);
+    hm.axis.assign(3 * (size_t)L, 0.0); hm.defang.resize(L);
+    for (int l = 0; l < L; ++l) {
+        const int p = d->parent_link[l];
+        if (p == 0 || p < -1 || p > L) return fail(KIN_ERR_INVALID_ARGUMENT, "parent_link must be a 1-based id or -1");
+        hm.parent[l] = p < 0 ? -1 : p - 1;
+        hm.jtype[l] = d->joint_type[l];
+        hm.qidx[l] = d->q_index[l];
+        hm.pose[l] = p < 0 ? kin::Xf::identity() : kin::Xf::from_colmajor16(d->joint_pose + 16 * (size_t)l);
+        for (int k = 0; k < 3; ++k) hm.axis[3 * l + k] = d->joint_axis[3 * l + k];
+        hm.defang[l] = d->default_angle[l];
+    }
+    std::string err;
+    if (!hm.finalize(err)) return fail(KIN_ERR_INVALID_ARGUMENT, err);
+    int rc = load_spheres(hm, d->n_spheres, d->sphere_link, d->sphere_center, d->sphere_radius);
+    if (rc == KIN_OK) rc = load_boxes(hm, d->n_boxes, d->box_pose, d->box_width);
+    return rc;
+}
+
+template <typename real, bool AOS>
+int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
+    auto kernel = kin::kin_eval_kernel<real, AOS>;
+    int dev_smem = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
+    const kin::ProgHeader &h = dp->prog.h;
+    const size_t tab = sizeof(int32_t) * (size_t)h.n_int + sizeof(real) * (size_t)h.n_real;
+    int best_block = 0, best_occ = 0;
+    size_t best_smem = 0;
+    const int cands[4] = {128, 96, 64, 32};
+    for (int c = 0; c < 4; ++c) {
+        const int b = cands[c];
+        const size_t smem = tab + sizeof(real) * (size_t)h.n_slots * b;
+        if (smem > (size_t)dev_smem) continue;
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, b, smem));
+        if (occ * b > best_occ * best_block) { best_block = b; best_occ = occ; best_smem = smem; }
+    }
+    if (best_block == 0) return fail(KIN_ERR_LIMIT, "model does not fit the shared-memory scratch of one CTA");
+    dp->block[pi][li] = best_block; dp->occ[pi][li] = best_occ; dp->smem[pi][li] = best_smem;
+    dp->regs[pi][li] = fa.numRegs;
+    return KIN_OK;
+}
+
+int get_program(KinModel *m, const KinCall *c, DeviceProgram **out) {
+    const bool want_coll = c->vals_out != nullptr;
+    const bool want_stale = want_coll && c->grads_out && c->scratch_mode == KIN_SCRATCH_REFERENCE;
+    const int n_fk = c->T_out ? c->n_fk_links : 0, n_jac = c->J_out ? c->n_jac_links : 0;
+    std::vector<int> key;
+    key.reserve(n_fk + n_jac + 4);
+    key.push_back(want_coll ? (want_stale ? 2 : 1) : 0);
+    key.push_back(n_fk);
+    for (int i = 0; i < n_fk; ++i) key.push_back(c->fk_links[i]);
+    for (int i = 0; i < n_jac; ++i) key.push_back(c->jac_links[i]);
+    std::lock_guard<std::mutex> lock(m->mu);
+    auto it = m->cache.find(key);
+    if (it == m->cache.end()) {
+        std::vector<int> fk(n_fk), jac(n_jac);
+        for (int i = 0; i < n_fk; ++i) {
+            if (c->fk_links[i] < 1 || c->fk_links[i] > m->hm.n_links) return fail(KIN_ERR_INVALID_ARGUMENT, "fk link id out of range");
+            fk[i] = c->fk_links[i] - 1;
+        }
+        for (int i = 0; i < n_jac; ++i) {
+            if (c->jac_links[i] < 1 || c->jac_links[i] > m->hm.n_links) return fail(KIN_ERR_INVALID_ARGUMENT, "jacobian link id out of range");
+            jac[i] = c->jac_links[i] - 1;
+        }
+        DeviceProgram *dp = new DeviceProgram();
+        std::string err;
+        if (!kin::compile_program(m->hm, fk, jac, want_coll, want_stale, dp->prog, err)) {
+            delete dp;
+            return fail(KIN_ERR_INVALID_ARGUMENT, err);
+        }
+        const kin::Program &p = dp->prog;
+        std::vector<float> r32(p.reals.begin(), p.reals.end());
+        cudaError_t e;
+        if ((e = cudaMalloc(&dp->d_int, sizeof(int32_t) * p.ints.size())) != cudaSuccess ||
+            (e = cudaMalloc(&dp->d_r64, sizeof(double) * p.reals.size())) != cudaSuccess ||
+            (e = cudaMalloc(&dp->d_r32, sizeof(float) * r32.size())) != cudaSuccess ||
+            (e = cudaMemcpy(dp->d_int, p.ints.data(), sizeof(int32_t) * p.ints.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(dp->d_r64, p.reals.data(), sizeof(double) * p.reals.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(dp->d_r32, r32.data(), sizeof(float) * r32.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            free_program(dp);
+            return fail_cuda(e, "uploading the kinematic program");
+        }
+        it = m->cache.emplace(key, dp).first;
+    }
+    DeviceProgram *dp = it->second;
+    const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout == KIN_LAYOUT_AOS ? 1 : 0;
+    if (dp->block[pi][li] == 0) {
+        int rc;
+        if (pi == 0) rc = li ? configure<double, true>(m, dp, pi, li) : configure<double, false>(m, dp, pi, li);
+        else rc = li ? configure<float, true>(m, dp, pi, li) : configure<float, false>(m, dp, pi, li);
+        if (rc != KIN_OK) return rc;
+    }
+    *out = dp;
+    return KIN_OK;
+}
+
+int validate_call(const KinModel *m, const KinCall *c) {
+    if (!m || !c) return fail(KIN_ERR_INVALID_ARGUMENT, "null model or call");
+    if (c->precision != KIN_F64 && c->precision != KIN_F32) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown precision");
+    if (c->layout != KIN_LAYOUT_SOA && c->layout != KIN_LAYOUT_AOS) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown layout");
+    if (c->n < 0) return fail(KIN_ERR_INVALID_ARGUMENT, "negative batch size");
+    if (c->n > 0 && !c->q) return fail(KIN_ERR_INVALID_ARGUMENT, "q is null");
+    if (c->batch_stride != 0 && c->batch_stride < c->n) return fail(KIN_ERR_INVALID_ARGUMENT, "batch_stride < n");
+    if (c->T_out && (c->n_fk_links <= 0 || !c->fk_links)) return fail(KIN_ERR_INVALID_ARGUMENT, "T_out without fk_links");
+    if (c->J_out && (c->n_jac_links <= 0 || !c->jac_links)) return fail(KIN_ERR_INVALID_ARGUMENT, "J_out without jac_links");
+    if (c->n_fk_links > KIN_MAX_LINKS || c->n_jac_links > KIN_MAX_LINKS) return fail(KIN_ERR_LIMIT, "too many requested links");
+    if ((c->grads_out || c->argmin_out) && !c->vals_out) return fail(KIN_ERR_INVALID_ARGUMENT, "grads_out/argmin_out need vals_out");
+    if (c->vals_out && m->hm.n_sph == 0) return fail(KIN_ERR_INVALID_ARGUMENT, "collision requested but the model has no spheres");
+    if (c->vals_out && m->hm.n_box == 0) return fail(KIN_ERR_INVALID_ARGUMENT, "collision requested but the model has no boxes");
+    if (c->grad_mode != KIN_GRAD_FD && c->grad_mode != KIN_GRAD_ANALYTIC) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown grad_mode");
+    if (c->scratch_mode != KIN_SCRATCH_REFERENCE && c->scratch_mode != KIN_SCRATCH_CLEAN) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown scratch_mode");
+    if (std::isnan(c->truncation_dist)) return fail(KIN_ERR_INVALID_ARGUMENT, "truncation_dist is NaN");
+    return KIN_OK;
+}
+
+int launch(KinModel *m, const KinCall *c, DeviceProgram *dp, cudaStream_t stream) {
+    const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout == KIN_LAYOUT_AOS ? 1 : 0;
+    kin::KernelArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.h = dp->prog.h;
+    a.tab_i = dp->d_int;
+    a.tab_r = pi ? (const void *)dp->d_r32 : (const void *)dp->d_r64;
+    a.q = c->q;
+    a.T_out = c->T_out; a.J_out = c->J_out; a.vals_out = c->vals_out; a.grads_out = c->grads_out;
+    a.argmin_out = c->argmin_out;
+    a.n = c->n; a.ld = c->batch_stride ? c->batch_stride : c->n;
+    a.with_rot = c->with_rot ? 1 : 0; a.rpy_jac = c->rpy_jac ? 1 : 0; a.keep_irrelevant = c->keep_irrelevant ? 1 : 0;
+    a.grad_mode = c->grad_mode; a.scratch_ref = c->scratch_mode == KIN_SCRATCH_REFERENCE;
+    a.truncation_dist = c->truncation_dist; a.vals_offset = c->vals_offset;
+    const int block = dp->block[pi][li];
+    const long long tiles = (c->n + block - 1) / block;
+    long long grid = (long long)dp->occ[pi][li] * m->n_sm;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) return KIN_OK;
+    const size_t smem = dp->smem[pi][li];
+    if (pi == 0) {
+        if (li) kin::kin_eval_kernel<double, true><<<(unsigned)grid, block, smem, stream>>>(a);
+        else kin::kin_eval_kernel<double, false><<<(unsigned)grid, block, smem, stream>>>(a);
+    } else {
+        if (li) kin::kin_eval_kernel<float, true><<<(unsigned)grid, block, smem, stream>>>(a);
+        else kin::kin_eval_kernel<float, false><<<(unsigned)grid, block, smem, stream>>>(a);
+    }
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return KIN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *kin_last_error(void) { return g_err.c_str(); }
+int kin_abi_version(void) { return KIN_B200_ABI_VERSION; }
+int64_t kin_launch_count(void) { return g_launches.load(); }
+
+int kin_model_create(const KinModelDesc *d, KinModel **out) {
+    if (!d || !out) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(KIN_ERR_NO_DEVICE, "no CUDA device: libkin_b200 has no CPU fallback");
+    }
+    KinModel *m = new KinModel();
+    int rc = host_model_from_desc(d, m->hm);
+    if (rc != KIN_OK) { delete m; return rc; }
+    cudaError_t e = cudaGetDevice(&m->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, m->device);
+    if (e != cudaSuccess) { delete m; return fail_cuda(e, "querying the device"); }
+    *out = m;
+    return KIN_OK;
+}
+
+// Host-only: compile the program a call would run and hand the tables back (no device needed).
+// Used by the CPU test-suite to check the flattener against the oracle.
+int kin_program_dump(const KinModelDesc *d, const int32_t *fk_links, int32_t n_fk, const int32_t *jac_links,
+                     int32_t n_jac, int32_t want_coll, int32_t want_stale, int32_t *header_out, int32_t header_cap,
+                     int32_t *ints_out, int32_t ints_cap, double *reals_out, int32_t reals_cap) {
+    if (!d) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
+    kin::HostModel hm;
+    int rc = host_model_from_desc(d, hm);
+    if (rc != KIN_OK) return rc;
+    std::vector<int> fk(n_fk), jac(n_jac);
+    for (int i = 0; i < n_fk; ++i) fk[i] = fk_links[i] - 1;
+    for (int i = 0; i < n_jac; ++i) jac[i] = jac_links[i] - 1;
+    kin::Program p;
+    std::string err;
+    if (!kin::compile_program(hm, fk, jac, want_coll != 0, want_stale != 0, p, err)) return fail(KIN_ERR_INVALID_ARGUMENT, err);
+    const int hn = (int)(sizeof(kin::ProgHeader) / sizeof(int32_t));
+    if (header_cap < hn || ints_cap < (int)p.ints.size() || reals_cap < (int)p.reals.size())
+        return fail(KIN_ERR_LIMIT, "kin_program_dump: output buffers too small");
+    std::memcpy(header_out, &p.h, sizeof(kin::ProgHeader));
+    std::memcpy(ints_out, p.ints.data(), sizeof(int32_t) * p.ints.size());
+    std::memcpy(reals_out, p.reals.data(), sizeof(double) * p.reals.size());
+    return KIN_OK;
+}
+
+int kin_model_destroy(KinModel *m) {
+    if (!m) return KIN_OK;
+    clear_cache(m);
+    for (int i = 0; i < HostStage::kStreams; ++i) {
+        if (m->stage.stream[i]) cudaStreamDestroy(m->stage.stream[i]);
+        if (m->stage.buf[i]) cudaFree(m->stage.buf[i]);
+    }
+    delete m;
+    return KIN_OK;
+}
+
+int kin_model_set_spheres(KinModel *m, int32_t n, const int32_t *link, const double *center, const double *radius) {
+    if (!m) return fail(KIN_ERR_INVALID_ARGUMENT, "null model");
+    std::lock_guard<std::mutex> lock(m->mu);
+    int rc = load_spheres(m->hm, n, link, center, radius);
+    clear_cache(m);
+    return rc;
+}
+
+int kin_model_set_boxes(KinModel *m, int32_t n, const double *pose, const double *width) {
+    if (!m) return fail(KIN_ERR_INVALID_ARGUMENT, "null model");
+    std::lock_guard<std::mutex> lock(m->mu);
+    int rc = load_boxes(m->hm, n, pose, width);
+    clear_cache(m);
+    return rc;
+}
+
+int kin_model_n_dof(const KinModel *m) { return m ? m->hm.n_dof() : 0; }
+int kin_model_n_spheres(const KinModel *m) { return m ? m->hm.n_sph : 0; }
+int kin_model_n_boxes(const KinModel *m) { return m ? m->hm.n_box : 0; }
+
+int kin_eval(KinModel *m, const KinCall *c) {
+    int rc = validate_call(m, c);
+    if (rc != KIN_OK) return rc;
+    if (c->n == 0) return KIN_OK;
+    if (!c->T_out && !c->J_out && !c->vals_out) return KIN_OK;
+    DeviceProgram *dp = nullptr;
+    rc = get_program(m, c, &dp);
+    if (rc != KIN_OK) return rc;
+    return launch(m, c, dp, (cudaStream_t)c->stream);
+}
+
+int kin_query_launch(KinModel *m, const KinCall *c, int32_t *regs, int32_t *smem_bytes, int32_t *block, int32_t *grid) {
+    int rc = validate_call(m, c);
+    if (rc != KIN_OK) return rc;
+    DeviceProgram *dp = nullptr;
+    rc = get_program(m, c, &dp);
+    if (rc != KIN_OK) return rc;
+    const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout == KIN_LAYOUT_AOS ? 1 : 0;
+    const int b = dp->block[pi][li];
+    long long tiles = (c->n + b - 1) / b, g = (long long)dp->occ[pi][li] * m->n_sm;
+    if (g > tiles) g = tiles;
+    if (regs) *regs = dp->regs[pi][li];
+    if (smem_bytes) *smem_bytes = (int32_t)dp->smem[pi][li];
+    if (block) *block = b;
+    if (grid) *grid = (int32_t)g;
+    return KIN_OK;
+}
+
+// Host-buffer variant: chunks of the batch are staged through kStreams device buffers; within a
+// stream the order is H2D(q) -> kernel -> D2H(outputs), and the streams overlap each other.
+int kin_eval_host(KinModel *m, const KinCall *c) {
+    int rc = validate_call(m, c);
+    if (rc != KIN_OK) return rc;
+    if (c->n == 0) return KIN_OK;
+    if (!c->T_out && !c->J_out && !c->vals_out) return KIN_OK;
+    DeviceProgram *dp = nullptr;
+    rc = get_program(m, c, &dp);
+    if (rc != KIN_OK) return rc;
+    const size_t es = c->precision == KIN_F32 ? 4 : 8;
+    const int ND = m->hm.n_dof(), S = m->hm.n_sph;
+    const int rows = c->with_rot ? 6 : 3;
+    // per-configuration element counts of each array
+    const size_t cq = ND, cT = c->T_out ? 12 * (size_t)c->n_fk_links : 0,
+                 cJ = c->J_out ? (size_t)rows * ND * c->n_jac_links : 0, cV = c->vals_out ? S : 0,
+                 cG = c->grads_out ? (size_t)ND * S : 0, cA = c->argmin_out ? S : 0;
+    const size_t per_cfg = es * (cq + cT + cJ + cV + cG) + 4 * cA;
+    long long chunk = 1 << 16;
+    if (chunk > c->n) chunk = c->n;
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t need = align(es * cq * chunk) + align(es * cT * chunk) + align(es * cJ * chunk) +
+                        align(es * cV * chunk) + align(es * cG * chunk) + align(4 * cA * chunk);
+    (void)per_cfg;
+    std::lock_guard<std::mutex> lock(m->mu);   // one host-staged call at a time per model
+    HostStage &st = m->stage;
+    if (st.bytes < need) {
+        for (int i = 0; i < HostStage::kStreams; ++i) {
+            if (st.buf[i]) { cudaFree(st.buf[i]); st.buf[i] = nullptr; }
+            CUDA_TRY(cudaMalloc(&st.buf[i], need));
+        }
+        st.bytes = need;
+    }
+    for (int i = 0; i < HostStage::kStreams; ++i)
+        if (!st.stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&st.stream[i], cudaStreamNonBlocking));
+
+    const long long N = c->n, ldh = c->batch_stride ? c->batch_stride : N;
+    const bool aos = c->layout == KIN_LAYOUT_AOS;
+    int k = 0;
+    for (long long n0 = 0; n0 < N; n0 += chunk, k = (k + 1) % HostStage::kStreams) {
+        const long long mcount = (N - n0 < chunk) ? N - n0 : chunk;
+        cudaStream_t s = st.stream[k];
+        unsigned char *base = (unsigned char *)st.buf[k];
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { void *p = base + off; off += align(bytes); return p; };
+        void *dq = carve(es * cq * chunk), *dT = carve(es * cT * chunk), *dJ = carve(es * cJ * chunk),
+             *dV = carve(es * cV * chunk), *dG = carve(es * cG * chunk), *dA = carve(4 * cA * chunk);
+        // host <-> device copy of one array with `comps` components per configuration
+        auto copy = [&](void *dev, const void *host_c, void *host_m, size_t comps, size_t esz, bool to_dev) -> cudaError_t {
+            if (comps == 0) return cudaSuccess;
+            if (aos) {
+                const size_t bytes = esz * comps * mcount, hoff = esz * comps * n0;
+                return to_dev ? cudaMemcpyAsync(dev, (const unsigned char *)host_c + hoff, bytes, cudaMemcpyHostToDevice, s)
+                              : cudaMemcpyAsync((unsigned char *)host_m + hoff, dev, bytes, cudaMemcpyDeviceToHost, s);
+            }
+            const size_t hoff = esz * n0, width = esz * mcount;
+            return to_dev ? cudaMemcpy2DAsync(dev, esz * mcount, (const unsigned char *)host_c + hoff, esz * ldh, width, comps, cudaMemcpyHostToDevice, s)
+                          : cudaMemcpy2DAsync((unsigned char *)host_m + hoff, esz * ldh, dev, esz * mcount, width, comps, cudaMemcpyDeviceToHost, s);
+        };
+        CUDA_TRY(copy(dq, c->q, nullptr, cq, es, true));
+        KinCall cc = *c;
+        cc.n = mcount; cc.batch_stride = 0; cc.q = dq;
+        cc.T_out = cT ? dT : nullptr; cc.J_out = cJ ? dJ : nullptr; cc.vals_out = cV ? dV : nullptr;
+        cc.grads_out = cG ? dG : nullptr; cc.argmin_out = cA ? (int32_t *)dA : nullptr;
+        rc = launch(m, &cc, dp, s);
+        if (rc != KIN_OK) return rc;
+        CUDA_TRY(copy(dT, nullptr, c->T_out, cT, es, false));
+        CUDA_TRY(copy(dJ, nullptr, c->J_out, cJ, es, false));
+        CUDA_TRY(copy(dV, nullptr, c->vals_out, cV, es, false));
+        CUDA_TRY(copy(dG, nullptr, c->grads_out, cG, es, false));
+        CUDA_TRY(copy(dA, nullptr, c->argmin_out, cA, 4, false));
+    }
+    for (int i = 0; i < HostStage::kStreams; ++i) CUDA_TRY(cudaStreamSynchronize(st.stream[i]));
+    return KIN_OK;
+}
+
+int kin_sdf_points(int32_t n_boxes, const double *box_pose, const double *box_width, int32_t precision, int32_t layout,
+                   const void *pts, int64_t n, int32_t grad_mode, void *vals_out, void *grads_out, int32_t *argmin_out,
+                   void *stream_) {
+    if (n < 0 || (n > 0 && (!pts || !vals_out))) return fail(KIN_ERR_INVALID_ARGUMENT, "null points or vals_out");
+    if (n_boxes <= 0) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_sdf_points needs at least one box");
+    if (precision != KIN_F64 && precision != KIN_F32) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown precision");
+    if (layout != KIN_LAYOUT_SOA && layout != KIN_LAYOUT_AOS) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown layout");
+    if (grad_mode != KIN_GRAD_FD && grad_mode != KIN_GRAD_ANALYTIC) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown grad_mode");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(KIN_ERR_NO_DEVICE, "no CUDA device: libkin_b200 has no CPU fallback");
+    }
+    kin::HostModel hm;
+    int rc = load_boxes(hm, n_boxes, box_pose, box_width);
+    if (rc != KIN_OK) return rc;
+    if (n == 0) return KIN_OK;
+    std::vector<double> t64((size_t)n_boxes * kin::BOX_REALS, 0.0);
+    for (int b = 0; b < n_boxes; ++b) {
+        double *br = &t64[(size_t)b * kin::BOX_REALS];
+        std::memcpy(br, hm.box_inv[b].r, sizeof(double) * 9);
+        std::memcpy(br + 9, hm.box_inv[b].p, sizeof(double) * 3);
+        std::memcpy(br + 12, &hm.box_half[3 * b], sizeof(double) * 3);
+    }
+    std::vector<float> t32(t64.begin(), t64.end());
+    const size_t es = precision == KIN_F32 ? 4 : 8, bytes = es * t64.size();
+    cudaStream_t stream = (cudaStream_t)stream_;
+    void *d_tab = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_tab, bytes, stream));
+    // pageable source: the copy is staged before the call returns, so the vectors may go out of scope
+    CUDA_TRY(cudaMemcpyAsync(d_tab, precision == KIN_F32 ? (const void *)t32.data() : (const void *)t64.data(), bytes,
+                             cudaMemcpyHostToDevice, stream));
+    const int block = 256;
+    long long grid = (n + block - 1) / block;
+    if (grid > 148 * 8) grid = 148 * 8;
+    const bool aos = layout == KIN_LAYOUT_AOS;
+    if (precision == KIN_F64) {
+        if (aos) kin::sdf_points_kernel<double, true><<<(unsigned)grid, block, bytes, stream>>>((const double *)d_tab, n_boxes, (const double *)pts, n, grad_mode, (double *)vals_out, (double *)grads_out, argmin_out);
+        else kin::sdf_points_kernel<double, false><<<(unsigned)grid, block, bytes, stream>>>((const double *)d_tab, n_boxes, (const double *)pts, n, grad_mode, (double *)vals_out, (double *)grads_out, argmin_out);
+    } else {
+        if (aos) kin::sdf_points_kernel<float, true><<<(unsigned)grid, block, bytes, stream>>>((const float *)d_tab, n_boxes, (const float *)pts, n, grad_mode, (float *)vals_out, (float *)grads_out, argmin_out);
+        else kin::sdf_points_kernel<float, false><<<(unsigned)grid, block, bytes, stream>>>((const float *)d_tab, n_boxes, (const float *)pts, n, grad_mode, (float *)vals_out, (float *)grads_out, argmin_out);
+    }
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaFreeAsync(d_tab, stream));
+    return KIN_OK;
+}
+
+int kin_fk_links(KinModel *m, int32_t precision, int32_t layout, const void *q, int64_t n, const int32_t *link_ids,
+                 int32_t n_req, void *T_out, void *stream) {
+    KinCall c;
+    std::memset(&c, 0, sizeof c);
+    c.precision = precision; c.layout = layout; c.n = n; c.q = q;
+    c.n_fk_links = n_req; c.fk_links = link_ids; c.T_out = T_out; c.stream = stream;
+    c.truncation_dist = INFINITY;
+    return kin_eval(m, &c);
+}
+
+int kin_fk_jacobian(KinModel *m, int32_t precision, int32_t layout, const void *q, int64_t n, const int32_t *link_ids,
+                    int32_t n_req, int32_t with_rot, int32_t rpy_jac, void *T_out, void *J_out, void *stream) {
+    KinCall c;
+    std::memset(&c, 0, sizeof c);
+    c.precision = precision; c.layout = layout; c.n = n; c.q = q;
+    c.n_fk_links = n_req; c.fk_links = link_ids; c.T_out = T_out;
+    c.n_jac_links = n_req; c.jac_links = link_ids; c.with_rot = with_rot; c.rpy_jac = rpy_jac; c.J_out = J_out;
+    c.stream = stream; c.truncation_dist = INFINITY;
+    return kin_eval(m, &c);
+}
+
+int kin_collision(KinModel *m, int32_t precision, int32_t layout, const void *q, int64_t n, double truncation_dist,
+                  int32_t grad_mode, int32_t scratch_mode, void *vals_out, void *grads_out, int32_t *argmin_out,
+                  void *stream) {
+    KinCall c;
+    std::memset(&c, 0, sizeof c);
+    c.precision = precision; c.layout = layout; c.n = n; c.q = q;
+    c.truncation_dist = truncation_dist; c.grad_mode = grad_mode; c.scratch_mode = scratch_mode;
+    c.vals_out = vals_out; c.grads_out = grads_out; c.argmin_out = argmin_out; c.stream = stream;
+    return kin_eval(m, &c);
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+"""Device models: flattens a ``Mechanism`` (+ control joints, frozen joint angles, sphere and box
+tables) into the ``KinModelDesc`` of include/kin_b200.h, keeps the resulting handles cached on the
+mechanism, and issues ``kin_eval`` calls on torch CUDA tensors.  torch is used for device memory and
+streams only."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .mechanism import Mechanism
+
+_MAX_CACHED = 8
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def make_desc(m: Mechanism, ctrl_ids, spheres=None, boxes=None):
+    """Mechanism (+ optional (links, centers, radii) and (poses, widths)) -> (KinModelDesc, keep-alive).
+    Pure host code: also used by the CPU tests through ``kin_program_dump``."""
+    L = len(m.links)
+    parent = np.full(L, -1, dtype=np.int32)
+    jtype = np.zeros(L, dtype=np.int32)
+    pose = np.tile(np.eye(4).reshape(-1), (L, 1))
+    axis = np.zeros((L, 3))
+    qidx = np.full(L, -1, dtype=np.int32)
+    defang = np.zeros(L)
+    col = {jid: c for c, jid in enumerate(ctrl_ids)}
+    for l in m.links:
+        i = l.id - 1
+        if l.plink_id == -1:
+            continue
+        j = m.joints[l.pjoint_id - 1]
+        parent[i] = l.plink_id
+        jtype[i] = j.type
+        pose[i] = j.pose.mat.T.reshape(-1)          # column-major, like Transform.mat in Julia
+        axis[i] = j.axis
+        qidx[i] = col.get(j.id, -1)
+        defang[i] = m.angles[j.id - 1]
+    keep = [parent, jtype, np.ascontiguousarray(pose), np.ascontiguousarray(axis), qidx, defang]
+    d = _lib.KinModelDesc()
+    d.n_links = L
+    d.parent_link, d.joint_type, d.joint_pose = _iptr(parent), _iptr(jtype), _dptr(keep[2])
+    d.joint_axis, d.q_index, d.default_angle = _dptr(keep[3]), _iptr(qidx), _dptr(defang)
+    d.n_joints = len(ctrl_ids)
+    d.with_base = int(m.with_base)
+    d.n_spheres = d.n_boxes = 0
+    if spheres is not None:
+        sl = np.ascontiguousarray(spheres[0], dtype=np.int32)
+        sc = np.ascontiguousarray(spheres[1], dtype=np.float64).reshape(-1, 3)
+        sr = np.ascontiguousarray(spheres[2], dtype=np.float64)
+        keep += [sl, sc, sr]
+        d.n_spheres, d.sphere_link, d.sphere_center, d.sphere_radius = len(sl), _iptr(sl), _dptr(sc), _dptr(sr)
+    if boxes is not None:
+        bp = np.ascontiguousarray(np.asarray(boxes[0], dtype=np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)).reshape(-1, 16)
+        bw = np.ascontiguousarray(boxes[1], dtype=np.float64).reshape(-1, 3)
+        keep += [bp, bw]
+        d.n_boxes, d.box_pose, d.box_width = len(bp), _dptr(bp), _dptr(bw)
+    return d, keep
+
+
+class DeviceModel:
+    """Owns one ``KinModel*``."""
+
+    def __init__(self, m: Mechanism, ctrl_ids):
+        d, self._keep = make_desc(m, ctrl_ids)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().kin_model_create(C.byref(d), C.byref(h)))
+        self.h = h
+        self.n_dof = len(ctrl_ids) + (3 if m.with_base else 0)
+        self.n_links = len(m.links)
+        self._sph_sig = self._box_sig = None
+        self.n_spheres = self.n_boxes = 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().kin_model_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_spheres(self, links, centers, radii):
+        links = np.ascontiguousarray(links, dtype=np.int32)
+        centers = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
+        radii = np.ascontiguousarray(radii, dtype=np.float64)
+        sig = (links.tobytes(), centers.tobytes(), radii.tobytes())
+        if sig != self._sph_sig:
+            _lib.check(_lib.lib().kin_model_set_spheres(self.h, len(links), _iptr(links), _dptr(centers), _dptr(radii)))
+            self._sph_sig, self.n_spheres = sig, len(links)
+
+    def set_boxes(self, poses, widths):
+        poses = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)).reshape(-1, 16)
+        widths = np.ascontiguousarray(widths, dtype=np.float64).reshape(-1, 3)
+        sig = (poses.tobytes(), widths.tobytes())
+        if sig != self._box_sig:
+            _lib.check(_lib.lib().kin_model_set_boxes(self.h, len(poses), _dptr(poses), _dptr(widths)))
+            self._box_sig, self.n_boxes = sig, len(poses)
+
+
+def device_model(m: Mechanism, ctrl_ids=None) -> DeviceModel:
+    """Cached per (structure, control joints, angles of the joints that are not controlled)."""
+    ctrl_ids = tuple(m._ctrl if ctrl_ids is None else ctrl_ids)
+    frozen = m.angles.copy()
+    for jid in ctrl_ids:
+        frozen[jid - 1] = 0.0
+    key = (m._structure_version, ctrl_ids, frozen.tobytes())
+    dm = m._models.get(key)
+    if dm is None:
+        if len(m._models) >= _MAX_CACHED:
+            m._models.pop(next(iter(m._models)))
+        dm = m._models[key] = DeviceModel(m, ctrl_ids)
+    return dm
+
+
+def current_q(m: Mechanism, dtype=None):
+    """The configuration batch as a CUDA tensor + its layout.  Returns (tensor, layout, N)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.KinError("no CUDA device: the kinematics.jl_b200 operators have no CPU fallback")
+    n_dof = len(m._ctrl) + (3 if m.with_base else 0)
+    if m._Q is None:
+        a = [m.angles[jid - 1] for jid in m._ctrl] + (list(m.base_pose) if m.with_base else [])
+        q = torch.tensor([a if a else [0.0]], dtype=dtype or torch.float64, device="cuda")
+        return q, _lib.AOS, 1
+    Q = m._Q
+    if not isinstance(Q, torch.Tensor):
+        Q = torch.as_tensor(np.ascontiguousarray(Q))
+    if not Q.is_cuda:
+        Q = Q.cuda()
+    if dtype is not None and Q.dtype != dtype:
+        Q = Q.to(dtype)
+    if Q.dtype not in (torch.float64, torch.float32):
+        Q = Q.double()
+    N = Q.shape[0]
+    if n_dof == 0:
+        return torch.zeros(1, dtype=Q.dtype, device="cuda"), _lib.AOS, N
+    if Q.is_contiguous():
+        return Q, _lib.AOS, N
+    if Q.t().is_contiguous():
+        return Q, _lib.SOA, N
+    return Q.contiguous(), _lib.AOS, N
+
+
+def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac_links=None, with_rot=True,
+             rpy_jac=False, keep_irrelevant=False, J_into=None, collision=False, with_grads=True,
+             truncation_dist=np.inf, grad_mode=_lib.GRAD_FD, scratch_mode=_lib.SCRATCH_REFERENCE,
+             want_argmin=False, vals_offset=0.0, stream=None):
+    """One ``kin_eval``.  Outputs are allocated in the layout of the call (default: the layout of Q) and
+    returned as batch-first VIEWS: T (N, n_fk, 3, 4), J (N, n_jac, rows, cols), vals (N, S),
+    grads (N, n_dof, S), argmin (N, S)."""
+    import torch
+    layout = q_layout if layout is None else layout
+    if layout != q_layout:                  # one layout per call: bring q to the output layout
+        Q = Q.t().contiguous().t() if layout == _lib.SOA else Q.contiguous()
+    dt = Q.dtype
+    dev = Q.device
+    c = _lib.KinCall()
+    c.precision = _lib.F32 if dt == torch.float32 else _lib.F64
+    c.layout = layout
+    c.n = N
+    c.batch_stride = 0
+    c.q = Q.data_ptr()
+    c.truncation_dist = float(truncation_dist)
+    c.grad_mode, c.scratch_mode = grad_mode, scratch_mode
+    c.vals_offset = float(vals_offset)
+    c.stream = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+    nd = dm.n_dof
+    out = {}
+    keep = []
+
+    def alloc(shape_soa, shape_aos, dtype=dt):
+        return torch.empty(shape_soa if layout == _lib.SOA else shape_aos, dtype=dtype, device=dev)
+
+    if fk_links is not None and len(fk_links):
+        ids = np.ascontiguousarray(fk_links, dtype=np.int32)
+        keep.append(ids)
+        n = len(ids)
+        T = alloc((n, 4, 3, N), (N, n, 4, 3))
+        c.n_fk_links, c.fk_links, c.T_out = n, _iptr(ids), T.data_ptr()
+        out["T"] = T.permute(3, 0, 2, 1) if layout == _lib.SOA else T.permute(0, 1, 3, 2)
+    if jac_links is not None and len(jac_links):
+        ids = np.ascontiguousarray(jac_links, dtype=np.int32)
+        keep.append(ids)
+        n, rows = len(ids), (6 if with_rot else 3)
+        if J_into is not None:
+            J = J_into                       # storage tensor in the call's layout (get_jacobian! semantics)
+        else:
+            J = alloc((n, nd, rows, N), (N, n, nd, rows))
+        c.n_jac_links, c.jac_links, c.J_out = n, _iptr(ids), J.data_ptr()
+        c.with_rot, c.rpy_jac, c.keep_irrelevant = int(with_rot), int(rpy_jac), int(keep_irrelevant)
+        out["J"] = J.permute(3, 0, 2, 1) if layout == _lib.SOA else J.permute(0, 1, 3, 2)
+    if collision:
+        S = dm.n_spheres
+        V = alloc((S, N), (N, S))
+        c.vals_out = V.data_ptr()
+        out["vals"] = V.t() if layout == _lib.SOA else V
+        if with_grads:
+            G = alloc((S, nd, N), (N, S, nd))
+            c.grads_out = G.data_ptr()
+            out["grads"] = G.permute(2, 1, 0) if layout == _lib.SOA else G.permute(0, 2, 1)
+        if want_argmin:
+            Am = alloc((S, N), (N, S), torch.int32)
+            c.argmin_out = Am.data_ptr()
+            out["argmin"] = Am.t() if layout == _lib.SOA else Am
+    _lib.check(_lib.lib().kin_eval(dm.h, C.byref(c)))
+    return out

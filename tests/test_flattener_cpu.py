@@ -1,0 +1,144 @@
+"""CPU: the product's host half (URDF reader -> KinModelDesc -> compiled kinematic program) against
+the oracle.  The program is executed by the numpy interpreter of tests/program_interp.py, which
+mirrors the kernel.  What this pins without a GPU: link/joint id assignment, topological flattening,
+constant folding of fixed chains, relevance masks, sphere pre-composition, box inversion, scratch
+(stale column) ordering."""
+import os
+
+import numpy as np
+import pytest
+
+import kinematics_jl_b200 as K
+from oracle import ref_model as R
+from conftest import DATA, GOLDEN
+import scenes
+from program_interp import dump_program, run_program
+
+
+def test_library_exports_every_declared_symbol():
+    import re
+    hdr = open(os.path.join(os.path.dirname(DATA), "include", "kin_b200.h")).read()
+    declared = set(re.findall(r"KIN_API [^;(]*?\b(kin_\w+)\s*\(", hdr))
+    from kinematics_jl_b200 import lib as L
+    assert declared == set(L.EXPORTS)
+    for name in declared:
+        assert hasattr(L.lib(), name), name
+    assert L.lib().kin_abi_version() == 1
+
+
+def test_no_device_is_a_loud_error():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    m, joints, _ = scenes.product_fetch()
+    K.set_joint_angles(m, joints, np.zeros(8))
+    with pytest.raises(K.KinError):
+        K.get_transform(m, K.find_link(m, "gripper_link"))
+
+
+def test_mechanism_mirror_structure():
+    """test_mechanism.jl:3-29, 54-67 through the product's parse_urdf."""
+    m = K.parse_urdf(os.path.join(DATA, "fetch.urdf"))
+    base = K.find_link(m, "base_link")
+    assert {l.name for l in K.child_links(m, base)} == {"r_wheel_link", "l_wheel_link", "torso_lift_link",
+                                                        "estop_link", "laser_link", "torso_fixed_link"}
+    assert K.isroot(base) and base.pjoint_id == -1
+    sh = K.find_link(m, "shoulder_pan_link")
+    assert K.parent_joint(m, sh).name == "shoulder_pan_joint"
+    assert K.parent_link(m, sh).name == "torso_lift_link"
+    assert [l.name for l in K.child_links(m, sh)] == ["shoulder_lift_link"]
+    assert [j.name for j in K.child_joints(m, sh)] == ["shoulder_lift_joint"]
+    for name in ["r_wheel_link", "l_wheel_link", "r_gripper_finger_link", "l_gripper_finger_link", "bellows_link2",
+                 "estop_link", "laser_link", "torso_fixed_link", "head_camera_rgb_optical_frame",
+                 "head_camera_depth_optical_frame"]:
+        assert K.isleaf(K.find_link(m, name)) and not K.find_link(m, name).cjoint_ids
+    shoulder, wrist = K.find_joint(m, "shoulder_pan_joint"), K.find_link(m, "wrist_roll_link")
+    assert K.is_relevant(m, K.find_joint(m, "torso_lift_joint"), K.find_link(m, "torso_lift_link"))
+    assert K.is_relevant(m, shoulder, wrist) and not K.is_relevant(m, shoulder, base)
+    new = K.add_new_link(m, K.Link("mylink", K.User), wrist, [0, 0, 0])
+    assert K.is_relevant(m, K.find_joint(m, "torso_lift_joint"), new)
+    # the mirror's ids and relevance table equal the oracle's
+    mo = R.parse_urdf(os.path.join(DATA, "fetch.urdf"))
+    R.add_new_link(mo, "mylink", R.find_link(mo, "wrist_roll_link"), [0, 0, 0])
+    assert [l.name for l in m.links] == [l.name for l in mo.links]
+    assert [j.name for j in m.joints] == [j.name for j in mo.joints]
+    tab = m.rptable
+    for j in mo.joints:
+        for l in mo.links:
+            assert tab[j.id - 1, l.id - 1] == R.is_relevant(mo, j, l)
+
+
+@pytest.mark.parametrize("with_base", [False, True])
+def test_program_fk_jacobian_vs_oracle(with_base):
+    m, joints, _ = scenes.product_fetch(with_base)
+    mo, jo, _ = scenes.oracle_fetch(with_base)
+    q = scenes.random_configs(jo, 64, with_base, seed=1, zeros_every=16)
+    link_ids = [l.id for l in m.links]
+    h, ti, tr = dump_program(m, [j.id for j in joints], link_ids, link_ids)
+    T_ref = R.batch_fk(mo, jo, q, mo.links)
+    for rpy_jac in (False, True):
+        out = run_program(h, ti, tr, q, with_rot=True, rpy_jac=rpy_jac)
+        J_ref = R.batch_jacobian(mo, jo, q, mo.links, True, rpy_jac)
+        np.testing.assert_allclose(out["T"], T_ref[:, :, :3, :], rtol=0, atol=2e-14)
+        np.testing.assert_allclose(out["J"], J_ref, rtol=1e-12, atol=1e-12)
+    out3 = run_program(h, ti, tr, q, with_rot=False)
+    np.testing.assert_allclose(out3["J"], R.batch_jacobian(mo, jo, q, mo.links, False), rtol=1e-12, atol=1e-12)
+
+
+def test_program_frozen_nonzero_joints_and_subset_requests():
+    """Un-controlled joints frozen at non-zero angles (head, gripper fingers) fold into constants."""
+    m, joints, _ = scenes.product_fetch(False)
+    mo, jo, _ = scenes.oracle_fetch(False)
+    extra = {"head_pan_joint": 0.4, "head_tilt_joint": -0.3, "l_gripper_finger_joint": 0.02, "bellows_joint": 0.0}
+    for name, a in extra.items():
+        if name in m.jointid_map:
+            K.set_joint_angle(m, K.find_joint(m, name), a)
+            R.set_joint_angles(mo, [R.find_joint(mo, name)], [a])
+    ctrl = joints[1:6]                    # a strict subset, not starting at the torso
+    ctrl_o = jo[1:6]
+    K.set_joint_angle(m, joints[0], 0.2)
+    R.set_joint_angles(mo, [jo[0]], [0.2])
+    q = scenes.random_configs(ctrl_o, 32, False, seed=2)
+    names = ["head_camera_rgb_optical_frame", "l_gripper_finger_link", "gripper_link", "base_link", "elbow_flex_link"]
+    h, ti, tr = dump_program(m, [j.id for j in ctrl], [K.find_link(m, n).id for n in names],
+                             [K.find_link(m, n).id for n in names])
+    out = run_program(h, ti, tr, q, with_rot=True, rpy_jac=True)
+    lo = [R.find_link(mo, n) for n in names]
+    np.testing.assert_allclose(out["T"], R.batch_fk(mo, ctrl_o, q, lo)[:, :, :3, :], rtol=0, atol=2e-14)
+    np.testing.assert_allclose(out["J"], R.batch_jacobian(mo, ctrl_o, q, lo, True, True), rtol=1e-12, atol=1e-12)
+
+
+def test_program_pr2_mini_ground_truth():
+    import json
+    g = json.load(open(os.path.join(DATA, "ground_truth.json")))
+    m = K.parse_urdf(os.path.join(GOLDEN, "pr2_right_arm_mini.urdf"))
+    joints = [K.find_joint(m, n) for n in g["joint_names"]]
+    links = [K.find_link(m, n) for n in g["link_names"]]
+    h, ti, tr = dump_program(m, [j.id for j in joints], [l.id for l in links], [])
+    T = run_program(h, ti, tr, np.array([g["angle_vector"]]))["T"][0]
+    for Tl, pose in zip(T, g["pose_list"]):
+        M = np.eye(4)
+        M[:3] = Tl
+        np.testing.assert_allclose(Tl[:, 3], pose[:3], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(K.rpy(K.Transform(M))[::-1], pose[3:], rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("with_base", [False, True])
+@pytest.mark.parametrize("truncation", [np.inf, 0.08])
+def test_program_collision_vs_oracle(with_base, truncation):
+    m, joints, sscc = scenes.product_fetch(with_base)
+    mo, jo, so = scenes.oracle_fetch(with_base)
+    sdf_o = scenes.oracle_fridge_sdf()
+    boxes = scenes.fridge_boxes_host()
+    q = scenes.random_configs(jo, 96, with_base, seed=3)
+    spheres = (sscc._parents, sscc._centers, sscc.sphere_radii)
+    h, ti, tr = dump_program(m, [j.id for j in joints], [], [], spheres, boxes)
+    for scratch_ref, mode in ((True, R.SCRATCH_REFERENCE), (False, R.SCRATCH_CLEAN)):
+        out = run_program(h, ti, tr, q, truncation=truncation, scratch_ref=scratch_ref)
+        vals, grads, am = R.batch_collision(so, jo, sdf_o, q, truncation, R.GRAD_FD, mode)
+        np.testing.assert_allclose(out["vals"], vals, rtol=1e-12, atol=1e-13)
+        assert np.array_equal(out["argmin"], am)
+        np.testing.assert_allclose(out["grads"], grads.transpose(0, 2, 1), rtol=0, atol=1e-7)
+        if not scratch_ref:        # analytic oracle: the FD gradient is within FD error of it
+            _, ga, _ = R.batch_collision(so, jo, sdf_o, q, truncation, R.GRAD_ANALYTIC, mode)
+            assert np.abs(out["grads"] - ga.transpose(0, 2, 1)).max() < 1e-4

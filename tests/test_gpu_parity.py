@@ -1,0 +1,383 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI of
+libkin_b200.so (ctypes, via the host mirror), against the CPU oracle on the same seeded inputs.
+
+Tolerances: FP64 transforms / Jacobians / distances 1e-12 relative (1e-12 absolute near
+zero); collision gradient 1e-12 vs the analytic oracle in analytic mode and 1e-7 absolute vs the
+forward-difference oracle in FD mode (the reference's FD with eps 1e-7 amplifies 1-ulp differences of
+sin/cos by 1e7); argmin box, truncation pattern and all index orders exact; FP32 mode 1e-5."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import kinematics_jl_b200 as K
+from kinematics_jl_b200 import lib as L
+from kinematics_jl_b200.device import device_model
+from oracle import ref_model as R
+from conftest import DATA, GOLDEN
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-12, 1e-12
+
+
+def dev(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+
+
+def host(t):
+    return t.double().cpu().numpy()
+
+
+def soa(t):
+    """(N, n_dof) tensor whose memory is (n_dof, N): consumed as KIN_LAYOUT_SOA."""
+    return t.t().contiguous().t()
+
+
+# ------------------------------------------------------------------------------------------------
+# FK: data/ground_truth.json through the kernel (test_kinematics.jl:2-39)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("with_base", [False, True])
+def test_fk_ground_truth_through_kernel(with_base):
+    g = json.load(open(os.path.join(DATA, "ground_truth.json")))
+    m = K.parse_urdf(os.path.join(GOLDEN, "pr2_right_arm_mini.urdf"), with_base=with_base)
+    joints = [K.find_joint(m, n) for n in g["joint_names"]]
+    links = [K.find_link(m, n) for n in g["link_names"]]
+    angles = list(g["angle_vector"]) + ([0.3, 0.3, 0.3] if with_base else [])
+    K.set_joint_angles(m, joints, angles)
+    for _ in range(2):
+        for link, pose in zip(links, g["pose_list"]):
+            tf = K.get_transform(m, link)
+            ypr = K.rpy(tf)[::-1]
+            if with_base:
+                from kinematics_jl_b200.transform import rotz
+                np.testing.assert_allclose(K.translation(tf), rotz(0.3) @ pose[:3] + [0.3, 0.3, 0.0], rtol=0, atol=1e-13)
+                np.testing.assert_allclose(ypr, np.array(pose[3:]) + [0.3, 0, 0], rtol=0, atol=1e-13)
+            else:
+                np.testing.assert_allclose(K.translation(tf), pose[:3], rtol=0, atol=1e-13)
+                np.testing.assert_allclose(ypr, pose[3:], rtol=0, atol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------
+# FK + Jacobians, every Fetch link, random in-limit configurations, both layouts
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("with_base", [False, True])
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_fk_and_jacobian_all_links(with_base, layout):
+    m, joints, _ = scenes.product_fetch(with_base)
+    mo, jo, _ = scenes.oracle_fetch(with_base)
+    q = scenes.random_configs(jo, 1000, with_base, seed=11, zeros_every=50)   # ragged: not a multiple of the CTA
+    Q = dev(q)
+    K.set_joint_angles(m, joints, soa(Q) if layout == "soa" else Q)
+    T = host(K.get_transform(m, m.links))
+    np.testing.assert_allclose(T, R.batch_fk(mo, jo, q, mo.links)[:, :, :3, :], rtol=RTOL, atol=ATOL)
+    for with_rot, rpy_jac in ((True, False), (True, True), (False, False)):
+        J = host(K.get_jacobian(m, m.links, joints, with_rot, rpy_jac=rpy_jac))
+        Jr = R.batch_jacobian(mo, jo, q, mo.links, with_rot, rpy_jac)
+        np.testing.assert_allclose(J, Jr, rtol=RTOL, atol=ATOL)
+
+
+def test_fk_single_link_and_empty_batch():
+    m, joints, _ = scenes.product_fetch(False)
+    mo, jo, _ = scenes.oracle_fetch(False)
+    q = scenes.random_configs(jo, 37, False, seed=5)
+    K.set_joint_angles(m, joints, dev(q))
+    g = K.find_link(m, "gripper_link")
+    T = host(K.get_transform(m, g))
+    assert T.shape == (37, 3, 4)
+    np.testing.assert_allclose(T, R.batch_fk(mo, jo, q, [R.find_link(mo, "gripper_link")])[:, 0, :3, :], rtol=RTOL, atol=ATOL)
+    K.set_joint_angles(m, joints, torch.zeros((0, 8), dtype=torch.float64, device="cuda"))
+    assert K.get_transform(m, g).shape == (0, 3, 4)
+
+
+def test_single_configuration_api_matches_reference_style():
+    """The reference's own call pattern (test_kinematics.jl:45-72) on one configuration: Jacobian vs
+    forward differences of get_transform, at the test angles and at zeros."""
+    m, joints, _ = scenes.product_fetch(True)
+    angles1 = np.array([0.2, 0.564, 0.35, -0.74, -0.7, -0.7, -0.17, -0.63, 0.3, 0.3, 0.3])
+    eps = 1e-7
+    for angles in (angles1, angles1 * 0):
+        for link in [K.find_link(m, n) for n in ("gripper_link", "head_tilt_link", "elbow_flex_link", "base_link")]:
+            K.set_joint_angles(m, joints, angles)
+            Ja = K.get_jacobian(m, link, joints, True, rpy_jac=True)
+            p0 = K.get_transform(m, link)
+            Jn = np.zeros((6, 11))
+            for i in range(11):
+                a = angles.copy()
+                a[i] += eps
+                K.set_joint_angles(m, joints, a)
+                p1 = K.get_transform(m, link)
+                Jn[:3, i] = (K.translation(p1) - K.translation(p0)) / eps
+                Jn[3:, i] = (K.rpy(p1) - K.rpy(p0)) / eps
+            np.testing.assert_allclose(Jn[:3], Ja[:3], rtol=0, atol=1e-5)
+            np.testing.assert_allclose(Jn[3:], Ja[3:], rtol=0, atol=1e-5)
+
+
+def test_get_jacobian_inplace_keeps_irrelevant_columns():
+    """get_jacobian! (algorithm.jl:91-96) writes only relevant columns."""
+    m, joints, _ = scenes.product_fetch(False)
+    mo, jo, _ = scenes.oracle_fetch(False)
+    q = scenes.random_configs(jo, 8, False, seed=6)
+    K.set_joint_angles(m, joints, dev(q))
+    link = K.find_link(m, "head_pan_link")      # moved by the torso only
+    store = torch.full((8, 8, 6), 7.0, dtype=torch.float64, device="cuda")   # AoS block (N, cols, rows)
+    K.get_jacobian_(m, link, joints, True, store.permute(0, 2, 1))
+    J = host(store.permute(0, 2, 1))
+    for n in range(8):
+        mat = np.full((6, 8), 7.0, order="F")
+        R.set_joint_angles(mo, jo, q[n])
+        R.get_jacobian_inplace(mo, R.find_link(mo, "head_pan_link"), jo, True, mat)
+        np.testing.assert_allclose(J[n], mat, rtol=RTOL, atol=ATOL)
+    assert np.all(J[:, :, 1:] == 7.0) and np.all(J[:, 3:, 0] == 7.0)   # prismatic: rows 4:6 untouched (:78-81)
+
+
+def test_frozen_joints_and_subset_of_control_joints():
+    m, joints, _ = scenes.product_fetch(False)
+    mo, jo, _ = scenes.oracle_fetch(False)
+    for name, a in {"head_pan_joint": 0.4, "head_tilt_joint": -0.3, "l_gripper_finger_joint": 0.02}.items():
+        K.set_joint_angle(m, K.find_joint(m, name), a)
+        R.set_joint_angles(mo, [R.find_joint(mo, name)], [a])
+    K.set_joint_angle(m, joints[0], 0.2)
+    R.set_joint_angles(mo, [jo[0]], [0.2])
+    ctrl, ctrl_o = joints[1:6], jo[1:6]
+    q = scenes.random_configs(ctrl_o, 64, False, seed=7)
+    K.set_joint_angles(m, ctrl, dev(q))
+    T = host(K.get_transform(m, m.links))
+    np.testing.assert_allclose(T, R.batch_fk(mo, ctrl_o, q, mo.links)[:, :, :3, :], rtol=RTOL, atol=ATOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# SDF at points (test_sdf.jl)
+# ------------------------------------------------------------------------------------------------
+def test_boxsdf_and_unionsdf_kats():
+    from kinematics_jl_b200.transform import rotz
+    pose = K.Transform(np.array([0.5, 0.5, 0.5]), rotz(0.3))
+    box = K.BoxSDF(pose, [1, 1, 1])
+    assert box(pose * [0.5, 0.5, 0.5]) == pytest.approx(0.0, abs=1e-12)      # test_sdf.jl:20-22
+    assert box(pose * [0.0, 0.0, 0.0]) == pytest.approx(-0.5)
+    assert box(pose * [0.0, 0.0, 1.0]) == pytest.approx(0.5)
+    p1, p2 = K.Transform(np.array([0.5, 0.5, 0.0])), K.Transform(np.array([-0.5, -0.5, 0.0]))
+    u = K.UnionSDF([K.BoxSDF(p1, [1, 1, 1]), K.BoxSDF(p2, [1, 1, 1])])
+    assert u(p1 * [0.5, 0.5, 0.5]) == pytest.approx(0.0, abs=1e-12)           # test_sdf.jl:32-35
+    assert u(p2 * [-0.5, -0.5, -0.5]) == pytest.approx(0.0, abs=1e-12)
+    assert u(p1 * [0.5, 0.5, 1.5]) == pytest.approx(1.0)
+    assert u(p1 * [-0.5, -0.5, -1.5]) == pytest.approx(1.0)
+    assert u(np.array([0.0, 0.0, 2.0]), return_argmin=True)[1] == 1           # first minimum (sdf.jl:112)
+
+
+def test_fridge_union_points_vs_oracle():
+    fridge = K.parse_urdf(os.path.join(DATA, "fridge.urdf"), with_base=True)
+    K.set_joint_angles(fridge, [K.find_joint(fridge, "door_joint")], scenes.FRIDGE_STATE)
+    sdf = K.UnionSDF(fridge)
+    so = scenes.oracle_fridge_sdf()
+    poses, widths = sdf.world_boxes()
+    assert len(poses) == 7
+    np.testing.assert_allclose(poses, np.stack(so.poses), rtol=0, atol=1e-15)
+    rng = np.random.default_rng(0)
+    pts = np.array([1.2, 0, 0.75]) + (rng.random((5000, 3)) - 0.5) * 2.25       # the cloud of test_sdf.jl:43-45, shifted with the base
+    vals, am = sdf(dev(pts), return_argmin=True)
+    g_fd = sdf.gradient(dev(pts))
+    g_an = sdf.gradient(dev(pts), grad_mode=K.GRAD_ANALYTIC)
+    v_ref = np.array([so(p) for p in pts])
+    am_ref = np.zeros(len(pts), dtype=np.int32)
+    gf_ref, ga_ref = np.zeros_like(pts), np.zeros_like(pts)
+    for i, p in enumerate(pts):
+        so(p)
+        am_ref[i] = so.argmin
+        gf_ref[i], ga_ref[i] = so.gradient(p), so.gradient(p, analytic=True)
+    np.testing.assert_allclose(host(vals), v_ref, rtol=RTOL, atol=1e-14)
+    assert np.array_equal(am.cpu().numpy(), am_ref)
+    np.testing.assert_allclose(host(g_an), ga_ref, rtol=RTOL, atol=1e-14)
+    np.testing.assert_allclose(host(g_fd), gf_ref, rtol=0, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# collision (test_collision.jl + the 16-sphere / fridge scene)
+# ------------------------------------------------------------------------------------------------
+ANGLES_SOLVED = [0.026928521116837873, 0.2378996102914415, 0.6445784881862138, -0.24833437463054583,
+                 -1.035118222590030, -0.170439396116480, -1.3891477169766988, -0.07058932825801573]
+
+
+@pytest.mark.parametrize("with_base", [False, True])
+def test_collision_reference_test_case(with_base):
+    """test_collision.jl:1-47 on the product: grads vs forward differences of the distances."""
+    m, joints, sscc = scenes.product_fetch(with_base, sphere_links=["wrist_flex_link"])
+    box = K.BoxSDF(K.Transform(np.array([1.0, 0.0, 0.8])), [0.3, 0.3, 0.3])
+    angles = np.array(ANGLES_SOLVED + ([0.0, 0, 0] if with_base else []))
+    K.set_joint_angles(m, joints, angles)
+    _, grads = K.compute_coll_dists_and_grads(sscc, joints, box)
+    d0 = K.compute_coll_dists(sscc, joints, box)
+    eps = 1e-7
+    for i in range(len(joints)):
+        av = angles.copy()
+        av[i] += eps
+        K.set_joint_angles(m, joints, av)
+        d1 = K.compute_coll_dists(sscc, joints, box)
+        np.testing.assert_allclose(grads[i, :], (d1 - d0) / eps, rtol=0, atol=1e-5)
+    K.set_joint_angles(m, joints, angles)
+    assert np.array_equal(K.compute_coll_dists(sscc, joints, box), K.compute_coll_dists_and_grads(sscc, joints, box)[0])
+
+
+def _fridge_scene(with_base):
+    m, joints, sscc = scenes.product_fetch(with_base)
+    mo, jo, so = scenes.oracle_fetch(with_base)
+    fridge = K.parse_urdf(os.path.join(DATA, "fridge.urdf"), with_base=True)
+    K.set_joint_angles(fridge, [K.find_joint(fridge, "door_joint")], scenes.FRIDGE_STATE)
+    return m, joints, sscc, K.UnionSDF(fridge), mo, jo, so, scenes.oracle_fridge_sdf()
+
+
+@pytest.mark.parametrize("with_base", [False, True])
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+@pytest.mark.parametrize("truncation", [np.inf, 0.08])
+def test_collision_fridge_vs_oracle(with_base, layout, truncation):
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(with_base)
+    q = scenes.random_configs(jo, 777, with_base, seed=21, zeros_every=100)
+    Q = dev(q)
+    K.set_joint_angles(m, joints, soa(Q) if layout == "soa" else Q)
+    d_only, am0 = K.compute_coll_dists(sscc, joints, sdf, return_argmin=True)
+    v_ref0, _, am_ref = R.batch_collision(so, jo, sdf_o, q, with_grads=False)
+    np.testing.assert_allclose(host(d_only), v_ref0, rtol=RTOL, atol=ATOL)
+    assert np.array_equal(am0.cpu().numpy(), am_ref)
+    for scratch, scratch_o in ((K.SCRATCH_REFERENCE, R.SCRATCH_REFERENCE), (K.SCRATCH_CLEAN, R.SCRATCH_CLEAN)):
+        for gm, gm_o, tol in ((K.GRAD_FD, R.GRAD_FD, 1e-7), (K.GRAD_ANALYTIC, R.GRAD_ANALYTIC, 1e-12)):
+            vals, grads, am = K.compute_coll_dists_and_grads(sscc, joints, sdf, truncation_dist=truncation, grad_mode=gm,
+                                                             scratch_mode=scratch, return_argmin=True)
+            v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, q, truncation, gm_o, scratch_o)
+            np.testing.assert_allclose(host(vals), v_ref, rtol=RTOL, atol=ATOL)
+            assert np.array_equal(am.cpu().numpy(), am_ref)
+            assert np.array_equal(host(vals) == truncation, v_ref == truncation)          # truncation pattern exact
+            np.testing.assert_allclose(host(grads), g_ref.transpose(0, 2, 1), rtol=tol if tol < 1e-9 else 0, atol=tol)
+
+
+def test_stale_scratch_differs_from_clean_as_in_the_reference():
+    m, joints, sscc, sdf, *_ = _fridge_scene(False)
+    K.set_joint_angles(m, joints, np.array(ANGLES_SOLVED))
+    _, g_ref = K.compute_coll_dists_and_grads(sscc, joints, sdf, scratch_mode=K.SCRATCH_REFERENCE)
+    _, g_clean = K.compute_coll_dists_and_grads(sscc, joints, sdf, scratch_mode=K.SCRATCH_CLEAN)
+    assert np.array_equal(g_ref[:, :4], g_clean[:, :4])
+    assert np.all(g_clean[1:, 4:8] == 0.0) and np.any(g_ref[1:7, 4:8] != 0.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# FP32 mode (1e-5)
+# ------------------------------------------------------------------------------------------------
+def test_fp32_mode():
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
+    q = scenes.random_configs(jo, 512, False, seed=31)
+    K.set_joint_angles(m, joints, dev(q, torch.float32))
+    T = K.get_transform(m, m.links)
+    assert T.dtype == torch.float32
+    np.testing.assert_allclose(host(T), R.batch_fk(mo, jo, q, mo.links[:25] + mo.links[25:])[:, :, :3, :], rtol=0, atol=1e-5)
+    J = K.get_jacobian(m, K.find_link(m, "gripper_link"), joints, True)
+    np.testing.assert_allclose(host(J), R.batch_jacobian(mo, jo, q, [R.find_link(mo, "gripper_link")], True)[:, 0], rtol=0, atol=1e-5)
+    vals, grads = K.compute_coll_dists_and_grads(sscc, joints, sdf, grad_mode=K.GRAD_ANALYTIC, scratch_mode=K.SCRATCH_CLEAN)
+    v_ref, g_ref, _ = R.batch_collision(so, jo, sdf_o, q, np.inf, R.GRAD_ANALYTIC, R.SCRATCH_CLEAN)
+    np.testing.assert_allclose(host(vals), v_ref, rtol=0, atol=1e-5)
+    # a box-face switch within float rounding flips the analytic gradient: compare where the argmin agrees
+    ok = np.abs(host(grads) - g_ref.transpose(0, 2, 1)).max(axis=1) < 1e-4
+    assert ok.mean() > 0.995
+
+
+# ------------------------------------------------------------------------------------------------
+# the fused call + the host-buffer entry point, straight through the C ABI
+# ------------------------------------------------------------------------------------------------
+def _fused_call(dm, n, qptr, layout, fk, jac, T, J, V, G, A):
+    c = L.KinCall()
+    c.precision, c.layout, c.n, c.q = L.F64, layout, n, qptr
+    c.n_fk_links, c.fk_links, c.T_out = len(fk), fk.ctypes.data_as(C.POINTER(C.c_int32)), T
+    c.n_jac_links, c.jac_links, c.J_out = len(jac), jac.ctypes.data_as(C.POINTER(C.c_int32)), J
+    c.with_rot = 1
+    c.truncation_dist = float("inf")
+    c.vals_out, c.grads_out, c.argmin_out = V, G, A
+    return c
+
+
+@pytest.mark.parametrize("layout", [L.AOS, L.SOA])
+def test_fused_device_and_host_entry_points(layout):
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
+    N = 70000                                   # > one staging chunk (65536) of kin_eval_host
+    q = scenes.random_configs(jo, N, False, seed=41)
+    K.set_joint_angles(m, joints, dev(q[:1]))
+    K.compute_coll_dists(sscc, joints, sdf)     # uploads the sphere / box tables into the device model
+    dm = device_model(m)
+    fk = np.arange(1, 26, dtype=np.int32)
+    jac = np.array([K.find_link(m, "gripper_link").id], dtype=np.int32)
+    nl, S, nd = 25, 16, 8
+    qh = np.ascontiguousarray(q if layout == L.AOS else q.T)
+    shapes = {"T": nl * 12, "J": 6 * nd, "V": S, "G": nd * S}
+    outs_h = {k: np.zeros((N, c) if layout == L.AOS else (c, N)) for k, c in shapes.items()}
+    am_h = np.zeros((N, S) if layout == L.AOS else (S, N), dtype=np.int32)
+    c = _fused_call(dm, N, qh.ctypes.data, layout, fk, jac, outs_h["T"].ctypes.data, outs_h["J"].ctypes.data,
+                    outs_h["V"].ctypes.data, outs_h["G"].ctypes.data, am_h.ctypes.data)
+    L.check(L.lib().kin_eval_host(dm.h, C.byref(c)))
+    qd = dev(qh)
+    outs_d = {k: torch.zeros(v.shape, dtype=torch.float64, device="cuda") for k, v in outs_h.items()}
+    am_d = torch.zeros(am_h.shape, dtype=torch.int32, device="cuda")
+    c = _fused_call(dm, N, qd.data_ptr(), layout, fk, jac, outs_d["T"].data_ptr(), outs_d["J"].data_ptr(),
+                    outs_d["V"].data_ptr(), outs_d["G"].data_ptr(), am_d.data_ptr())
+    c.stream = torch.cuda.current_stream().cuda_stream
+    L.check(L.lib().kin_eval(dm.h, C.byref(c)))
+    torch.cuda.synchronize()
+    for k in outs_h:
+        assert np.array_equal(outs_h[k], outs_d[k].cpu().numpy()), k      # same kernel, same bits
+    assert np.array_equal(am_h, am_d.cpu().numpy())
+    rec = (lambda a: a) if layout == L.AOS else (lambda a: a.T)
+    sub = slice(0, 2000)
+    T = rec(outs_h["T"])[sub].reshape(-1, nl, 4, 3).transpose(0, 1, 3, 2)
+    np.testing.assert_allclose(T, R.batch_fk(mo, jo, q[sub], mo.links[:25])[:, :, :3, :], rtol=RTOL, atol=ATOL)
+    J = rec(outs_h["J"])[sub].reshape(-1, nd, 6).transpose(0, 2, 1)
+    np.testing.assert_allclose(J, R.batch_jacobian(mo, jo, q[sub], [R.find_link(mo, "gripper_link")], True)[:, 0], rtol=RTOL, atol=ATOL)
+    v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, q[sub])
+    np.testing.assert_allclose(rec(outs_h["V"])[sub], v_ref, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(rec(outs_h["G"])[sub].reshape(-1, S, nd), g_ref, rtol=0, atol=1e-7)
+    assert np.array_equal(rec(am_h)[sub], am_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json full size (2^24 configurations): size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties():
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
+    N = 1 << 24
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lo = torch.tensor([j.lower_limit if np.isfinite(j.lower_limit) else -np.pi for j in joints], device="cuda", dtype=torch.float64)
+    hi = torch.tensor([j.upper_limit if np.isfinite(j.upper_limit) else np.pi for j in joints], device="cuda", dtype=torch.float64)
+    Qs = (lo[:, None] + (hi - lo)[:, None] * torch.rand((8, N), generator=g, device="cuda", dtype=torch.float64))
+    K.set_joint_angles(m, joints, Qs.t())                       # SoA
+    gl = K.find_link(m, "gripper_link")
+    T = K.get_transform(m, m.links[:25])                        # (N, 25, 3, 4) view
+    Rm = T[..., :3]
+    # every link rotation is orthonormal with det +1
+    err = (Rm.transpose(-1, -2) @ Rm - torch.eye(3, device="cuda", dtype=torch.float64)).abs().amax()
+    assert float(err) < 1e-13
+    assert float((torch.linalg.det(Rm[:, gl.id - 1]) - 1).abs().max()) < 1e-13
+    # geometric Jacobian of the gripper: column of a revolute joint is orthogonal to its own angular part
+    J = K.get_jacobian(m, gl, joints, True)                     # (N, 6, 8)
+    dots = (J[:, :3, 1:] * J[:, 3:, 1:]).sum(1).abs().amax()
+    assert float(dots) < 1e-13
+    assert float((J[:, 3:, 1:].norm(dim=1) - 1).abs().max()) < 1e-13       # unit axes
+    assert float(J[:, 3:, 0].abs().max()) == 0.0 and float((J[:, :3, 0].norm(dim=1) - 1).abs().max()) < 1e-13
+    # reach bound: the gripper never leaves the sphere of the summed link lengths
+    assert float(T[:, gl.id - 1, :, 3].norm(dim=1).max()) < 2.0
+    del T, Rm, J
+    # collision: distances bounded by the workspace, argmin in range, first / last chunks equal the oracle
+    vals, grads, am = K.compute_coll_dists_and_grads(sscc, joints, sdf, return_argmin=True)
+    assert int(am.min()) >= 1 and int(am.max()) <= 7
+    assert bool(torch.isfinite(vals).all()) and bool(torch.isfinite(grads).all())
+    for sl in (slice(0, 512), slice(N - 512, N)):
+        qs = Qs[:, sl].t().contiguous().cpu().numpy()
+        v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, qs)
+        np.testing.assert_allclose(host(vals[sl]), v_ref, rtol=RTOL, atol=ATOL)
+        assert np.array_equal(am[sl].cpu().numpy(), am_ref)
+        np.testing.assert_allclose(host(grads[sl]), g_ref.transpose(0, 2, 1), rtol=0, atol=1e-7)
+    # checksum of checksums: AoS and SoA runs of the same kernel agree bit for bit
+    sub = Qs[:, : 1 << 20]
+    K.set_joint_angles(m, joints, sub.t())
+    v_soa = K.compute_coll_dists(sscc, joints, sdf)
+    K.set_joint_angles(m, joints, sub.t().contiguous())
+    v_aos = K.compute_coll_dists(sscc, joints, sdf)
+    assert torch.equal(v_soa, v_aos)

@@ -41,6 +41,7 @@ struct DeviceProgram {
     float *d_r32 = nullptr;
     // launch configuration per (precision, layout)
     int block[2][2] = {{0, 0}, {0, 0}}, occ[2][2] = {{0, 0}, {0, 0}}, regs[2][2] = {{0, 0}, {0, 0}};
+    int bs_index[2][2] = {{0, 0}, {0, 0}};
     size_t smem[2][2] = {{0, 0}, {0, 0}};
 };
 
@@ -132,29 +133,41 @@ int host_model_from_desc(const KinModelDesc *d, kin::HostModel &hm) {
     return rc;
 }
 
-template <typename real, bool AOS>
+using KernelFn = void (*)(const kin::KernelArgs);
+constexpr int kNumBS = 4;
+const int kBS[kNumBS] = {128, 96, 64, 32};
+
+// [precision][layout][block size][collision]
+#define KIN_K(real, aos, bs, coll) kin::kin_eval_kernel<real, aos, bs, coll>
+#define KIN_BS_ROW(real, aos) \
+    {{KIN_K(real, aos, 128, false), KIN_K(real, aos, 128, true)}, {KIN_K(real, aos, 96, false), KIN_K(real, aos, 96, true)}, \
+     {KIN_K(real, aos, 64, false), KIN_K(real, aos, 64, true)}, {KIN_K(real, aos, 32, false), KIN_K(real, aos, 32, true)}}
+const KernelFn kKernels[2][2][kNumBS][2] = {{KIN_BS_ROW(double, false), KIN_BS_ROW(double, true)},
+                                            {KIN_BS_ROW(float, false), KIN_BS_ROW(float, true)}};
+
 int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
-    auto kernel = kin::kin_eval_kernel<real, AOS>;
+    const kin::ProgHeader &h = dp->prog.h;
+    const int coll = h.n_sph > 0 ? 1 : 0;
+    const size_t rs = pi ? sizeof(float) : sizeof(double);
+    const size_t tab = sizeof(int32_t) * (size_t)h.n_int + rs * (size_t)h.n_real;
     int dev_smem = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
-    cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, kernel));
-    const kin::ProgHeader &h = dp->prog.h;
-    const size_t tab = sizeof(int32_t) * (size_t)h.n_int + sizeof(real) * (size_t)h.n_real;
-    int best_block = 0, best_occ = 0;
+    int best = -1, best_threads = 0, best_occ = 0;
     size_t best_smem = 0;
-    const int cands[4] = {128, 96, 64, 32};
-    for (int c = 0; c < 4; ++c) {
-        const int b = cands[c];
-        const size_t smem = tab + sizeof(real) * (size_t)h.n_slots * b;
+    for (int bi = 0; bi < kNumBS; ++bi) {
+        const int b = kBS[bi];
+        const size_t smem = tab + rs * (size_t)h.n_slots * b;
         if (smem > (size_t)dev_smem) continue;
+        KernelFn k = kKernels[pi][li][bi][coll];
+        CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
         int occ = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, b, smem));
-        if (occ * b > best_occ * best_block) { best_block = b; best_occ = occ; best_smem = smem; }
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, b, smem));
+        if (occ * b > best_threads) { best = bi; best_threads = occ * b; best_occ = occ; best_smem = smem; }
     }
-    if (best_block == 0) return fail(KIN_ERR_LIMIT, "model does not fit the shared-memory scratch of one CTA");
-    dp->block[pi][li] = best_block; dp->occ[pi][li] = best_occ; dp->smem[pi][li] = best_smem;
+    if (best < 0) return fail(KIN_ERR_LIMIT, "model does not fit the shared-memory scratch of one CTA");
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, kKernels[pi][li][best][coll]));
+    dp->block[pi][li] = kBS[best]; dp->bs_index[pi][li] = best; dp->occ[pi][li] = best_occ; dp->smem[pi][li] = best_smem;
     dp->regs[pi][li] = fa.numRegs;
     return KIN_OK;
 }
@@ -204,9 +217,7 @@ int get_program(KinModel *m, const KinCall *c, DeviceProgram **out) {
     DeviceProgram *dp = it->second;
     const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout == KIN_LAYOUT_AOS ? 1 : 0;
     if (dp->block[pi][li] == 0) {
-        int rc;
-        if (pi == 0) rc = li ? configure<double, true>(m, dp, pi, li) : configure<double, false>(m, dp, pi, li);
-        else rc = li ? configure<float, true>(m, dp, pi, li) : configure<float, false>(m, dp, pi, li);
+        int rc = configure(m, dp, pi, li);
         if (rc != KIN_OK) return rc;
     }
     *out = dp;
@@ -252,13 +263,8 @@ int launch(KinModel *m, const KinCall *c, DeviceProgram *dp, cudaStream_t stream
     if (grid > tiles) grid = tiles;
     if (grid < 1) return KIN_OK;
     const size_t smem = dp->smem[pi][li];
-    if (pi == 0) {
-        if (li) kin::kin_eval_kernel<double, true><<<(unsigned)grid, block, smem, stream>>>(a);
-        else kin::kin_eval_kernel<double, false><<<(unsigned)grid, block, smem, stream>>>(a);
-    } else {
-        if (li) kin::kin_eval_kernel<float, true><<<(unsigned)grid, block, smem, stream>>>(a);
-        else kin::kin_eval_kernel<float, false><<<(unsigned)grid, block, smem, stream>>>(a);
-    }
+    const int coll = (dp->prog.h.n_sph > 0 && c->vals_out) ? 1 : 0;
+    kKernels[pi][li][dp->bs_index[pi][li]][coll]<<<(unsigned)grid, block, smem, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     return KIN_OK;

@@ -46,10 +46,13 @@ __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x
 __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
 __device__ __forceinline__ double abs_(double x) { return fabs(x); }
 __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
-__device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
-__device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
-__device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+// max(x, 0) without the NaN plumbing of fmax(): clear every bit when the sign bit is set.
+// (fmax/fmin on doubles expand to ~8 instructions each on sm_100a; this is 3 integer ops.)
+__device__ __forceinline__ double relu_(double x) {
+    const int hi = __double2hiint(x), lo = __double2loint(x), m = ~(hi >> 31);
+    return __hiloint2double(hi & m, lo & m);
+}
+__device__ __forceinline__ float relu_(float x) { return fmaxf(x, 0.0f); }
 
 // out = a * b  (a: running transform, b: constant from the table at `c`, R row-major then t)
 template <typename real>
@@ -69,91 +72,142 @@ __device__ __forceinline__ void tf_mul_const(const Tf<real> &a, const real *__re
     }
 }
 
-// Output addressing.  SoA: component-major with leading dimension ld; AoS: record-major.
-template <bool AOS>
-struct OutIdx {
-    long long n, ld; int rec;
-    __device__ __forceinline__ long long operator()(int comp) const {
-        return AOS ? n * rec + comp : (long long)comp * ld + n;
-    }
-};
-
-// BoxSDF call (sdf.jl:67-74) for the box whose table row starts at `b`.
+// One row of the box table in registers.
+template <typename real> struct BoxRow { real r[9], t[3], h[3]; };
 template <typename real>
-__device__ __forceinline__ real box_sdf(const real *__restrict__ b, real px, real py, real pz) {
-    real lx = fma_(b[0], px, fma_(b[1], py, fma_(b[2], pz, b[9])));
-    real ly = fma_(b[3], px, fma_(b[4], py, fma_(b[5], pz, b[10])));
-    real lz = fma_(b[6], px, fma_(b[7], py, fma_(b[8], pz, b[11])));
-    real qx = abs_(lx) - b[12], qy = abs_(ly) - b[13], qz = abs_(lz) - b[14];
-    real mx = max_(qx, real(0)), my = max_(qy, real(0)), mz = max_(qz, real(0));
-    real nrm = sqrt_(fma_(mx, mx, fma_(my, my, mz * mz)));
-    return nrm + min_(max_(max_(qx, qy), qz), real(0));
+__device__ __forceinline__ void load_box(const real *__restrict__ b, BoxRow<real> &o) {
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) o.r[i] = b[i];
+    #pragma unroll
+    for (int i = 0; i < 3; ++i) { o.t[i] = b[9 + i]; o.h[i] = b[12 + i]; }
 }
 
-// closed-form gradient of the same box, world frame (extension; KIN_GRAD_ANALYTIC)
+// BoxSDF call (sdf.jl:67-74) in "key" form.  With q = |inv_pose * p| - w/2 and s = |max(q,0)|^2 the
+// reference value is d = sqrt(s) + min(max(q), 0); exactly one of the two terms is non-zero, so
+//     key = s            if s > 0   (outside: d = sqrt(s) > 0)
+//         = min(max q,0) if s == 0  (inside / on the surface: d = key <= 0)
+// is a monotone function of d (d = key > 0 ? sqrt(key) : key).  The union's argmin (sdf.jl:108-114)
+// is taken on the key with the same first-minimum rule, which needs ONE sqrt per sphere instead of
+// one per box; it can differ from the reference only when two boxes' distances tie within 1 ulp.
 template <typename real>
-__device__ __forceinline__ void box_grad_analytic(const real *__restrict__ b, real px, real py, real pz, real g[3]) {
+__device__ __forceinline__ real box_key(const BoxRow<real> &b, real px, real py, real pz) {
+    const real lx = fma_(b.r[0], px, fma_(b.r[1], py, fma_(b.r[2], pz, b.t[0])));
+    const real ly = fma_(b.r[3], px, fma_(b.r[4], py, fma_(b.r[5], pz, b.t[1])));
+    const real lz = fma_(b.r[6], px, fma_(b.r[7], py, fma_(b.r[8], pz, b.t[2])));
+    const real qx = abs_(lx) - b.h[0], qy = abs_(ly) - b.h[1], qz = abs_(lz) - b.h[2];
+    const real mx = relu_(qx), my = relu_(qy), mz = relu_(qz);
+    const real s = fma_(mx, mx, fma_(my, my, mz * mz));
+    real t = qx > qy ? qx : qy;
+    t = t > qz ? t : qz;
+    const real inside = t < real(0) ? t : real(0);
+    return s > real(0) ? s : inside;
+}
+template <typename real>
+__device__ __forceinline__ real key_to_dist(real key) { return key > real(0) ? sqrt_(key) : key; }
+
+// closed-form gradient of one box, world frame (extension; KIN_GRAD_ANALYTIC)
+template <typename real>
+__device__ __forceinline__ void box_grad_analytic(const BoxRow<real> &b, real px, real py, real pz, real g[3]) {
     real l[3], q[3], m[3], gl[3] = {0, 0, 0};
-    l[0] = fma_(b[0], px, fma_(b[1], py, fma_(b[2], pz, b[9])));
-    l[1] = fma_(b[3], px, fma_(b[4], py, fma_(b[5], pz, b[10])));
-    l[2] = fma_(b[6], px, fma_(b[7], py, fma_(b[8], pz, b[11])));
+    l[0] = fma_(b.r[0], px, fma_(b.r[1], py, fma_(b.r[2], pz, b.t[0])));
+    l[1] = fma_(b.r[3], px, fma_(b.r[4], py, fma_(b.r[5], pz, b.t[1])));
+    l[2] = fma_(b.r[6], px, fma_(b.r[7], py, fma_(b.r[8], pz, b.t[2])));
     #pragma unroll
-    for (int i = 0; i < 3; ++i) { q[i] = abs_(l[i]) - b[12 + i]; m[i] = max_(q[i], real(0)); }
-    real nrm = sqrt_(fma_(m[0], m[0], fma_(m[1], m[1], m[2] * m[2])));
+    for (int i = 0; i < 3; ++i) { q[i] = abs_(l[i]) - b.h[i]; m[i] = relu_(q[i]); }
+    const real nrm = sqrt_(fma_(m[0], m[0], fma_(m[1], m[1], m[2] * m[2])));
     if (nrm > real(0)) {
         #pragma unroll
         for (int i = 0; i < 3; ++i) gl[i] = (m[i] / nrm) * (l[i] < real(0) ? real(-1) : real(1));
     } else {
         int k = 0;
         if (q[1] > q[k]) k = 1;
-        if (q[2] > q[k]) k = 2;
+        if (q[2] > (k == 1 ? q[1] : q[0])) k = 2;
         #pragma unroll
         for (int i = 0; i < 3; ++i) if (i == k) gl[i] = l[i] < real(0) ? real(-1) : real(1);
     }
-    // world = R * g_local, and the table holds inv_R = R' row-major => R[r][c] = b[c*3 + r]
+    // world = R * g_local, and the table holds inv_R = R' row-major => R[r][c] = b.r[c*3 + r]
     #pragma unroll
-    for (int r = 0; r < 3; ++r) g[r] = fma_(b[0 + r], gl[0], fma_(b[3 + r], gl[1], b[6 + r] * gl[2]));
+    for (int r = 0; r < 3; ++r) g[r] = fma_(b.r[0 + r], gl[0], fma_(b.r[3 + r], gl[1], b.r[6 + r] * gl[2]));
 }
 
-template <typename real, bool AOS>
-__global__ void __launch_bounds__(128)
+// gradient!(sdf, p, out) on the argmin box (sdf.jl:34-41, 116-119)
+template <typename real>
+__device__ __forceinline__ void box_gradient(const BoxRow<real> &b, int grad_mode, real px, real py, real pz, real dmin, real g[3]) {
+    if (grad_mode == 0) {
+        // (f(p + eps e_i) - f(p)) / eps with eps = 1e-7; the division is done as a multiplication by 1e7
+        // (differs from x / 1e-7 by at most 1 ulp of the quotient, far below the FD truncation error)
+        const real eps = real(1e-7), ieps = real(1e7);
+        g[0] = (key_to_dist(box_key(b, px + eps, py, pz)) - dmin) * ieps;
+        g[1] = (key_to_dist(box_key(b, px, py + eps, pz)) - dmin) * ieps;
+        g[2] = (key_to_dist(box_key(b, px, py, pz + eps)) - dmin) * ieps;
+    } else {
+        box_grad_analytic(b, px, py, pz, g);
+    }
+}
+
+// Euler-rate coefficients of rpy_derivative! (algorithm.jl:56-63) for the link rotation R (row-major):
+// rows 4:6 of a revolute column are (k[0] x - k[1] y, k[2] x + k[3] y, k[4] x + k[5] y + z).
+// The reference takes sin/cos of -pitch and -yaw after extracting them with atan2 (transform.jl:45-48);
+// sin/cos of an atan2 are ratios of the same matrix entries, so no inverse trigonometry is needed:
+//   yaw   = atan2(R21, R11)                  -> cos = R11 / hypot(R11, R21),  sin = R21 / hypot(R11, R21)
+//   pitch = atan2(-R31, hypot(R32, R33))     -> cos = hypot(R32, R33) / |row 3| ,  sin = -R31 / |row 3|
+template <typename real>
+__device__ __forceinline__ void rpy_rate_coeffs(const Tf<real> &T, real k[6]) {
+    const real hy = sqrt_(fma_(T.r[0], T.r[0], T.r[3] * T.r[3]));
+    const real ihy = real(1) / hy;
+    const real cy = hy > real(0) ? T.r[0] * ihy : real(1);      // atan2(0, 0) = 0
+    const real sy = hy > real(0) ? T.r[3] * ihy : real(0);
+    const real hp = sqrt_(fma_(T.r[7], T.r[7], T.r[8] * T.r[8]));
+    const real in = real(1) / sqrt_(fma_(T.r[6], T.r[6], hp * hp));
+    const real cp = hp * in, sp = -T.r[6] * in;
+    // a2 = -pitch, a3 = -yaw: c2 = cp, s2 = -sp, c3 = cy, s3 = -sy
+    const real ic2 = real(1) / cp;
+    k[0] = cy * ic2; k[1] = -sy * ic2; k[2] = -sy; k[3] = cy; k[4] = cy * sp * ic2; k[5] = sy * sp * ic2;
+}
+
+constexpr int SPH_GROUP = 4;   // spheres evaluated together against each box row (register blocking)
+
+template <typename real, bool AOS, int BS, bool COLL>
+__global__ void __launch_bounds__(BS)
 kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ProgHeader &h = A.h;
     int32_t *ti = reinterpret_cast<int32_t *>(smem_raw);
     real *tr = reinterpret_cast<real *>(smem_raw + sizeof(int32_t) * (size_t)h.n_int);
-    real *scr = tr + h.n_real;                         // [slot][thread]
-    const int tid = threadIdx.x, bs = blockDim.x;
+    const int tid = threadIdx.x;
+    real *scr = tr + h.n_real + tid;                   // [slot][thread]: SCR(slot) = scr[slot * BS]
+    #define SCR(slot) scr[(slot) * BS]
 
     // ---- stage the program tables once per CTA ----
     {
         const int4 *src = reinterpret_cast<const int4 *>(A.tab_i);
         int4 *dst = reinterpret_cast<int4 *>(ti);
-        for (int i = tid; i < h.n_int / 4; i += bs) dst[i] = src[i];
+        for (int i = tid; i < h.n_int / 4; i += BS) dst[i] = src[i];
         const real *rs = reinterpret_cast<const real *>(A.tab_r);
-        for (int i = tid; i < h.n_real; i += bs) tr[i] = rs[i];
+        for (int i = tid; i < h.n_real; i += BS) tr[i] = rs[i];
     }
     __syncthreads();
 
-    const real *q = reinterpret_cast<const real *>(A.q);
-    real *T_out = reinterpret_cast<real *>(A.T_out);
-    real *J_out = reinterpret_cast<real *>(A.J_out);
-    real *V_out = reinterpret_cast<real *>(A.vals_out);
-    real *G_out = reinterpret_cast<real *>(A.grads_out);
-    const int D = h.n_joints, ND = h.n_dof;
+    // The planar base is compiled into three ordinary nodes (prismatic x, y; revolute z), so every one of
+    // the ND columns is an ordinary joint column here; DC = columns that are control joints.
+    const int DC = h.n_joints, ND = h.n_dof;
     const int rows = A.with_rot ? 6 : 3;
-    #define SCR(slot) scr[(slot) * bs + tid]
+    // distance between consecutive components of one configuration's record
+    const size_t es = AOS ? size_t(1) : (size_t)A.ld;
 
-    const long long n_tiles = (A.n + bs - 1) / bs;
+    const long long n_tiles = (A.n + BS - 1) / BS;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long n = tile * bs + tid;
+        const long long n = tile * BS + tid;
         if (n >= A.n) continue;      // no block-level sync below this point
 
         // ---- configuration -> scratch (all loads in flight together) ----
-        for (int c = 0; c < ND; ++c)
-            SCR(h.so_q + c) = AOS ? q[n * ND + c] : q[(long long)c * A.ld + n];
+        {
+            const real *qn = reinterpret_cast<const real *>(A.q) + (AOS ? n * ND : n);
+            for (int c = 0; c < ND; ++c) SCR(h.so_q + c) = qn[c * es];
+        }
+        real *Tn = reinterpret_cast<real *>(A.T_out) + (AOS ? n * (12 * h.n_fk) : n);
+        real *Jn = reinterpret_cast<real *>(A.J_out) + (AOS ? n * (rows * ND * h.n_jac) : n);
 
-        real bx = 0, by = 0;          // planar base position (algorithm.jl:99)
         Tf<real> T;                   // running world transform of the current node
 
         // =========================== phase 1 ===========================
@@ -165,27 +219,21 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 #pragma unroll
                 for (int i = 0; i < 9; ++i) T.r[i] = (i % 4 == 0) ? real(1) : real(0);
                 T.p[0] = T.p[1] = T.p[2] = real(0);
-                if (h.with_base) {   // base_pose_to_transform, transform.jl:33-37
-                    bx = SCR(h.so_q + D); by = SCR(h.so_q + D + 1);
-                    real s, c;
-                    sincos_(SCR(h.so_q + D + 2), &s, &c);
-                    T.r[0] = c; T.r[1] = -s; T.r[3] = s; T.r[4] = c;
-                    T.p[0] = bx; T.p[1] = by;
-                }
             } else {
                 const int psrc = ni[0], flags = ni[2], qcol = ni[3];
                 if (psrc >= 0) {
+                    const real *sv = &SCR(h.so_save + 12 * psrc);
                     #pragma unroll
-                    for (int i = 0; i < 9; ++i) T.r[i] = SCR(h.so_save + 12 * psrc + i);
+                    for (int i = 0; i < 9; ++i) T.r[i] = sv[i * BS];
                     #pragma unroll
-                    for (int i = 0; i < 3; ++i) T.p[i] = SCR(h.so_save + 12 * psrc + 9 + i);
+                    for (int i = 0; i < 3; ++i) T.p[i] = sv[(9 + i) * BS];
                 }
                 // A = T_parent * joint.pose : the joint frame (algorithm.jl:47-48)
                 Tf<real> Aj;
                 tf_mul_const(T, nr, flags & NF_OFF_R_IDENTITY, Aj);
                 const int code = (flags >> NF_AXIS_SHIFT) & NF_AXIS_MASK;
                 real ax, ay, az;          // world joint axis (algorithm.jl:50)
-                real sgn = code >= 4 ? real(-1) : real(1);
+                const real sgn = code >= 4 ? real(-1) : real(1);
                 switch (code) {
                     case 1: case 4: ax = sgn * Aj.r[0]; ay = sgn * Aj.r[3]; az = sgn * Aj.r[6]; break;
                     case 2: case 5: ax = sgn * Aj.r[1]; ay = sgn * Aj.r[4]; az = sgn * Aj.r[7]; break;
@@ -195,9 +243,9 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                         ay = fma_(Aj.r[3], nr[12], fma_(Aj.r[4], nr[13], Aj.r[5] * nr[14]));
                         az = fma_(Aj.r[6], nr[12], fma_(Aj.r[7], nr[13], Aj.r[8] * nr[14]));
                 }
-                const int jf = h.so_jf + 6 * qcol;
-                SCR(jf + 0) = Aj.p[0]; SCR(jf + 1) = Aj.p[1]; SCR(jf + 2) = Aj.p[2];
-                SCR(jf + 3) = ax; SCR(jf + 4) = ay; SCR(jf + 5) = az;
+                real *jf = &SCR(h.so_jf + 6 * qcol);
+                jf[0] = Aj.p[0]; jf[BS] = Aj.p[1]; jf[2 * BS] = Aj.p[2];
+                jf[3 * BS] = ax; jf[4 * BS] = ay; jf[5 * BS] = az;
                 const real qa = SCR(h.so_q + qcol);
                 T = Aj;
                 if (jtype == 2) {          // prismatic: pose * Trans(axis * a), mechanism.jl:100-103
@@ -235,10 +283,11 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 }
             }
             if (ni[4] >= 0) {
+                real *sv = &SCR(h.so_save + 12 * ni[4]);
                 #pragma unroll
-                for (int i = 0; i < 9; ++i) SCR(h.so_save + 12 * ni[4] + i) = T.r[i];
+                for (int i = 0; i < 9; ++i) sv[i * BS] = T.r[i];
                 #pragma unroll
-                for (int i = 0; i < 3; ++i) SCR(h.so_save + 12 * ni[4] + 9 + i) = T.p[i];
+                for (int i = 0; i < 3; ++i) sv[(9 + i) * BS] = T.p[i];
             }
 
             // ---- requested links hanging from this node ----
@@ -247,145 +296,144 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 const real *ar = tr + h.ro_att + a * ATT_REALS;
                 Tf<real> Tl;
                 tf_mul_const(T, ar, ai[1] & AF_R_IDENTITY, Tl);
-                if (ai[0] >= 0 && T_out) {       // get_transform, as 3x4 column-major
-                    OutIdx<AOS> o{n, A.ld, 12 * h.n_fk};
-                    const int base = 12 * ai[0];
+                if (ai[0] >= 0 && A.T_out) {       // get_transform, as 3x4 column-major
+                    real *o = Tn + (size_t)(12 * ai[0]) * es;
                     #pragma unroll
                     for (int c = 0; c < 3; ++c)
                         #pragma unroll
-                        for (int r = 0; r < 3; ++r) T_out[o(base + c * 3 + r)] = Tl.r[r * 3 + c];
+                        for (int r = 0; r < 3; ++r) o[(c * 3 + r) * es] = Tl.r[r * 3 + c];
                     #pragma unroll
-                    for (int r = 0; r < 3; ++r) T_out[o(base + 9 + r)] = Tl.p[r];
+                    for (int r = 0; r < 3; ++r) o[(9 + r) * es] = Tl.p[r];
                 }
-                if (ai[2] >= 0 && J_out) {       // get_jacobian, algorithm.jl:83-114
-                    OutIdx<AOS> o{n, A.ld, rows * ND * h.n_jac};
-                    const int jbase = ai[2] * rows * ND;
+                if (ai[2] >= 0 && A.J_out) {       // get_jacobian, algorithm.jl:83-114
+                    real *o = Jn + (size_t)(ai[2] * rows * ND) * es;
                     const unsigned mask = (unsigned)ai[3];
-                    real k_rx = 0, k_ry = 0, k_px = 0, k_py = 0, k_yx = 0, k_yy = 0;
-                    if (A.with_rot && A.rpy_jac) {
-                        // rpy(T) (transform.jl:45-48, RotZYX) then the Euler-rate map (algorithm.jl:56-63)
-                        const real yaw = atan2_(Tl.r[3], Tl.r[0]);
-                        const real pitch = atan2_(-Tl.r[6], sqrt_(fma_(Tl.r[7], Tl.r[7], Tl.r[8] * Tl.r[8])));
-                        real s2, c2, s3, c3;
-                        sincos_(-pitch, &s2, &c2);
-                        sincos_(-yaw, &s3, &c3);
-                        k_rx = c3 / c2; k_ry = s3 / c2;
-                        k_px = s3; k_py = c3;
-                        k_yx = -c3 * s2 / c2; k_yy = s3 * s2 / c2;
-                    }
-                    for (int j = 0; j < D; ++j) {
-                        const int cb = jbase + j * rows;
+                    real k[6] = {0, 0, 0, 0, 0, 0};
+                    if (A.with_rot && A.rpy_jac) rpy_rate_coeffs(Tl, k);
+                    for (int j = 0; j < ND; ++j, o += rows * es) {
                         if ((mask >> j) & 1u) {
-                            const int jf = h.so_jf + 6 * j;
-                            const real ax = SCR(jf + 3), ay = SCR(jf + 4), az = SCR(jf + 5);
+                            const real *jf = &SCR(h.so_jf + 6 * j);
+                            const real ax = jf[3 * BS], ay = jf[4 * BS], az = jf[5 * BS];
                             if (ti[h.io_col_type + j] == 1) {
-                                const real dx = Tl.p[0] - SCR(jf + 0), dy = Tl.p[1] - SCR(jf + 1), dz = Tl.p[2] - SCR(jf + 2);
-                                J_out[o(cb + 0)] = fma_(ay, dz, -(az * dy));
-                                J_out[o(cb + 1)] = fma_(az, dx, -(ax * dz));
-                                J_out[o(cb + 2)] = fma_(ax, dy, -(ay * dx));
+                                const real dx = Tl.p[0] - jf[0], dy = Tl.p[1] - jf[BS], dz = Tl.p[2] - jf[2 * BS];
+                                o[0] = fma_(ay, dz, -(az * dy));
+                                o[es] = fma_(az, dx, -(ax * dz));
+                                o[2 * es] = fma_(ax, dy, -(ay * dx));
                                 if (A.with_rot) {
                                     if (A.rpy_jac) {
-                                        J_out[o(cb + 3)] = k_rx * ax - k_ry * ay;
-                                        J_out[o(cb + 4)] = fma_(k_px, ax, k_py * ay);
-                                        J_out[o(cb + 5)] = fma_(k_yx, ax, k_yy * ay) + az;
+                                        o[3 * es] = k[0] * ax - k[1] * ay;
+                                        o[4 * es] = fma_(k[2], ax, k[3] * ay);
+                                        o[5 * es] = fma_(k[4], ax, k[5] * ay) + az;
                                     } else {
-                                        J_out[o(cb + 3)] = ax; J_out[o(cb + 4)] = ay; J_out[o(cb + 5)] = az;
+                                        o[3 * es] = ax; o[4 * es] = ay; o[5 * es] = az;
                                     }
                                 }
-                            } else {   // prismatic: rows 4:6 untouched by the reference (algorithm.jl:78-81)
-                                J_out[o(cb + 0)] = ax; J_out[o(cb + 1)] = ay; J_out[o(cb + 2)] = az;
-                                if (A.with_rot && !A.keep_irrelevant) {
-                                    J_out[o(cb + 3)] = real(0); J_out[o(cb + 4)] = real(0); J_out[o(cb + 5)] = real(0);
-                                }
+                            } else {   // prismatic: rows 4:6 untouched by the reference (algorithm.jl:78-81),
+                                       // except in the base block, which it always writes (algorithm.jl:102-104)
+                                o[0] = ax; o[es] = ay; o[2 * es] = az;
+                                if (A.with_rot && (!A.keep_irrelevant || j >= DC)) { o[3 * es] = real(0); o[4 * es] = real(0); o[5 * es] = real(0); }
                             }
                         } else if (!A.keep_irrelevant) {
-                            for (int r = 0; r < rows; ++r) J_out[o(cb + r)] = real(0);
-                        }
-                    }
-                    if (h.with_base) {   // algorithm.jl:98-105
-                        const real x = Tl.p[0] - bx, y = Tl.p[1] - by;
-                        const int cb = jbase + D * rows;
-                        J_out[o(cb + 0)] = real(1); J_out[o(cb + 1)] = real(0); J_out[o(cb + 2)] = real(0);
-                        J_out[o(cb + rows + 0)] = real(0); J_out[o(cb + rows + 1)] = real(1); J_out[o(cb + rows + 2)] = real(0);
-                        J_out[o(cb + 2 * rows + 0)] = -y; J_out[o(cb + 2 * rows + 1)] = x; J_out[o(cb + 2 * rows + 2)] = real(0);
-                        if (A.with_rot) {
-                            for (int c = 0; c < 3; ++c)
-                                for (int r = 3; r < 6; ++r) J_out[o(cb + c * rows + r)] = (c == 2 && r == 5) ? real(1) : real(0);
+                            for (int r = 0; r < rows; ++r) o[r * es] = real(0);
                         }
                     }
                 }
             }
 
             // ---- collision-sphere centres on this node (collision.jl:54 / :80) ----
-            for (int k = ni[7]; k < ni[8]; ++k) {
-                const int s = ti[h.io_sph_order + k];
-                const real *sr = tr + h.ro_sph + s * SPH_REALS;
-                #pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    SCR(h.so_cent + 3 * s + i) =
-                        fma_(T.r[i * 3 + 0], sr[0], fma_(T.r[i * 3 + 1], sr[1], fma_(T.r[i * 3 + 2], sr[2], T.p[i])));
+            if (COLL) {
+                for (int k = ni[7]; k < ni[8]; ++k) {
+                    const int s = ti[h.io_sph_order + k];
+                    const real *sr = tr + h.ro_sph + s * SPH_REALS;
+                    real *cs = &SCR(h.so_cent + 3 * s);
+                    #pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        cs[i * BS] = fma_(T.r[i * 3 + 0], sr[0], fma_(T.r[i * 3 + 1], sr[1], fma_(T.r[i * 3 + 2], sr[2], T.p[i])));
+                }
             }
         }
 
         // =========================== phase 2 ===========================
-        if (h.n_sph > 0 && V_out) {
-            const bool want_grads = G_out != nullptr;
+        if (COLL) {
+            const int S = h.n_sph;
+            const bool want_grads = A.grads_out != nullptr;
             const bool stale = want_grads && A.scratch_ref;
-            const real trunc = (real)A.truncation_dist;
+            const real trunc = (real)A.truncation_dist, voff = (real)A.vals_offset;
             if (stale)
-                for (int i = 0; i < 3 * D; ++i) SCR(h.so_stale + i) = real(0);   // jac = zeros(3, n_dof), collision.jl:76
-            OutIdx<AOS> ov{n, A.ld, h.n_sph};
-            OutIdx<AOS> og{n, A.ld, ND * h.n_sph};
-            for (int s = 0; s < h.n_sph; ++s) {
-                const real px = SCR(h.so_cent + 3 * s), py = SCR(h.so_cent + 3 * s + 1), pz = SCR(h.so_cent + 3 * s + 2);
-                // UnionSDF: all boxes, first minimum wins (sdf.jl:108-114)
-                real dmin = CUDART_INF;
-                int kmin = 0;
-                for (int b = 0; b < h.n_box; ++b) {
-                    const real d = box_sdf(tr + h.ro_box + b * BOX_REALS, px, py, pz);
-                    if (d < dmin) { dmin = d; kmin = b; }
+                for (int i = 0; i < 3 * ND; ++i) SCR(h.so_stale + i) = real(0);   // jac = zeros(3, n_dof), collision.jl:76
+            real *Vp = reinterpret_cast<real *>(A.vals_out) + (AOS ? n * S : n);
+            real *Gp = reinterpret_cast<real *>(A.grads_out) + (AOS ? n * ((long long)ND * S) : n);
+            int32_t *Ap = A.argmin_out ? A.argmin_out + (AOS ? n * S : n) : nullptr;
+            real *hand = &SCR(h.so_q);      // q is dead: (dmin, argmin) of the current sphere group
+
+            for (int s0 = 0; s0 < S; s0 += SPH_GROUP) {
+                // ---- 2a: distances of SPH_GROUP spheres; one box-table row feeds all of them ----
+                {
+                    real px[SPH_GROUP], py[SPH_GROUP], pz[SPH_GROUP], kmin[SPH_GROUP];
+                    int kidx[SPH_GROUP];
+                    #pragma unroll
+                    for (int g = 0; g < SPH_GROUP; ++g) {
+                        const real *cs = &SCR(h.so_cent + 3 * min(s0 + g, S - 1));
+                        px[g] = cs[0]; py[g] = cs[BS]; pz[g] = cs[2 * BS];
+                        kmin[g] = CUDART_INF; kidx[g] = 0;
+                    }
+                    // UnionSDF: all boxes, first minimum wins (sdf.jl:108-114)
+                    for (int b = 0; b < h.n_box; ++b) {
+                        BoxRow<real> row;
+                        load_box(tr + h.ro_box + b * BOX_REALS, row);
+                        #pragma unroll
+                        for (int g = 0; g < SPH_GROUP; ++g) {
+                            const real key = box_key(row, px[g], py[g], pz[g]);
+                            if (key < kmin[g]) { kmin[g] = key; kidx[g] = b; }
+                        }
+                    }
+                    #pragma unroll
+                    for (int g = 0; g < SPH_GROUP; ++g) {
+                        hand[g * BS] = key_to_dist(kmin[g]);
+                        reinterpret_cast<int *>(&hand[(SPH_GROUP + g) * BS])[0] = kidx[g];
+                    }
                 }
-                const real dist0 = dmin - tr[h.ro_sph + s * SPH_REALS + 3];
-                if (A.argmin_out) A.argmin_out[ov(s)] = kmin + 1;
-                const bool truncated = dist0 > trunc;
-                V_out[ov(s)] = (truncated ? trunc : dist0) - (real)A.vals_offset;
-                if (!want_grads) continue;
-                if (truncated) {            // collision.jl:84-86
-                    for (int j = 0; j < ND; ++j) G_out[og(s * ND + j)] = real(0);
-                    continue;
-                }
-                real g[3];
-                const real *bk = tr + h.ro_box + kmin * BOX_REALS;
-                if (A.grad_mode == 0) {     // forward difference on the argmin box, sdf.jl:34-41
-                    const real eps = real(1e-7);
-                    g[0] = (box_sdf(bk, px + eps, py, pz) - dmin) / eps;
-                    g[1] = (box_sdf(bk, px, py + eps, pz) - dmin) / eps;
-                    g[2] = (box_sdf(bk, px, py, pz + eps) - dmin) / eps;
-                } else {
-                    box_grad_analytic(bk, px, py, pz, g);
-                }
-                const unsigned mask = (unsigned)ti[h.io_sph_mask + s];
-                for (int j = 0; j < D; ++j) {
-                    real cx, cy, cz;
-                    const bool rel = (mask >> j) & 1u;
-                    if (rel) {              // joint_jacobian!, algorithm.jl:65-81
-                        const int jf = h.so_jf + 6 * j;
-                        const real ax = SCR(jf + 3), ay = SCR(jf + 4), az = SCR(jf + 5);
-                        if (ti[h.io_col_type + j] == 1) {
-                            const real dx = px - SCR(jf + 0), dy = py - SCR(jf + 1), dz = pz - SCR(jf + 2);
-                            cx = fma_(ay, dz, -(az * dy)); cy = fma_(az, dx, -(ax * dz)); cz = fma_(ax, dy, -(ay * dx));
-                        } else { cx = ax; cy = ay; cz = az; }
-                        if (stale) { SCR(h.so_stale + 3 * j) = cx; SCR(h.so_stale + 3 * j + 1) = cy; SCR(h.so_stale + 3 * j + 2) = cz; }
-                    } else if (stale) {     // column left over from an earlier sphere (collision.jl:76,90)
-                        cx = SCR(h.so_stale + 3 * j); cy = SCR(h.so_stale + 3 * j + 1); cz = SCR(h.so_stale + 3 * j + 2);
-                    } else { cx = cy = cz = real(0); }
-                    G_out[og(s * ND + j)] = fma_(g[0], cx, fma_(g[1], cy, g[2] * cz));   // transpose(grad) * jac
-                }
-                if (h.with_base) {          // base columns are rewritten for every sphere (algorithm.jl:98-101)
-                    const real x = px - bx, y = py - by;
-                    G_out[og(s * ND + D)] = g[0];
-                    G_out[og(s * ND + D + 1)] = g[1];
-                    G_out[og(s * ND + D + 2)] = fma_(g[1], x, -(g[0] * y));
+                // ---- 2b: per sphere, IN sphere order (the shared scratch of collision.jl:76,90 makes the
+                //      order observable): value, truncation, gradient, chain rule ----
+                #pragma unroll 1
+                for (int g = 0; g < SPH_GROUP && s0 + g < S; ++g) {
+                    const int s = s0 + g;
+                    const real dmin = hand[g * BS];
+                    const int kmin = reinterpret_cast<const int *>(&hand[(SPH_GROUP + g) * BS])[0];
+                    const real dist0 = dmin - tr[h.ro_sph + s * SPH_REALS + 3];
+                    const bool truncated = dist0 > trunc;
+                    Vp[s * es] = (truncated ? trunc : dist0) - voff;
+                    if (Ap) Ap[s * es] = kmin + 1;
+                    if (!want_grads) continue;
+                    if (truncated) {            // collision.jl:84-86
+                        for (int j = 0; j < ND; ++j, Gp += es) *Gp = real(0);
+                        continue;
+                    }
+                    const real *cs = &SCR(h.so_cent + 3 * s);
+                    const real px = cs[0], py = cs[BS], pz = cs[2 * BS];
+                    real grad[3];
+                    {
+                        BoxRow<real> row;
+                        load_box(tr + h.ro_box + kmin * BOX_REALS, row);
+                        box_gradient(row, A.grad_mode, px, py, pz, dmin, grad);
+                    }
+                    const unsigned mask = (unsigned)ti[h.io_sph_mask + s];
+                    for (int j = 0; j < ND; ++j, Gp += es) {
+                        real cx, cy, cz;
+                        if ((mask >> j) & 1u) {   // joint_jacobian!, algorithm.jl:65-81
+                            const real *jf = &SCR(h.so_jf + 6 * j);
+                            const real ax = jf[3 * BS], ay = jf[4 * BS], az = jf[5 * BS];
+                            if (ti[h.io_col_type + j] == 1) {
+                                const real dx = px - jf[0], dy = py - jf[BS], dz = pz - jf[2 * BS];
+                                cx = fma_(ay, dz, -(az * dy)); cy = fma_(az, dx, -(ax * dz)); cz = fma_(ax, dy, -(ay * dx));
+                            } else { cx = ax; cy = ay; cz = az; }
+                            if (stale) { real *st = &SCR(h.so_stale + 3 * j); st[0] = cx; st[BS] = cy; st[2 * BS] = cz; }
+                        } else if (stale) {     // column left over from an earlier sphere (collision.jl:76,90)
+                            const real *st = &SCR(h.so_stale + 3 * j);
+                            cx = st[0]; cy = st[BS]; cz = st[2 * BS];
+                        } else { cx = cy = cz = real(0); }
+                        *Gp = fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz));   // transpose(grad) * jac
+                    }
                 }
             }
         }
@@ -405,25 +453,21 @@ sdf_points_kernel(const real *__restrict__ boxes, int n_box, const real *__restr
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n_pts; n += (long long)gridDim.x * blockDim.x) {
         const real px = AOS ? pts[3 * n] : pts[n], py = AOS ? pts[3 * n + 1] : pts[n_pts + n],
                    pz = AOS ? pts[3 * n + 2] : pts[2 * n_pts + n];
-        real dmin = CUDART_INF;
-        int kmin = 0;
+        real kmin = CUDART_INF;
+        int kidx = 0;
+        BoxRow<real> row;
         for (int b = 0; b < n_box; ++b) {
-            const real d = box_sdf(tb + b * BOX_REALS, px, py, pz);
-            if (d < dmin) { dmin = d; kmin = b; }
+            load_box(tb + b * BOX_REALS, row);
+            const real key = box_key(row, px, py, pz);
+            if (key < kmin) { kmin = key; kidx = b; }
         }
+        const real dmin = key_to_dist(kmin);
         vals[n] = dmin;
-        if (argmin) argmin[n] = kmin + 1;
+        if (argmin) argmin[n] = kidx + 1;
         if (grads) {
             real g[3];
-            const real *bk = tb + kmin * BOX_REALS;
-            if (grad_mode == 0) {
-                const real eps = real(1e-7);
-                g[0] = (box_sdf(bk, px + eps, py, pz) - dmin) / eps;
-                g[1] = (box_sdf(bk, px, py + eps, pz) - dmin) / eps;
-                g[2] = (box_sdf(bk, px, py, pz + eps) - dmin) / eps;
-            } else {
-                box_grad_analytic(bk, px, py, pz, g);
-            }
+            load_box(tb + kidx * BOX_REALS, row);
+            box_gradient(row, grad_mode, px, py, pz, dmin, g);
             #pragma unroll
             for (int i = 0; i < 3; ++i) grads[AOS ? 3 * n + i : (long long)i * n_pts + n] = g[i];
         }

@@ -71,7 +71,7 @@ static Xf frozen_joint_transform(const HostModel &m, int l) {
 
 bool HostModel::finalize(std::string &err) {
     if (n_links <= 0) { err = "n_links must be positive"; return false; }
-    if (n_joints < 0 || n_joints > 32) { err = "n_joints out of range (KIN_MAX_JOINTS)"; return false; }
+    if (n_joints < 0 || n_joints + (with_base ? 3 : 0) > 32) { err = "n_joints (+3 base columns) exceeds KIN_MAX_JOINTS"; return false; }
     std::vector<int> seen(n_joints, 0);
     std::vector<std::vector<int>> kids(n_links);
     for (int l = 0; l < n_links; ++l) {
@@ -139,17 +139,35 @@ bool compile_program(const HostModel &m, const std::vector<int> &fk_links, const
     nodes[0].link = -1; nodes[0].parent = -1; nodes[0].jtype = NODE_ROOT; nodes[0].qcol = -1;
     nodes[0].off = Xf::identity(); nodes[0].relmask = 0;
     nodes[0].axis[0] = nodes[0].axis[1] = nodes[0].axis[2] = 0;
+    // Planar base (transform.jl:33-37: Trans(x, y, 0) * Rz(theta)) = three ordinary nodes under the root:
+    // prismatic x, prismatic y, revolute z, driven by columns D, D+1, D+2.  Their Jacobian columns are
+    // exactly the reference's base block (algorithm.jl:98-105): (1,0,0), (0,1,0), z x (p - base).
+    int root_node = 0;
+    if (m.with_base) {
+        const double ax[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int k = 0; k < 3; ++k) {
+            Node n;
+            n.link = -1; n.parent = root_node; n.jtype = k < 2 ? 2 : 1; n.qcol = m.n_joints + k;
+            n.off = Xf::identity();
+            std::memcpy(n.axis, ax[k], sizeof n.axis);
+            n.relmask = nodes[root_node].relmask | (1u << n.qcol);
+            nodes[root_node].kids.push_back((int)nodes.size());
+            root_node = (int)nodes.size();
+            nodes.push_back(n);
+        }
+    }
+    const unsigned base_mask = nodes[root_node].relmask;
     std::vector<int> node_of(L, 0);     // dynamic node each link hangs from
     std::vector<Xf> C(L);               // link = T_node * C
     for (int l : m.topo) {
         int p = m.parent[l];
-        if (p < 0) { node_of[l] = 0; C[l] = Xf::identity(); continue; }
+        if (p < 0) { node_of[l] = root_node; C[l] = Xf::identity(); continue; }
         if (m.qidx[l] >= 0) {
             Node n;
             n.link = l; n.parent = node_of[p]; n.jtype = m.jtype[l]; n.qcol = m.qidx[l];
             n.off = C[p] * m.pose[l];
             std::memcpy(n.axis, &m.axis[3 * l], sizeof n.axis);
-            n.relmask = m.relmask[l];
+            n.relmask = m.relmask[l] | base_mask;
             nodes[n.parent].kids.push_back((int)nodes.size());
             node_of[l] = (int)nodes.size();
             nodes.push_back(n);
@@ -234,7 +252,7 @@ bool compile_program(const HostModel &m, const std::vector<int> &fk_links, const
     h.io_att = (int)I.size();          I.resize(I.size() + (size_t)h.n_att * ATT_INTS, 0);
     h.io_sph_order = (int)I.size();    I.resize(I.size() + S, 0);
     h.io_sph_mask = (int)I.size();     I.resize(I.size() + S, 0);
-    h.io_col_type = (int)I.size();     I.resize(I.size() + m.n_joints, 0);
+    h.io_col_type = (int)I.size();     I.resize(I.size() + m.n_dof(), 0);
     while (I.size() % 4) I.push_back(0);
     h.n_int = (int)I.size();
 
@@ -291,6 +309,7 @@ bool compile_program(const HostModel &m, const std::vector<int> &fk_links, const
     }
     for (int l = 0; l < L; ++l)
         if (m.qidx[l] >= 0) I[h.io_col_type + m.qidx[l]] = m.jtype[l];
+    if (m.with_base) { I[h.io_col_type + m.n_joints] = 2; I[h.io_col_type + m.n_joints + 1] = 2; I[h.io_col_type + m.n_joints + 2] = 1; }
     for (int b = 0; b < h.n_box; ++b) {
         double *br = &R[h.ro_box + (size_t)b * BOX_REALS];
         std::memcpy(br, m.box_inv[b].r, sizeof(double) * 9);
@@ -299,12 +318,13 @@ bool compile_program(const HostModel &m, const std::vector<int> &fk_links, const
     }
 
     // ---- per-thread scratch map ----
+    // so_q doubles as the per-group (dmin, argmin) hand-over of the collision phase: 2 * SPH_GROUP slots
     int so = 0;
-    h.so_q = so;      so += h.n_dof;
+    h.so_q = so;      so += std::max(h.n_dof, S > 0 ? 8 : 0);
     h.so_save = so;   so += 12 * max_slots;
-    h.so_jf = so;     so += 6 * m.n_joints;
+    h.so_jf = so;     so += 6 * h.n_dof;
     h.so_cent = so;   so += 3 * S;
-    h.so_stale = so;  so += (want_coll && want_stale) ? 3 * m.n_joints : 0;
+    h.so_stale = so;  so += (want_coll && want_stale) ? 3 * h.n_dof : 0;
     h.n_slots = so;
     return true;
 }

@@ -35,7 +35,7 @@ struct HostModel {
     std::vector<unsigned> relmask;  // [L] bit c set <=> control column c moves link (rptable, mechanism.jl:117-139)
 
     int n_dof() const { return n_joints + (with_base ? 3 : 0); }
-    bool finalize(std::string &err);  // validates, builds topo + relmask
+    bool finalize(std::string &err);  // validates, builds topo + relmask (control-joint bits only)
 };
 
 struct Program {

@@ -50,7 +50,8 @@ def run_program(h, ti, tr, Q, with_rot=True, rpy_jac=False, truncation=np.inf, g
     """Q: (N, n_dof).  Returns dict with T (N, n_fk, 3, 4), J (N, n_jac, rows, cols), vals (N, S),
     grads (N, n_dof, S), argmin (N, S)."""
     N = Q.shape[0]
-    D, ND = h["n_joints"], h["n_dof"]
+    ND = h["n_dof"]
+    D = ND          # the planar base is compiled into three ordinary nodes: every column is a joint column
     rows = 6 if with_rot else 3
     T_out = np.zeros((N, h["n_fk"], 3, 4))
     J_out = np.zeros((N, h["n_jac"], rows, ND))
@@ -58,7 +59,6 @@ def run_program(h, ti, tr, Q, with_rot=True, rpy_jac=False, truncation=np.inf, g
     jf_o, jf_a = np.zeros((N, max(D, 1), 3)), np.zeros((N, max(D, 1), 3))
     cent = np.zeros((N, max(h["n_sph"], 1), 3))
     col_type = ti[h["io_col_type"]:h["io_col_type"] + D]
-    bx = by = np.zeros(N)
     R = p = None
     for node in range(h["n_nodes"]):
         ni = ti[h["io_node"] + node * NODE_INTS: h["io_node"] + (node + 1) * NODE_INTS]
@@ -67,11 +67,6 @@ def run_program(h, ti, tr, Q, with_rot=True, rpy_jac=False, truncation=np.inf, g
         if jtype == 3:
             R = np.tile(np.eye(3), (N, 1, 1))
             p = np.zeros((N, 3))
-            if h["with_base"]:
-                bx, by, th = Q[:, D], Q[:, D + 1], Q[:, D + 2]
-                c, s = np.cos(th), np.sin(th)
-                R[:, 0, 0], R[:, 0, 1], R[:, 1, 0], R[:, 1, 1] = c, -s, s, c
-                p[:, 0], p[:, 1] = bx, by
         else:
             if psrc >= 0:
                 R, p = save[psrc]
@@ -124,12 +119,6 @@ def run_program(h, ti, tr, Q, with_rot=True, rpy_jac=False, truncation=np.inf, g
                                 J_out[:, ai[2], 3:, j] = a_w
                     else:
                         J_out[:, ai[2], :3, j] = a_w
-                if h["with_base"]:
-                    x, y = pl[:, 0] - bx, pl[:, 1] - by
-                    J_out[:, ai[2], 0, D], J_out[:, ai[2], 1, D + 1] = 1.0, 1.0
-                    J_out[:, ai[2], 0, D + 2], J_out[:, ai[2], 1, D + 2] = -y, x
-                    if with_rot:
-                        J_out[:, ai[2], 5, D + 2] = 1.0
         for k in range(s0, s1):
             s = ti[h["io_sph_order"] + k]
             sr = tr[h["ro_sph"] + s * SPH_REALS: h["ro_sph"] + (s + 1) * SPH_REALS]
@@ -176,9 +165,5 @@ def run_program(h, ti, tr, Q, with_rot=True, rpy_jac=False, truncation=np.inf, g
                 else:
                     colv = np.zeros((N, 3))
                 grads[live, j, s] = np.einsum("ni,ni->n", g, colv)[live]
-            if h["with_base"]:
-                x, y = P[:, 0] - bx, P[:, 1] - by
-                grads[live, D, s], grads[live, D + 1, s] = g[live, 0], g[live, 1]
-                grads[live, D + 2, s] = (g[:, 1] * x - g[:, 0] * y)[live]
         out.update(vals=vals, grads=grads, argmin=argmin)
     return out

@@ -84,26 +84,32 @@ __device__ __forceinline__ void load_box(const real *__restrict__ b, BoxRow<real
 
 // BoxSDF call (sdf.jl:67-74) in "key" form.  With q = |inv_pose * p| - w/2 and s = |max(q,0)|^2 the
 // reference value is d = sqrt(s) + min(max(q), 0); exactly one of the two terms is non-zero, so
-//     key = s            if s > 0   (outside: d = sqrt(s) > 0)
+//     key = 4 s          if s > 0   (outside: d = sqrt(s) = sqrt(key) / 2 > 0)
 //         = min(max q,0) if s == 0  (inside / on the surface: d = key <= 0)
-// is a monotone function of d (d = key > 0 ? sqrt(key) : key).  The union's argmin (sdf.jl:108-114)
-// is taken on the key with the same first-minimum rule, which needs ONE sqrt per sphere instead of
-// one per box; it can differ from the reference only when two boxes' distances tie within 1 ulp.
+// is a monotone function of d.  The union's argmin (sdf.jl:108-114) is taken on the key with the same
+// first-minimum rule, which needs ONE sqrt per sphere instead of one per box; it can differ from the
+// reference only when two boxes' distances tie within 1 ulp.
+// 2 max(q, 0) = q + |q| exactly, and scaling by 2 / 4 commutes with rounding, so sqrt(key) / 2 is
+// bit-identical to sqrt(s): the clamp costs one DADD per axis instead of a compare-and-select.
+template <typename real>
+__device__ __noinline__ real box_inside_key(real qx, real qy, real qz) {   // rare: centre inside the box
+    real t = qx > qy ? qx : qy;
+    t = t > qz ? t : qz;
+    return t < real(0) ? t : real(0);
+}
 template <typename real>
 __device__ __forceinline__ real box_key(const BoxRow<real> &b, real px, real py, real pz) {
     const real lx = fma_(b.r[0], px, fma_(b.r[1], py, fma_(b.r[2], pz, b.t[0])));
     const real ly = fma_(b.r[3], px, fma_(b.r[4], py, fma_(b.r[5], pz, b.t[1])));
     const real lz = fma_(b.r[6], px, fma_(b.r[7], py, fma_(b.r[8], pz, b.t[2])));
     const real qx = abs_(lx) - b.h[0], qy = abs_(ly) - b.h[1], qz = abs_(lz) - b.h[2];
-    const real mx = relu_(qx), my = relu_(qy), mz = relu_(qz);
-    const real s = fma_(mx, mx, fma_(my, my, mz * mz));
-    real t = qx > qy ? qx : qy;
-    t = t > qz ? t : qz;
-    const real inside = t < real(0) ? t : real(0);
-    return s > real(0) ? s : inside;
+    const real mx = qx + abs_(qx), my = qy + abs_(qy), mz = qz + abs_(qz);
+    real key = fma_(mx, mx, fma_(my, my, mz * mz));
+    if (!(key > real(0))) key = box_inside_key(qx, qy, qz);
+    return key;
 }
 template <typename real>
-__device__ __forceinline__ real key_to_dist(real key) { return key > real(0) ? sqrt_(key) : key; }
+__device__ __forceinline__ real key_to_dist(real key) { return key > real(0) ? real(0.5) * sqrt_(key) : key; }
 
 // closed-form gradient of one box, world frame (extension; KIN_GRAD_ANALYTIC)
 template <typename real>
@@ -191,6 +197,10 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     // The planar base is compiled into three ordinary nodes (prismatic x, y; revolute z), so every one of
     // the ND columns is an ordinary joint column here; DC = columns that are control joints.
     const int DC = h.n_joints, ND = h.n_dof;
+    unsigned rev_mask = 0;              // bit j: column j is a revolute joint
+    for (int j = 0; j < ND; ++j) rev_mask |= (ti[h.io_col_type + j] == 1 ? 1u : 0u) << j;
+    const real *jf0 = &SCR(h.so_jf);
+    real *stale0 = &SCR(h.so_stale);
     const int rows = A.with_rot ? 6 : 3;
     // distance between consecutive components of one configuration's record
     const size_t es = AOS ? size_t(1) : (size_t)A.ld;
@@ -310,11 +320,11 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     const unsigned mask = (unsigned)ai[3];
                     real k[6] = {0, 0, 0, 0, 0, 0};
                     if (A.with_rot && A.rpy_jac) rpy_rate_coeffs(Tl, k);
-                    for (int j = 0; j < ND; ++j, o += rows * es) {
+                    const real *jf = jf0;
+                    for (int j = 0; j < ND; ++j, o += rows * es, jf += 6 * BS) {
                         if ((mask >> j) & 1u) {
-                            const real *jf = &SCR(h.so_jf + 6 * j);
                             const real ax = jf[3 * BS], ay = jf[4 * BS], az = jf[5 * BS];
-                            if (ti[h.io_col_type + j] == 1) {
+                            if ((rev_mask >> j) & 1u) {
                                 const real dx = Tl.p[0] - jf[0], dy = Tl.p[1] - jf[BS], dz = Tl.p[2] - jf[2 * BS];
                                 o[0] = fma_(ay, dz, -(az * dy));
                                 o[es] = fma_(az, dx, -(ax * dz));
@@ -360,7 +370,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
             const bool stale = want_grads && A.scratch_ref;
             const real trunc = (real)A.truncation_dist, voff = (real)A.vals_offset;
             if (stale)
-                for (int i = 0; i < 3 * ND; ++i) SCR(h.so_stale + i) = real(0);   // jac = zeros(3, n_dof), collision.jl:76
+                for (int i = 0; i < 3 * ND; ++i) stale0[i * BS] = real(0);   // jac = zeros(3, n_dof), collision.jl:76
             real *Vp = reinterpret_cast<real *>(A.vals_out) + (AOS ? n * S : n);
             real *Gp = reinterpret_cast<real *>(A.grads_out) + (AOS ? n * ((long long)ND * S) : n);
             int32_t *Ap = A.argmin_out ? A.argmin_out + (AOS ? n * S : n) : nullptr;
@@ -418,18 +428,18 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                         box_gradient(row, A.grad_mode, px, py, pz, dmin, grad);
                     }
                     const unsigned mask = (unsigned)ti[h.io_sph_mask + s];
-                    for (int j = 0; j < ND; ++j, Gp += es) {
+                    const real *jf = jf0;
+                    real *st = stale0;
+                    for (int j = 0; j < ND; ++j, Gp += es, jf += 6 * BS, st += 3 * BS) {
                         real cx, cy, cz;
                         if ((mask >> j) & 1u) {   // joint_jacobian!, algorithm.jl:65-81
-                            const real *jf = &SCR(h.so_jf + 6 * j);
                             const real ax = jf[3 * BS], ay = jf[4 * BS], az = jf[5 * BS];
-                            if (ti[h.io_col_type + j] == 1) {
+                            if ((rev_mask >> j) & 1u) {
                                 const real dx = px - jf[0], dy = py - jf[BS], dz = pz - jf[2 * BS];
                                 cx = fma_(ay, dz, -(az * dy)); cy = fma_(az, dx, -(ax * dz)); cz = fma_(ax, dy, -(ay * dx));
                             } else { cx = ax; cy = ay; cz = az; }
-                            if (stale) { real *st = &SCR(h.so_stale + 3 * j); st[0] = cx; st[BS] = cy; st[2 * BS] = cz; }
+                            if (stale) { st[0] = cx; st[BS] = cy; st[2 * BS] = cz; }
                         } else if (stale) {     // column left over from an earlier sphere (collision.jl:76,90)
-                            const real *st = &SCR(h.so_stale + 3 * j);
                             cx = st[0]; cy = st[BS]; cz = st[2 * BS];
                         } else { cx = cy = cz = real(0); }
                         *Gp = fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz));   // transpose(grad) * jac

@@ -137,17 +137,17 @@ using KernelFn = void (*)(const kin::KernelArgs);
 constexpr int kNumBS = 4;
 const int kBS[kNumBS] = {128, 96, 64, 32};
 
-// [precision][layout][block size][collision]
-#define KIN_K(real, aos, bs, coll) kin::kin_eval_kernel<real, aos, bs, coll>
+// [precision][layout][block size][collision][joint frames in registers]
+#define KIN_K(real, aos, bs, coll) {kin::kin_eval_kernel<real, aos, bs, coll, 0>, kin::kin_eval_kernel<real, aos, bs, coll, kin::JF_REGS>}
 #define KIN_BS_ROW(real, aos) \
     {{KIN_K(real, aos, 128, false), KIN_K(real, aos, 128, true)}, {KIN_K(real, aos, 96, false), KIN_K(real, aos, 96, true)}, \
      {KIN_K(real, aos, 64, false), KIN_K(real, aos, 64, true)}, {KIN_K(real, aos, 32, false), KIN_K(real, aos, 32, true)}}
-const KernelFn kKernels[2][2][kNumBS][2] = {{KIN_BS_ROW(double, false), KIN_BS_ROW(double, true)},
-                                            {KIN_BS_ROW(float, false), KIN_BS_ROW(float, true)}};
+const KernelFn kKernels[2][2][kNumBS][2][2] = {{KIN_BS_ROW(double, false), KIN_BS_ROW(double, true)},
+                                               {KIN_BS_ROW(float, false), KIN_BS_ROW(float, true)}};
 
 int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
     const kin::ProgHeader &h = dp->prog.h;
-    const int coll = h.n_sph > 0 ? 1 : 0;
+    const int coll = h.n_sph > 0 ? 1 : 0, jr = (coll && h.n_dof <= kin::JF_REGS) ? 1 : 0;
     const size_t rs = pi ? sizeof(float) : sizeof(double);
     const size_t tab = sizeof(int32_t) * (size_t)h.n_int + rs * (size_t)h.n_real;
     int dev_smem = 0;
@@ -158,7 +158,7 @@ int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
         const int b = kBS[bi];
         const size_t smem = tab + rs * (size_t)h.n_slots * b;
         if (smem > (size_t)dev_smem) continue;
-        KernelFn k = kKernels[pi][li][bi][coll];
+        KernelFn k = kKernels[pi][li][bi][coll][jr];
         CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));
         int occ = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, b, smem));
@@ -166,7 +166,7 @@ int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
     }
     if (best < 0) return fail(KIN_ERR_LIMIT, "model does not fit the shared-memory scratch of one CTA");
     cudaFuncAttributes fa;
-    CUDA_TRY(cudaFuncGetAttributes(&fa, kKernels[pi][li][best][coll]));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, kKernels[pi][li][best][coll][jr]));
     dp->block[pi][li] = kBS[best]; dp->bs_index[pi][li] = best; dp->occ[pi][li] = best_occ; dp->smem[pi][li] = best_smem;
     dp->regs[pi][li] = fa.numRegs;
     return KIN_OK;
@@ -196,7 +196,7 @@ int get_program(KinModel *m, const KinCall *c, DeviceProgram **out) {
         }
         DeviceProgram *dp = new DeviceProgram();
         std::string err;
-        if (!kin::compile_program(m->hm, fk, jac, want_coll, want_stale, dp->prog, err)) {
+        if (!kin::compile_program(m->hm, fk, jac, want_coll, want_stale, kin::JF_REGS, dp->prog, err)) {
             delete dp;
             return fail(KIN_ERR_INVALID_ARGUMENT, err);
         }
@@ -263,8 +263,8 @@ int launch(KinModel *m, const KinCall *c, DeviceProgram *dp, cudaStream_t stream
     if (grid > tiles) grid = tiles;
     if (grid < 1) return KIN_OK;
     const size_t smem = dp->smem[pi][li];
-    const int coll = (dp->prog.h.n_sph > 0 && c->vals_out) ? 1 : 0;
-    kKernels[pi][li][dp->bs_index[pi][li]][coll]<<<(unsigned)grid, block, smem, stream>>>(a);
+    const int coll = (dp->prog.h.n_sph > 0 && c->vals_out) ? 1 : 0, jr = (coll && dp->prog.h.n_dof <= kin::JF_REGS) ? 1 : 0;
+    kKernels[pi][li][dp->bs_index[pi][li]][coll][jr]<<<(unsigned)grid, block, smem, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
     return KIN_OK;
@@ -310,7 +310,7 @@ int kin_program_dump(const KinModelDesc *d, const int32_t *fk_links, int32_t n_f
     for (int i = 0; i < n_jac; ++i) jac[i] = jac_links[i] - 1;
     kin::Program p;
     std::string err;
-    if (!kin::compile_program(hm, fk, jac, want_coll != 0, want_stale != 0, p, err)) return fail(KIN_ERR_INVALID_ARGUMENT, err);
+    if (!kin::compile_program(hm, fk, jac, want_coll != 0, want_stale != 0, kin::JF_REGS, p, err)) return fail(KIN_ERR_INVALID_ARGUMENT, err);
     const int hn = (int)(sizeof(kin::ProgHeader) / sizeof(int32_t));
     if (header_cap < hn || ints_cap < (int)p.ints.size() || reals_cap < (int)p.reals.size())
         return fail(KIN_ERR_LIMIT, "kin_program_dump: output buffers too small");

@@ -172,9 +172,30 @@ __device__ __forceinline__ void rpy_rate_coeffs(const Tf<real> &T, real k[6]) {
 }
 
 constexpr int SPH_GROUP = 4;   // spheres evaluated together against each box row (register blocking)
+constexpr int JF_REGS = 8;     // joint frames kept in registers when the model has at most this many columns
+static_assert(JF_REGS == 8, "the switch statements in kin_eval_kernel enumerate 8 cases");
 
-template <typename real, bool AOS, int BS, bool COLL>
-__global__ void __launch_bounds__(BS)
+// World joint frame (origin, axis) of one configuration column: FloatingAxis, mechanism.jl:105-108.
+template <typename real> struct JFrame { real o[3], a[3]; };
+
+// One Jacobian column of a point p w.r.t. column j (joint_jacobian!, algorithm.jl:65-81)
+template <typename real>
+__device__ __forceinline__ void jac_col(const JFrame<real> &f, bool revolute, real px, real py, real pz, real &cx, real &cy, real &cz) {
+    if (revolute) {
+        const real dx = px - f.o[0], dy = py - f.o[1], dz = pz - f.o[2];
+        cx = fma_(f.a[1], dz, -(f.a[2] * dy)); cy = fma_(f.a[2], dx, -(f.a[0] * dz)); cz = fma_(f.a[0], dy, -(f.a[1] * dx));
+    } else { cx = f.a[0]; cy = f.a[1]; cz = f.a[2]; }
+}
+
+// JR = 0: joint frames live in the shared scratch (any number of columns, rolled loops);
+// JR > 0: the model has at most JR columns and the frames live in registers (static indexing through
+//         fully unrolled loops), which frees 6 * n_dof scratch slots per thread and lets a third CTA fit.
+// Register budget: registers are allocated per SM sub-partition (16 K each), so 8 resident warps (4 CTAs
+// of 64 threads, 2 warps per sub-partition) may use up to 255 registers per thread, while a 9th warp
+// would cap every thread at 168 and spill.  With the frames in registers the collision kernel is
+// therefore built for 4 x 64 threads per SM.
+template <typename real, bool AOS, int BS, bool COLL, int JR>
+__global__ void __launch_bounds__(BS, (JR > 0 && COLL) ? (BS == 64 ? 4 : BS == 128 ? 2 : BS == 32 ? 8 : 2) : 1)
 kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ProgHeader &h = A.h;
@@ -199,11 +220,21 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     const int DC = h.n_joints, ND = h.n_dof;
     unsigned rev_mask = 0;              // bit j: column j is a revolute joint
     for (int j = 0; j < ND; ++j) rev_mask |= (ti[h.io_col_type + j] == 1 ? 1u : 0u) << j;
-    const real *jf0 = &SCR(h.so_jf);
+    real *jf0 = &SCR(h.so_jf);          // JR == 0 only
     real *stale0 = &SCR(h.so_stale);
     const int rows = A.with_rot ? 6 : 3;
     // distance between consecutive components of one configuration's record
     const size_t es = AOS ? size_t(1) : (size_t)A.ld;
+
+    // frame of column j: registers (j is a compile-time constant after unrolling) or scratch
+    JFrame<real> jfr[JR > 0 ? JR : 1];
+    #define JF_LOAD(f, j, ptr)                                                              \
+        JFrame<real> f;                                                                     \
+        if (JR > 0) f = jfr[j];                                                             \
+        else { f.o[0] = (ptr)[0]; f.o[1] = (ptr)[BS]; f.o[2] = (ptr)[2 * BS];               \
+               f.a[0] = (ptr)[3 * BS]; f.a[1] = (ptr)[4 * BS]; f.a[2] = (ptr)[5 * BS]; }
+    // for (j = 0; j < ND; ++j): unrolled to JR iterations with an early exit, or rolled
+    #define FOR_COLUMNS(j) _Pragma("unroll") for (int j = 0; j < (JR > 0 ? JR : ND); ++j) if (JR > 0 && j >= ND) break; else
 
     const long long n_tiles = (A.n + BS - 1) / BS;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -213,6 +244,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
         // ---- configuration -> scratch (all loads in flight together) ----
         {
             const real *qn = reinterpret_cast<const real *>(A.q) + (AOS ? n * ND : n);
+            #pragma unroll 4
             for (int c = 0; c < ND; ++c) SCR(h.so_q + c) = qn[c * es];
         }
         real *Tn = reinterpret_cast<real *>(A.T_out) + (AOS ? n * (12 * h.n_fk) : n);
@@ -242,24 +274,34 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 Tf<real> Aj;
                 tf_mul_const(T, nr, flags & NF_OFF_R_IDENTITY, Aj);
                 const int code = (flags >> NF_AXIS_SHIFT) & NF_AXIS_MASK;
-                real ax, ay, az;          // world joint axis (algorithm.jl:50)
+                JFrame<real> f;           // world joint origin and axis (algorithm.jl:49-50)
+                f.o[0] = Aj.p[0]; f.o[1] = Aj.p[1]; f.o[2] = Aj.p[2];
                 const real sgn = code >= 4 ? real(-1) : real(1);
                 switch (code) {
-                    case 1: case 4: ax = sgn * Aj.r[0]; ay = sgn * Aj.r[3]; az = sgn * Aj.r[6]; break;
-                    case 2: case 5: ax = sgn * Aj.r[1]; ay = sgn * Aj.r[4]; az = sgn * Aj.r[7]; break;
-                    case 3: case 6: ax = sgn * Aj.r[2]; ay = sgn * Aj.r[5]; az = sgn * Aj.r[8]; break;
+                    case 1: case 4: f.a[0] = sgn * Aj.r[0]; f.a[1] = sgn * Aj.r[3]; f.a[2] = sgn * Aj.r[6]; break;
+                    case 2: case 5: f.a[0] = sgn * Aj.r[1]; f.a[1] = sgn * Aj.r[4]; f.a[2] = sgn * Aj.r[7]; break;
+                    case 3: case 6: f.a[0] = sgn * Aj.r[2]; f.a[1] = sgn * Aj.r[5]; f.a[2] = sgn * Aj.r[8]; break;
                     default:
-                        ax = fma_(Aj.r[0], nr[12], fma_(Aj.r[1], nr[13], Aj.r[2] * nr[14]));
-                        ay = fma_(Aj.r[3], nr[12], fma_(Aj.r[4], nr[13], Aj.r[5] * nr[14]));
-                        az = fma_(Aj.r[6], nr[12], fma_(Aj.r[7], nr[13], Aj.r[8] * nr[14]));
+                        f.a[0] = fma_(Aj.r[0], nr[12], fma_(Aj.r[1], nr[13], Aj.r[2] * nr[14]));
+                        f.a[1] = fma_(Aj.r[3], nr[12], fma_(Aj.r[4], nr[13], Aj.r[5] * nr[14]));
+                        f.a[2] = fma_(Aj.r[6], nr[12], fma_(Aj.r[7], nr[13], Aj.r[8] * nr[14]));
                 }
-                real *jf = &SCR(h.so_jf + 6 * qcol);
-                jf[0] = Aj.p[0]; jf[BS] = Aj.p[1]; jf[2 * BS] = Aj.p[2];
-                jf[3 * BS] = ax; jf[4 * BS] = ay; jf[5 * BS] = az;
+                if (JR > 0) {
+                    switch (qcol) {       // uniform branch: one register copy, static indices
+                        #define KIN_CASE(k) case k: if (k < JR) jfr[k < JR ? k : 0] = f; break;
+                        KIN_CASE(0) KIN_CASE(1) KIN_CASE(2) KIN_CASE(3) KIN_CASE(4) KIN_CASE(5) KIN_CASE(6) KIN_CASE(7)
+                        #undef KIN_CASE
+                        default: break;
+                    }
+                } else {
+                    real *jf = jf0 + 6 * BS * qcol;
+                    jf[0] = f.o[0]; jf[BS] = f.o[1]; jf[2 * BS] = f.o[2];
+                    jf[3 * BS] = f.a[0]; jf[4 * BS] = f.a[1]; jf[5 * BS] = f.a[2];
+                }
                 const real qa = SCR(h.so_q + qcol);
                 T = Aj;
                 if (jtype == 2) {          // prismatic: pose * Trans(axis * a), mechanism.jl:100-103
-                    T.p[0] = fma_(ax, qa, Aj.p[0]); T.p[1] = fma_(ay, qa, Aj.p[1]); T.p[2] = fma_(az, qa, Aj.p[2]);
+                    T.p[0] = fma_(f.a[0], qa, Aj.p[0]); T.p[1] = fma_(f.a[1], qa, Aj.p[1]); T.p[2] = fma_(f.a[2], qa, Aj.p[2]);
                 } else {                   // revolute: pose * R(axis, a), mechanism.jl:94-98
                     real s, c;
                     sincos_(code >= 4 ? -qa : qa, &s, &c);
@@ -321,31 +363,45 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     real k[6] = {0, 0, 0, 0, 0, 0};
                     if (A.with_rot && A.rpy_jac) rpy_rate_coeffs(Tl, k);
                     const real *jf = jf0;
-                    for (int j = 0; j < ND; ++j, o += rows * es, jf += 6 * BS) {
+                    #pragma unroll 1
+                    for (int j = 0; j < ND; ++j) {      // rolled: executed once per requested link only
                         if ((mask >> j) & 1u) {
-                            const real ax = jf[3 * BS], ay = jf[4 * BS], az = jf[5 * BS];
-                            if ((rev_mask >> j) & 1u) {
-                                const real dx = Tl.p[0] - jf[0], dy = Tl.p[1] - jf[BS], dz = Tl.p[2] - jf[2 * BS];
-                                o[0] = fma_(ay, dz, -(az * dy));
-                                o[es] = fma_(az, dx, -(ax * dz));
-                                o[2 * es] = fma_(ax, dy, -(ay * dx));
-                                if (A.with_rot) {
-                                    if (A.rpy_jac) {
-                                        o[3 * es] = k[0] * ax - k[1] * ay;
-                                        o[4 * es] = fma_(k[2], ax, k[3] * ay);
-                                        o[5 * es] = fma_(k[4], ax, k[5] * ay) + az;
-                                    } else {
-                                        o[3 * es] = ax; o[4 * es] = ay; o[5 * es] = az;
-                                    }
+                            JFrame<real> f;
+                            if (JR > 0) {
+                                switch (j) {
+                                    #define KIN_CASE(k) case k: f = jfr[k < JR ? k : 0]; break;
+                                    KIN_CASE(0) KIN_CASE(1) KIN_CASE(2) KIN_CASE(3) KIN_CASE(4) KIN_CASE(5) KIN_CASE(6) KIN_CASE(7)
+                                    #undef KIN_CASE
+                                    default: f = jfr[0]; break;
                                 }
-                            } else {   // prismatic: rows 4:6 untouched by the reference (algorithm.jl:78-81),
-                                       // except in the base block, which it always writes (algorithm.jl:102-104)
-                                o[0] = ax; o[es] = ay; o[2 * es] = az;
-                                if (A.with_rot && (!A.keep_irrelevant || j >= DC)) { o[3 * es] = real(0); o[4 * es] = real(0); o[5 * es] = real(0); }
+                            } else {
+                                f.o[0] = jf[0]; f.o[1] = jf[BS]; f.o[2] = jf[2 * BS];
+                                f.a[0] = jf[3 * BS]; f.a[1] = jf[4 * BS]; f.a[2] = jf[5 * BS];
+                            }
+                            real cx, cy, cz;
+                            const bool rev = (rev_mask >> j) & 1u;
+                            jac_col(f, rev, Tl.p[0], Tl.p[1], Tl.p[2], cx, cy, cz);
+                            o[0] = cx; o[es] = cy; o[2 * es] = cz;
+                            if (A.with_rot) {
+                                if (rev) {
+                                    if (A.rpy_jac) {
+                                        o[3 * es] = k[0] * f.a[0] - k[1] * f.a[1];
+                                        o[4 * es] = fma_(k[2], f.a[0], k[3] * f.a[1]);
+                                        o[5 * es] = fma_(k[4], f.a[0], k[5] * f.a[1]) + f.a[2];
+                                    } else {
+                                        o[3 * es] = f.a[0]; o[4 * es] = f.a[1]; o[5 * es] = f.a[2];
+                                    }
+                                } else if (!A.keep_irrelevant || j >= DC) {
+                                    // prismatic: rows 4:6 untouched by the reference (algorithm.jl:78-81), except in
+                                    // the base block, which it always writes (algorithm.jl:102-104)
+                                    o[3 * es] = real(0); o[4 * es] = real(0); o[5 * es] = real(0);
+                                }
                             }
                         } else if (!A.keep_irrelevant) {
                             for (int r = 0; r < rows; ++r) o[r * es] = real(0);
                         }
+                        o += rows * es;
+                        jf += 6 * BS;
                     }
                 }
             }
@@ -399,7 +455,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     }
                     #pragma unroll
                     for (int g = 0; g < SPH_GROUP; ++g) {
-                        hand[g * BS] = key_to_dist(kmin[g]);
+                        hand[g * BS] = kmin[g];      // the key; converted to a distance once, in 2b
                         reinterpret_cast<int *>(&hand[(SPH_GROUP + g) * BS])[0] = kidx[g];
                     }
                 }
@@ -408,7 +464,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 #pragma unroll 1
                 for (int g = 0; g < SPH_GROUP && s0 + g < S; ++g) {
                     const int s = s0 + g;
-                    const real dmin = hand[g * BS];
+                    const real dmin = key_to_dist(hand[g * BS]);
                     const int kmin = reinterpret_cast<const int *>(&hand[(SPH_GROUP + g) * BS])[0];
                     const real dist0 = dmin - tr[h.ro_sph + s * SPH_REALS + 3];
                     const bool truncated = dist0 > trunc;
@@ -430,25 +486,25 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     const unsigned mask = (unsigned)ti[h.io_sph_mask + s];
                     const real *jf = jf0;
                     real *st = stale0;
-                    for (int j = 0; j < ND; ++j, Gp += es, jf += 6 * BS, st += 3 * BS) {
+                    FOR_COLUMNS(j) {
                         real cx, cy, cz;
                         if ((mask >> j) & 1u) {   // joint_jacobian!, algorithm.jl:65-81
-                            const real ax = jf[3 * BS], ay = jf[4 * BS], az = jf[5 * BS];
-                            if ((rev_mask >> j) & 1u) {
-                                const real dx = px - jf[0], dy = py - jf[BS], dz = pz - jf[2 * BS];
-                                cx = fma_(ay, dz, -(az * dy)); cy = fma_(az, dx, -(ax * dz)); cz = fma_(ax, dy, -(ay * dx));
-                            } else { cx = ax; cy = ay; cz = az; }
+                            JF_LOAD(f, j, jf)
+                            jac_col(f, (rev_mask >> j) & 1u, px, py, pz, cx, cy, cz);
                             if (stale) { st[0] = cx; st[BS] = cy; st[2 * BS] = cz; }
                         } else if (stale) {     // column left over from an earlier sphere (collision.jl:76,90)
                             cx = st[0]; cy = st[BS]; cz = st[2 * BS];
                         } else { cx = cy = cz = real(0); }
                         *Gp = fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz));   // transpose(grad) * jac
+                        Gp += es; jf += 6 * BS; st += 3 * BS;
                     }
                 }
             }
         }
     }
     #undef SCR
+    #undef JF_LOAD
+    #undef FOR_COLUMNS
 }
 
 // sdf(p) and gradient!(sdf, p, out) for a batch of points (sdf.jl:34-41, 67-74, 108-119).

@@ -129,7 +129,7 @@ struct Att {
 }  // namespace
 
 bool compile_program(const HostModel &m, const std::vector<int> &fk_links, const std::vector<int> &jac_links,
-                     bool want_coll, bool want_stale, Program &out, std::string &err) {
+                     bool want_coll, bool want_stale, int jf_regs, Program &out, std::string &err) {
     const int L = m.n_links;
     for (int l : fk_links) if (l < 0 || l >= L) { err = "fk link id out of range"; return false; }
     for (int l : jac_links) if (l < 0 || l >= L) { err = "jacobian link id out of range"; return false; }
@@ -322,7 +322,7 @@ bool compile_program(const HostModel &m, const std::vector<int> &fk_links, const
     int so = 0;
     h.so_q = so;      so += std::max(h.n_dof, S > 0 ? 8 : 0);
     h.so_save = so;   so += 12 * max_slots;
-    h.so_jf = so;     so += 6 * h.n_dof;
+    h.so_jf = so;     so += (want_coll && jf_regs > 0 && h.n_dof <= jf_regs) ? 0 : 6 * h.n_dof;   // frames in registers: no slots
     h.so_cent = so;   so += 3 * S;
     h.so_stale = so;  so += (want_coll && want_stale) ? 3 * h.n_dof : 0;
     h.n_slots = so;

@@ -46,6 +46,6 @@ struct Program {
 
 // fk_links / jac_links are 0-based link indices in output order.
 bool compile_program(const HostModel &m, const std::vector<int> &fk_links, const std::vector<int> &jac_links,
-                     bool want_coll, bool want_stale, Program &out, std::string &err);
+                     bool want_coll, bool want_stale, int jf_regs, Program &out, std::string &err);
 
 }  // namespace kin

@@ -199,6 +199,20 @@ KIN_API int kin_sdf_points(int32_t n_boxes, const double *box_pose, const double
                    int32_t layout, const void *pts, int64_t n, int32_t grad_mode, void *vals_out,
                    void *grads_out, int32_t *argmin_out, void *stream);
 
+/* Pose residuals of one link against target poses -- the per-iteration evaluations of the IK and
+ * planning callers:
+ *   KIN_POSE_IK_OBJECTIVE  inverse_kinematics.jl:38-50: e = [p_t - p; rpy_t - rpy] (3 or 6 rows),
+ *                          val_out[N] = sum(e.^2), jac_out (n_dof per configuration) = -2 J' e
+ *   KIN_POSE_CONSTRAINT    planning.jl:114-138: val_out (dim = 3|6 per configuration) = [p - p_t; rpy - rpy_t],
+ *                          jac_out ((n_dof, dim) column-major per configuration) = transpose of the Jacobian
+ * J is the Euler-rate Jacobian (rpy_jac = true), rpy = [roll, pitch, yaw] of RotZYX (transform.jl:45-48).
+ * target: DEVICE, [x, y, z, roll, pitch, yaw] per configuration in `layout` (6 components), or ONE
+ * target shared by the batch when target_per_config == 0 (6 contiguous values). */
+typedef enum { KIN_POSE_IK_OBJECTIVE = 0, KIN_POSE_CONSTRAINT = 1 } KinPoseMode;
+KIN_API int kin_pose_residual(KinModel *model, int32_t precision, int32_t layout, const void *q, int64_t n,
+                              int32_t link_id, const void *target, int32_t target_per_config, int32_t with_rot,
+                              int32_t mode, void *val_out, void *jac_out, void *stream);
+
 /* Diagnostics for bench.py / tests: kernel launches issued by this library since load, and the
  * static resources of the kernel a call would use (registers / thread, dynamic shared memory bytes /
  * CTA, threads / CTA, CTAs in the grid).  */

@@ -504,6 +504,46 @@ int kin_sdf_points(int32_t n_boxes, const double *box_pose, const double *box_wi
     return KIN_OK;
 }
 
+int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void *q, int64_t n, int32_t link_id,
+                      const void *target, int32_t target_per_config, int32_t with_rot, int32_t mode, void *val_out,
+                      void *jac_out, void *stream_) {
+    if (!m) return fail(KIN_ERR_INVALID_ARGUMENT, "null model");
+    if (n < 0 || (n > 0 && (!q || !target || !val_out || !jac_out))) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
+    if (mode != KIN_POSE_IK_OBJECTIVE && mode != KIN_POSE_CONSTRAINT) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown pose mode");
+    if (n == 0) return KIN_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t es = precision == KIN_F32 ? 4 : 8;
+    const int nd = m->hm.n_dof(), rows = with_rot ? 6 : 3;
+    void *ws = nullptr;
+    const size_t tb = es * 12 * (size_t)n, jb = es * (size_t)rows * nd * (size_t)n;
+    CUDA_TRY(cudaMallocAsync(&ws, tb + jb, stream));
+    KinCall c;
+    std::memset(&c, 0, sizeof c);
+    c.precision = precision; c.layout = layout; c.n = n; c.q = q;
+    c.n_fk_links = 1; c.fk_links = &link_id; c.T_out = ws;
+    c.n_jac_links = 1; c.jac_links = &link_id; c.with_rot = with_rot; c.rpy_jac = 1; c.J_out = (unsigned char *)ws + tb;
+    c.truncation_dist = INFINITY; c.stream = stream_;
+    int rc = kin_eval(m, &c);
+    if (rc != KIN_OK) { cudaFreeAsync(ws, stream); return rc; }
+    const int block = 256;
+    long long grid = (n + block - 1) / block;
+    if (grid > 148 * 16) grid = 148 * 16;
+    const bool aos = layout == KIN_LAYOUT_AOS;
+    if (precision == KIN_F64) {
+        auto T = (const double *)ws, J = (const double *)((unsigned char *)ws + tb);
+        if (aos) kin::pose_residual_kernel<double, true><<<(unsigned)grid, block, 0, stream>>>(T, J, (const double *)target, target_per_config, n, nd, with_rot, mode, (double *)val_out, (double *)jac_out);
+        else kin::pose_residual_kernel<double, false><<<(unsigned)grid, block, 0, stream>>>(T, J, (const double *)target, target_per_config, n, nd, with_rot, mode, (double *)val_out, (double *)jac_out);
+    } else {
+        auto T = (const float *)ws, J = (const float *)((unsigned char *)ws + tb);
+        if (aos) kin::pose_residual_kernel<float, true><<<(unsigned)grid, block, 0, stream>>>(T, J, (const float *)target, target_per_config, n, nd, with_rot, mode, (float *)val_out, (float *)jac_out);
+        else kin::pose_residual_kernel<float, false><<<(unsigned)grid, block, 0, stream>>>(T, J, (const float *)target, target_per_config, n, nd, with_rot, mode, (float *)val_out, (float *)jac_out);
+    }
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaFreeAsync(ws, stream));
+    return KIN_OK;
+}
+
 int kin_fk_links(KinModel *m, int32_t precision, int32_t layout, const void *q, int64_t n, const int32_t *link_ids,
                  int32_t n_req, void *T_out, void *stream) {
     KinCall c;

@@ -540,4 +540,53 @@ sdf_points_kernel(const real *__restrict__ boxes, int n_box, const real *__restr
     }
 }
 
+// Pose residual / IK objective from the link transform T (12 per configuration) and its Euler-rate
+// Jacobian J (6 or 3 x n_dof), both produced by kin_eval_kernel in the same layout.
+//   mode 0  inverse_kinematics.jl:38-50   f = sum(e^2), grad = -2 J' e,   e = [p_t - p; rpy_t - rpy]
+//   mode 1  planning.jl:114-138           val = [p - p_t; rpy - rpy_t],   jac_T(n_dof, dim) = J'
+template <typename real, bool AOS>
+__global__ void __launch_bounds__(256)
+pose_residual_kernel(const real *__restrict__ T, const real *__restrict__ J, const real *__restrict__ target,
+                     int target_per_config, long long n_cfg, int nd, int with_rot, int mode,
+                     real *__restrict__ val_out, real *__restrict__ jac_out) {
+    const int rows = with_rot ? 6 : 3;
+    for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n_cfg; n += (long long)gridDim.x * blockDim.x) {
+        const size_t es = AOS ? size_t(1) : (size_t)n_cfg;
+        const real *Tn = T + (AOS ? n * 12 : n);
+        const real *Jn = J + (AOS ? n * (long long)(rows * nd) : n);
+        const real *tg = target_per_config ? target + (AOS ? n * 6 : n) : target;
+        const size_t ts = target_per_config ? es : size_t(1);
+        real e[6];
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) e[i] = Tn[(9 + i) * es] - tg[i * ts];          // p - p_t
+        if (with_rot) {   // rpy(T), transform.jl:45-48 (RotZYX): R[r][c] = T[c*3 + r]
+            const real r00 = Tn[0], r10 = Tn[es], r20 = Tn[2 * es], r01 = Tn[3 * es], r11 = Tn[4 * es],
+                       r21 = Tn[5 * es], r02 = Tn[6 * es], r12 = Tn[7 * es], r22 = Tn[8 * es];
+            const real yaw = atan2_(r10, r00);
+            real s1, c1;
+            sincos_(yaw, &s1, &c1);
+            const real pitch = atan2_(-r20, sqrt_(fma_(r21, r21, r22 * r22)));
+            const real roll = atan2_(fma_(r02, s1, -(r12 * c1)), fma_(r11, c1, -(r01 * s1)));
+            e[3] = roll - tg[3 * ts]; e[4] = pitch - tg[4 * ts]; e[5] = yaw - tg[5 * ts];
+        }
+        if (mode == 0) {
+            real f = 0;
+            for (int r = 0; r < rows; ++r) { e[r] = -e[r]; f = fma_(e[r], e[r], f); }   // e = target - now
+            val_out[n] = f;
+            real *g = jac_out + (AOS ? n * nd : n);
+            for (int j = 0; j < nd; ++j) {
+                real acc = 0;
+                for (int r = 0; r < rows; ++r) acc = fma_(Jn[(size_t)(j * rows + r) * es], e[r], acc);
+                g[j * es] = real(-2) * acc;
+            }
+        } else {
+            real *v = val_out + (AOS ? n * rows : n);
+            for (int r = 0; r < rows; ++r) v[r * es] = e[r];
+            real *jt = jac_out + (AOS ? n * (long long)(rows * nd) : n);
+            for (int r = 0; r < rows; ++r)
+                for (int j = 0; j < nd; ++j) jt[(size_t)(r * nd + j) * es] = Jn[(size_t)(j * rows + r) * es];
+        }
+    }
+}
+
 }  // namespace kin

@@ -1,0 +1,113 @@
+"""The per-iteration evaluation of the reference's IK driver (inverse_kinematics.jl:38-50) on the B200
+backend, batched over independent problems, plus a batched damped-least-squares driver that uses it.
+The SLSQP solver itself (NLopt) is third-party and out of scope."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .algorithm import _check_joints
+from .device import current_q, device_model
+from .mechanism import Mechanism, set_joint_angles
+from .transform import Transform, rpy, translation
+
+
+def _targets_tensor(target, N, dtype, device):
+    """target: Transform (shared), or (N, 6) [x, y, z, roll, pitch, yaw] array / tensor.
+    -> (tensor, per_config flag)"""
+    import torch
+    if isinstance(target, Transform):
+        t = np.concatenate([translation(target), rpy(target)])
+        return torch.tensor(t, dtype=dtype, device=device), 0
+    t = target if isinstance(target, torch.Tensor) else torch.as_tensor(np.asarray(target, dtype=np.float64))
+    t = t.to(device=device, dtype=dtype)
+    if t.dim() == 1:
+        return t.contiguous(), 0
+    assert t.shape == (N, 6), "targets must be (N, 6): x, y, z, roll, pitch, yaw"
+    return t, 1
+
+
+def _pose_residual(m: Mechanism, link, joints, target, with_rot, mode):
+    import torch
+    _check_joints(m, joints)
+    dm = device_model(m)
+    Q, layout, N = current_q(m)
+    nd, rows = dm.n_dof, (6 if with_rot else 3)
+    tg, per = _targets_tensor(target, N, Q.dtype, Q.device)
+    if per:   # bring the targets to the layout of q
+        tg = tg.t().contiguous().t() if layout == _lib.SOA else tg.contiguous()
+    soa = layout == _lib.SOA
+    if mode == _lib.POSE_IK_OBJECTIVE:
+        val = torch.empty(N, dtype=Q.dtype, device=Q.device)
+        jac = torch.empty((nd, N) if soa else (N, nd), dtype=Q.dtype, device=Q.device)
+        jac_view = jac.t() if soa else jac
+    else:
+        val = torch.empty((rows, N) if soa else (N, rows), dtype=Q.dtype, device=Q.device)
+        jac = torch.empty((rows, nd, N) if soa else (N, rows, nd), dtype=Q.dtype, device=Q.device)
+        jac_view = jac.permute(2, 1, 0) if soa else jac.permute(0, 2, 1)          # (N, n_dof, dim)
+        val = val.t() if soa else val
+    _lib.check(_lib.lib().kin_pose_residual(
+        dm.h, _lib.F32 if Q.dtype == torch.float32 else _lib.F64, layout, Q.data_ptr(), N, link.id, tg.data_ptr(), per,
+        int(with_rot), mode, val.data_ptr(), jac.data_ptr(), torch.cuda.current_stream(Q.device).cuda_stream))
+    return val, jac_view
+
+
+def ik_objective(m: Mechanism, link, joints, target_pose, with_rot=True):
+    """``f_objective`` of inverse_kinematics.jl:38-50 at the configuration(s) of the last set_joint_angles:
+    f = sum(pose_diff^2), grad = -2 J' pose_diff with the Euler-rate Jacobian.
+    single -> (float, ndarray (n_dof,)); batch -> tensors (N,), (N, n_dof)."""
+    f, g = _pose_residual(m, link, joints, target_pose, with_rot, _lib.POSE_IK_OBJECTIVE)
+    if m._single:
+        return float(f[0]), g[0].double().cpu().numpy()
+    return f, g
+
+
+def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=True, iters=100, ftol=1e-10):
+    """Batched IK for N independent pose targets (config 4 of BASELINE.json): Levenberg-Marquardt with
+    per-problem adaptive damping and an active set for the joint limits on the reference's objective f = |[p - p_t; rpy - rpy_t]|^2
+    (inverse_kinematics.jl:38-50), iterates clamped to the joint limits (:52-63).  Every evaluation of the
+    residual and of its Euler-rate Jacobian is one libkin_b200 call over the whole batch; the 8x8 normal
+    equations are solved with torch.  Angle residuals are wrapped to (-pi, pi] for stepping.
+    ``targets`` (N, 6) [x y z roll pitch yaw], ``q0`` (N, n_dof).  Returns (q, f)."""
+    import torch
+    from .planning import pose_constraint
+    nb = 3 if m.with_base else 0
+    lo = torch.tensor([j.lower_limit for j in joints] + [-np.inf] * nb, device="cuda", dtype=torch.float64)
+    hi = torch.tensor([j.upper_limit for j in joints] + [np.inf] * nb, device="cuda", dtype=torch.float64)
+    q = torch.as_tensor(q0, dtype=torch.float64, device="cuda").clone()
+    N, nd = q.shape
+    eye = torch.eye(nd, dtype=torch.float64, device="cuda")
+
+    def evaluate(qq):
+        set_joint_angles(m, joints, qq)
+        e, JT = pose_constraint(m, link, joints, targets, with_rot)     # e (N, dim) = now - target, JT (N, nd, dim)
+        e = e.clone()
+        if with_rot:
+            e[:, 3:] = torch.remainder(e[:, 3:] + np.pi, 2 * np.pi) - np.pi
+        return e, JT, (e * e).sum(dim=1)
+
+    e, JT, f = evaluate(q)
+    lam = torch.full((N,), 1e-2, dtype=torch.float64, device="cuda")
+    for _ in range(iters):
+        H = JT @ JT.transpose(1, 2)
+        g = (JT @ e.unsqueeze(-1)).squeeze(-1)
+        # projected step: a joint sitting on a limit whose gradient pushes outward is frozen (active set)
+        free = ~(((q <= lo + 1e-12) & (g > 0)) | ((q >= hi - 1e-12) & (g < 0)))
+        fm = free.to(q.dtype)
+        H = H + lam[:, None, None] * (eye + torch.diag_embed(torch.diagonal(H, dim1=1, dim2=2)))
+        H = H * (fm[:, :, None] * fm[:, None, :]) + torch.diag_embed(1.0 - fm)
+        step = torch.linalg.solve(H, (g * fm).unsqueeze(-1)).squeeze(-1)
+        q_new = torch.minimum(torch.maximum(q - step, lo), hi)
+        e_new, JT_new, f_new = evaluate(q_new)
+        ok = f_new < f
+        q = torch.where(ok[:, None], q_new, q)
+        e = torch.where(ok[:, None], e_new, e)
+        JT = torch.where(ok[:, None, None], JT_new, JT)
+        f = torch.where(ok, f_new, f)
+        lam = torch.where(ok, lam * 0.3, lam * 4.0).clamp(1e-9, 1e4)
+        if float(f.max()) < ftol:
+            break
+    set_joint_angles(m, joints, q)
+    return q, f

@@ -15,6 +15,7 @@ SOA, AOS = 0, 1
 FIXED, REVOLUTE, PRISMATIC = 0, 1, 2
 GRAD_FD, GRAD_ANALYTIC = 0, 1
 SCRATCH_REFERENCE, SCRATCH_CLEAN = 0, 1
+POSE_IK_OBJECTIVE, POSE_CONSTRAINT = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -50,7 +51,7 @@ class KinCall(C.Structure):
 EXPORTS = ["kin_last_error", "kin_abi_version", "kin_model_create", "kin_model_destroy", "kin_model_set_spheres",
            "kin_model_set_boxes", "kin_model_n_dof", "kin_model_n_spheres", "kin_model_n_boxes", "kin_eval",
            "kin_eval_host", "kin_fk_links", "kin_fk_jacobian", "kin_collision", "kin_launch_count",
-           "kin_query_launch", "kin_sdf_points", "kin_program_dump"]
+           "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual"]
 
 
 def needs_build() -> bool:
@@ -99,6 +100,8 @@ def lib():
         L.kin_query_launch.argtypes = [C.c_void_p, C.POINTER(KinCall), _ip, _ip, _ip, _ip]
         L.kin_sdf_points.argtypes = [C.c_int32, _dp, _dp, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kin_pose_residual.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kin_program_dump.argtypes = [C.POINTER(KinModelDesc), _ip, C.c_int32, _ip, C.c_int32, C.c_int32, C.c_int32,
                                        _ip, C.c_int32, _ip, C.c_int32, _dp, C.c_int32]
         _LIB = L

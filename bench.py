@@ -151,10 +151,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1 << 24, help="configurations per GPU")
-    ap.add_argument("--n-e2e", type=int, default=1 << 21, help="configurations per e2e step (host buffers)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-north-star", action="store_true")
+    ap.add_argument("--configs", dest="n", type=int, default=1 << 24, help="configurations per GPU")
+    ap.add_argument("--configs-e2e", dest="n_e2e", type=int, default=1 << 21, help="configurations per e2e step (host buffers)")
+    ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-north-star", dest="no_north_star", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_main(args)

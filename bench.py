@@ -275,6 +275,42 @@ def main():
                               "launch": launch_info(callf)}}
         del V, G
 
+    # ---- other rows of BASELINE.md section 3, same batch (reported, not the headline) ----
+    variants = {}
+    if not args.no_north_star:
+        def variant(name, bytes_per_cfg, call_):
+            tms_, per_, _ = timed(call_, max(3, args.steps // 2), W)
+            ms_ = float(np.mean(per_))
+            variants[name] = {"value": world * N / (ms_ * 1e-3), "unit": UNIT, "ms_per_step": ms_,
+                              "algorithmic_bytes_per_config": bytes_per_cfg,
+                              "hbm_frac": bytes_per_cfg * N / (ms_ * 1e-3) / 1e9 / peak, "launch": launch_info(call_)}
+        cg = make_call(N, Q.data_ptr(), T.data_ptr(), J.data_ptr())
+        cg.n_fk_links, cg.fk_links = 1, jac_ids.ctypes.data_as(ip)
+        variant("fk_gripper+gripper_jacobian", 8 * N_DOF + 96 + 384, cg)
+        V = torch.empty((N_SPH, N), dtype=torch.float64, device=dev)
+        G = torch.empty((N_SPH * N_DOF, N), dtype=torch.float64, device=dev)
+        cc = make_call(N, Q.data_ptr(), None, None, V.data_ptr(), G.data_ptr())
+        cc.n_fk_links = cc.n_jac_links = 0
+        variant("collision_cost_grad(S=16,B=7,fd,reference-scratch)", 8 * N_DOF + 8 * N_SPH + 8 * N_SPH * N_DOF, cc)
+        cc2 = make_call(N, Q.data_ptr(), None, None, V.data_ptr(), G.data_ptr())
+        cc2.n_fk_links = cc2.n_jac_links = 0
+        cc2.grad_mode, cc2.scratch_mode = L.GRAD_ANALYTIC, L.SCRATCH_CLEAN
+        variant("collision_cost_grad(S=16,B=7,analytic,clean-scratch)", 8 * N_DOF + 8 * N_SPH + 8 * N_SPH * N_DOF, cc2)
+        del V, G
+        # the fused step in the AoS layout (one contiguous record per configuration, planning.jl:58)
+        Na = min(N, 1 << 22)
+        Qa = Q[:, :Na].t().contiguous()
+        Ta = torch.empty((Na, N_LINKS * 12), dtype=torch.float64, device=dev)
+        Ja = torch.empty((Na, 6 * N_DOF), dtype=torch.float64, device=dev)
+        Va = torch.empty((Na, N_SPH), dtype=torch.float64, device=dev)
+        Ga = torch.empty((Na, N_SPH * N_DOF), dtype=torch.float64, device=dev)
+        ca = make_call(Na, Qa.data_ptr(), Ta.data_ptr(), Ja.data_ptr(), Va.data_ptr(), Ga.data_ptr(), layout=L.AOS)
+        tms_, per_, _ = timed(ca, max(3, args.steps // 2), W)
+        ms_ = float(np.mean(per_))
+        variants["fused_aos_layout"] = {"value": world * Na / (ms_ * 1e-3), "unit": UNIT, "ms_per_step": ms_, "configs": Na,
+                                        "hbm_frac": BYTES_FUSED * Na / (ms_ * 1e-3) / 1e9 / peak, "launch": launch_info(ca)}
+        del Qa, Ta, Ja, Va, Ga
+
     # ---- e2e: the C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region ----
     Ne = min(args.n_e2e, N)
     qh = torch.empty((N_DOF, Ne), dtype=torch.float64).pin_memory()
@@ -315,7 +351,7 @@ def main():
                            "n_dof": N_DOF, "configs_per_gpu": N, "layout": "soa", "parallelism": "batch-shard x%d, no collective" % world,
                            "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % (BYTES_FKJ * N / 1e9)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "north_star": north}
+                "north_star": north, "variants": variants}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -57,18 +57,24 @@ __device__ __forceinline__ float relu_(float x) { return fmaxf(x, 0.0f); }
 // out = a * b  (a: running transform, b: constant from the table at `c`, R row-major then t)
 template <typename real>
 __device__ __forceinline__ void tf_mul_const(const Tf<real> &a, const real *__restrict__ c, bool r_identity, Tf<real> &o) {
+    // the table row goes to registers first: the compiler cannot prove that scratch stores in between do
+    // not alias the table and would otherwise re-load every operand
+    const real t0 = c[9], t1 = c[10], t2 = c[11];
     #pragma unroll
     for (int i = 0; i < 3; ++i)
-        o.p[i] = fma_(a.r[i * 3 + 0], c[9], fma_(a.r[i * 3 + 1], c[10], fma_(a.r[i * 3 + 2], c[11], a.p[i])));
+        o.p[i] = fma_(a.r[i * 3 + 0], t0, fma_(a.r[i * 3 + 1], t1, fma_(a.r[i * 3 + 2], t2, a.p[i])));
     if (r_identity) {
         #pragma unroll
         for (int i = 0; i < 9; ++i) o.r[i] = a.r[i];
     } else {
+        real m[9];
+        #pragma unroll
+        for (int i = 0; i < 9; ++i) m[i] = c[i];
         #pragma unroll
         for (int i = 0; i < 3; ++i)
             #pragma unroll
             for (int j = 0; j < 3; ++j)
-                o.r[i * 3 + j] = fma_(a.r[i * 3 + 0], c[j], fma_(a.r[i * 3 + 1], c[3 + j], a.r[i * 3 + 2] * c[6 + j]));
+                o.r[i * 3 + j] = fma_(a.r[i * 3 + 0], m[j], fma_(a.r[i * 3 + 1], m[3 + j], a.r[i * 3 + 2] * m[6 + j]));
     }
 }
 
@@ -171,6 +177,17 @@ __device__ __forceinline__ void rpy_rate_coeffs(const Tf<real> &T, real k[6]) {
     k[0] = cy * ic2; k[1] = -sy * ic2; k[2] = -sy; k[3] = cy; k[4] = cy * sp * ic2; k[5] = sy * sp * ic2;
 }
 
+// cp.async of one element global -> shared (LDGSTS): the next tile's configuration lands in the scratch
+// while the current tile is being computed
+__device__ __forceinline__ void cp_async_elem(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_elem(float *smem_dst, const float *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 constexpr int SPH_GROUP = 4;   // spheres evaluated together against each box row (register blocking)
 constexpr int JF_REGS = 8;     // joint frames kept in registers when the model has at most this many columns
 static_assert(JF_REGS == 8, "the switch statements in kin_eval_kernel enumerate 8 cases");
@@ -218,6 +235,11 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     // The planar base is compiled into three ordinary nodes (prismatic x, y; revolute z), so every one of
     // the ND columns is an ordinary joint column here; DC = columns that are control joints.
     const int DC = h.n_joints, ND = h.n_dof;
+    // header fields used in loops, as locals (kernel parameters are otherwise re-read from the constant bank)
+    const int n_nodes = h.n_nodes, n_box = h.n_box, S = h.n_sph, n_fk = h.n_fk;
+    const int io_node = h.io_node, io_att = h.io_att, io_sph_order = h.io_sph_order, io_sph_mask = h.io_sph_mask;
+    const int ro_node = h.ro_node, ro_att = h.ro_att, ro_sph = h.ro_sph, ro_box = h.ro_box;
+    const int so_save = h.so_save, so_cent = h.so_cent;
     unsigned rev_mask = 0;              // bit j: column j is a revolute joint
     for (int j = 0; j < ND; ++j) rev_mask |= (ti[h.io_col_type + j] == 1 ? 1u : 0u) << j;
     real *jf0 = &SCR(h.so_jf);          // JR == 0 only
@@ -236,26 +258,35 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     // for (j = 0; j < ND; ++j): unrolled to JR iterations with an early exit, or rolled
     #define FOR_COLUMNS(j) _Pragma("unroll") for (int j = 0; j < (JR > 0 ? JR : ND); ++j) if (JR > 0 && j >= ND) break; else
 
-    const long long n_tiles = (A.n + BS - 1) / BS;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long n = tile * BS + tid;
-        if (n >= A.n) continue;      // no block-level sync below this point
-
-        // ---- configuration -> scratch (all loads in flight together) ----
-        {
-            const real *qn = reinterpret_cast<const real *>(A.q) + (AOS ? n * ND : n);
-            #pragma unroll 4
-            for (int c = 0; c < ND; ++c) SCR(h.so_q + c) = qn[c * es];
+    // configuration -> scratch with cp.async, double-buffered across tiles (buffers so_q / so_q2)
+    const int q_stride = h.so_q2 - h.so_q;
+    auto prefetch_q = [&](long long tile_, int buf) {
+        const long long n_ = tile_ * BS + tid;
+        if (n_ < A.n) {
+            const real *qn = reinterpret_cast<const real *>(A.q) + (AOS ? n_ * ND : n_);
+            real *dst = &SCR(h.so_q + buf * q_stride);
+            for (int c = 0; c < ND; ++c) cp_async_elem(dst + c * BS, qn + c * es);
         }
-        real *Tn = reinterpret_cast<real *>(A.T_out) + (AOS ? n * (12 * h.n_fk) : n);
+        cp_async_commit();
+    };
+    const long long n_tiles = (A.n + BS - 1) / BS;
+    if ((long long)blockIdx.x < n_tiles) prefetch_q(blockIdx.x, 0);
+    int buf = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        const long long n = tile * BS + tid;
+        if (tile + gridDim.x < n_tiles) { prefetch_q(tile + gridDim.x, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        if (n >= A.n) continue;      // no block-level sync below this point
+        const int so_q = h.so_q + buf * q_stride;
+        real *Tn = reinterpret_cast<real *>(A.T_out) + (AOS ? n * (12 * n_fk) : n);
         real *Jn = reinterpret_cast<real *>(A.J_out) + (AOS ? n * (rows * ND * h.n_jac) : n);
 
         Tf<real> T;                   // running world transform of the current node
 
         // =========================== phase 1 ===========================
-        for (int node = 0; node < h.n_nodes; ++node) {
-            const int32_t *ni = ti + h.io_node + node * NODE_INTS;
-            const real *nr = tr + h.ro_node + node * NODE_REALS;
+        for (int node = 0; node < n_nodes; ++node) {
+            const int32_t *ni = ti + io_node + node * NODE_INTS;
+            const real *nr = tr + ro_node + node * NODE_REALS;
             const int jtype = ni[1];
             if (jtype == NODE_ROOT) {
                 #pragma unroll
@@ -264,7 +295,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
             } else {
                 const int psrc = ni[0], flags = ni[2], qcol = ni[3];
                 if (psrc >= 0) {
-                    const real *sv = &SCR(h.so_save + 12 * psrc);
+                    const real *sv = &SCR(so_save + 12 * psrc);
                     #pragma unroll
                     for (int i = 0; i < 9; ++i) T.r[i] = sv[i * BS];
                     #pragma unroll
@@ -298,7 +329,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     jf[0] = f.o[0]; jf[BS] = f.o[1]; jf[2 * BS] = f.o[2];
                     jf[3 * BS] = f.a[0]; jf[4 * BS] = f.a[1]; jf[5 * BS] = f.a[2];
                 }
-                const real qa = SCR(h.so_q + qcol);
+                const real qa = SCR(so_q + qcol);
                 T = Aj;
                 if (jtype == 2) {          // prismatic: pose * Trans(axis * a), mechanism.jl:100-103
                     T.p[0] = fma_(f.a[0], qa, Aj.p[0]); T.p[1] = fma_(f.a[1], qa, Aj.p[1]); T.p[2] = fma_(f.a[2], qa, Aj.p[2]);
@@ -335,7 +366,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 }
             }
             if (ni[4] >= 0) {
-                real *sv = &SCR(h.so_save + 12 * ni[4]);
+                real *sv = &SCR(so_save + 12 * ni[4]);
                 #pragma unroll
                 for (int i = 0; i < 9; ++i) sv[i * BS] = T.r[i];
                 #pragma unroll
@@ -344,8 +375,8 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
 
             // ---- requested links hanging from this node ----
             for (int a = ni[5]; a < ni[6]; ++a) {
-                const int32_t *ai = ti + h.io_att + a * ATT_INTS;
-                const real *ar = tr + h.ro_att + a * ATT_REALS;
+                const int32_t *ai = ti + io_att + a * ATT_INTS;
+                const real *ar = tr + ro_att + a * ATT_REALS;
                 Tf<real> Tl;
                 tf_mul_const(T, ar, ai[1] & AF_R_IDENTITY, Tl);
                 if (ai[0] >= 0 && A.T_out) {       // get_transform, as 3x4 column-major
@@ -409,19 +440,19 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
             // ---- collision-sphere centres on this node (collision.jl:54 / :80) ----
             if (COLL) {
                 for (int k = ni[7]; k < ni[8]; ++k) {
-                    const int s = ti[h.io_sph_order + k];
-                    const real *sr = tr + h.ro_sph + s * SPH_REALS;
-                    real *cs = &SCR(h.so_cent + 3 * s);
+                    const int s = ti[io_sph_order + k];
+                    const real *sr = tr + ro_sph + s * SPH_REALS;
+                    const real c0 = sr[0], c1 = sr[1], c2 = sr[2];
+                    real *cs = &SCR(so_cent + 3 * s);
                     #pragma unroll
                     for (int i = 0; i < 3; ++i)
-                        cs[i * BS] = fma_(T.r[i * 3 + 0], sr[0], fma_(T.r[i * 3 + 1], sr[1], fma_(T.r[i * 3 + 2], sr[2], T.p[i])));
+                        cs[i * BS] = fma_(T.r[i * 3 + 0], c0, fma_(T.r[i * 3 + 1], c1, fma_(T.r[i * 3 + 2], c2, T.p[i])));
                 }
             }
         }
 
         // =========================== phase 2 ===========================
         if (COLL) {
-            const int S = h.n_sph;
             const bool want_grads = A.grads_out != nullptr;
             const bool stale = want_grads && A.scratch_ref;
             const real trunc = (real)A.truncation_dist, voff = (real)A.vals_offset;
@@ -430,7 +461,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
             real *Vp = reinterpret_cast<real *>(A.vals_out) + (AOS ? n * S : n);
             real *Gp = reinterpret_cast<real *>(A.grads_out) + (AOS ? n * ((long long)ND * S) : n);
             int32_t *Ap = A.argmin_out ? A.argmin_out + (AOS ? n * S : n) : nullptr;
-            real *hand = &SCR(h.so_q);      // q is dead: (dmin, argmin) of the current sphere group
+            real *hand = &SCR(so_q);      // q is dead: (dmin, argmin) of the current sphere group
 
             for (int s0 = 0; s0 < S; s0 += SPH_GROUP) {
                 // ---- 2a: distances of SPH_GROUP spheres; one box-table row feeds all of them ----
@@ -439,14 +470,14 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     int kidx[SPH_GROUP];
                     #pragma unroll
                     for (int g = 0; g < SPH_GROUP; ++g) {
-                        const real *cs = &SCR(h.so_cent + 3 * min(s0 + g, S - 1));
+                        const real *cs = &SCR(so_cent + 3 * min(s0 + g, S - 1));
                         px[g] = cs[0]; py[g] = cs[BS]; pz[g] = cs[2 * BS];
                         kmin[g] = CUDART_INF; kidx[g] = 0;
                     }
                     // UnionSDF: all boxes, first minimum wins (sdf.jl:108-114)
-                    for (int b = 0; b < h.n_box; ++b) {
+                    for (int b = 0; b < n_box; ++b) {
                         BoxRow<real> row;
-                        load_box(tr + h.ro_box + b * BOX_REALS, row);
+                        load_box(tr + ro_box + b * BOX_REALS, row);
                         #pragma unroll
                         for (int g = 0; g < SPH_GROUP; ++g) {
                             const real key = box_key(row, px[g], py[g], pz[g]);
@@ -455,7 +486,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     }
                     #pragma unroll
                     for (int g = 0; g < SPH_GROUP; ++g) {
-                        hand[g * BS] = kmin[g];      // the key; converted to a distance once, in 2b
+                        hand[g * BS] = key_to_dist(kmin[g]);     // four independent sqrt chains interleave here
                         reinterpret_cast<int *>(&hand[(SPH_GROUP + g) * BS])[0] = kidx[g];
                     }
                 }
@@ -464,26 +495,27 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 #pragma unroll 1
                 for (int g = 0; g < SPH_GROUP && s0 + g < S; ++g) {
                     const int s = s0 + g;
-                    const real dmin = key_to_dist(hand[g * BS]);
+                    const real dmin = hand[g * BS];
                     const int kmin = reinterpret_cast<const int *>(&hand[(SPH_GROUP + g) * BS])[0];
-                    const real dist0 = dmin - tr[h.ro_sph + s * SPH_REALS + 3];
+                    const real dist0 = dmin - tr[ro_sph + s * SPH_REALS + 3];
                     const bool truncated = dist0 > trunc;
-                    Vp[s * es] = (truncated ? trunc : dist0) - voff;
-                    if (Ap) Ap[s * es] = kmin + 1;
+                    *Vp = (truncated ? trunc : dist0) - voff;
+                    Vp += es;
+                    if (Ap) { *Ap = kmin + 1; Ap += es; }
                     if (!want_grads) continue;
                     if (truncated) {            // collision.jl:84-86
                         for (int j = 0; j < ND; ++j, Gp += es) *Gp = real(0);
                         continue;
                     }
-                    const real *cs = &SCR(h.so_cent + 3 * s);
+                    const real *cs = &SCR(so_cent + 3 * s);
                     const real px = cs[0], py = cs[BS], pz = cs[2 * BS];
                     real grad[3];
                     {
                         BoxRow<real> row;
-                        load_box(tr + h.ro_box + kmin * BOX_REALS, row);
+                        load_box(tr + ro_box + kmin * BOX_REALS, row);
                         box_gradient(row, A.grad_mode, px, py, pz, dmin, grad);
                     }
-                    const unsigned mask = (unsigned)ti[h.io_sph_mask + s];
+                    const unsigned mask = (unsigned)ti[io_sph_mask + s];
                     const real *jf = jf0;
                     real *st = stale0;
                     FOR_COLUMNS(j) {

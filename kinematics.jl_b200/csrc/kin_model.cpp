@@ -320,7 +320,9 @@ bool compile_program(const HostModel &m, const std::vector<int> &fk_links, const
     // ---- per-thread scratch map ----
     // so_q doubles as the per-group (dmin, argmin) hand-over of the collision phase: 2 * SPH_GROUP slots
     int so = 0;
-    h.so_q = so;      so += std::max(h.n_dof, S > 0 ? 8 : 0);
+    const int q_slots = std::max(std::max(h.n_dof, 1), S > 0 ? 8 : 0);
+    h.so_q = so;      so += q_slots;
+    h.so_q2 = so;     so += q_slots;
     h.so_save = so;   so += 12 * max_slots;
     h.so_jf = so;     so += (want_coll && jf_regs > 0 && h.n_dof <= jf_regs) ? 0 : 6 * h.n_dof;   // frames in registers: no slots
     h.so_cent = so;   so += 3 * S;

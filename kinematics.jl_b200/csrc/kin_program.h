@@ -57,6 +57,7 @@ struct ProgHeader {
     int n_real;
     // per-thread scratch slots (in reals)
     int so_q, so_save, so_jf, so_cent, so_stale, n_slots;
+    int so_q2;                  // second configuration buffer (the next tile is prefetched with cp.async)
 };
 
 }  // namespace kin

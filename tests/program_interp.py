@@ -13,7 +13,7 @@ NODE_INTS, NODE_REALS, ATT_INTS, ATT_REALS, SPH_REALS, BOX_REALS = 12, 16, 4, 12
 HEADER_FIELDS = ["n_nodes", "n_att", "n_sph", "n_box", "n_joints", "with_base", "n_dof", "n_fk", "n_jac",
                  "io_node", "io_att", "io_sph_order", "io_sph_mask", "io_col_type", "n_int",
                  "ro_node", "ro_att", "ro_sph", "ro_box", "n_real",
-                 "so_q", "so_save", "so_jf", "so_cent", "so_stale", "n_slots"]
+                 "so_q", "so_save", "so_jf", "so_cent", "so_stale", "n_slots", "so_q2"]
 
 
 def dump_program(mech, ctrl_ids, fk_ids, jac_ids, spheres=None, boxes=None, want_stale=True):

@@ -103,14 +103,20 @@ __device__ __noinline__ real box_inside_key(real qx, real qy, real qz) {   // ra
     t = t > qz ? t : qz;
     return t < real(0) ? t : real(0);
 }
+// outside part of the key and the q vector (needed only if the key turns out to be zero)
 template <typename real>
-__device__ __forceinline__ real box_key(const BoxRow<real> &b, real px, real py, real pz) {
+__device__ __forceinline__ real box_key_outside(const BoxRow<real> &b, real px, real py, real pz, real &qx, real &qy, real &qz) {
     const real lx = fma_(b.r[0], px, fma_(b.r[1], py, fma_(b.r[2], pz, b.t[0])));
     const real ly = fma_(b.r[3], px, fma_(b.r[4], py, fma_(b.r[5], pz, b.t[1])));
     const real lz = fma_(b.r[6], px, fma_(b.r[7], py, fma_(b.r[8], pz, b.t[2])));
-    const real qx = abs_(lx) - b.h[0], qy = abs_(ly) - b.h[1], qz = abs_(lz) - b.h[2];
+    qx = abs_(lx) - b.h[0]; qy = abs_(ly) - b.h[1]; qz = abs_(lz) - b.h[2];
     const real mx = qx + abs_(qx), my = qy + abs_(qy), mz = qz + abs_(qz);
-    real key = fma_(mx, mx, fma_(my, my, mz * mz));
+    return fma_(mx, mx, fma_(my, my, mz * mz));
+}
+template <typename real>
+__device__ __forceinline__ real box_key(const BoxRow<real> &b, real px, real py, real pz) {
+    real qx, qy, qz;
+    real key = box_key_outside(b, px, py, pz, qx, qy, qz);
     if (!(key > real(0))) key = box_inside_key(qx, qy, qz);
     return key;
 }
@@ -478,11 +484,21 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     for (int b = 0; b < n_box; ++b) {
                         BoxRow<real> row;
                         load_box(tr + ro_box + b * BOX_REALS, row);
+                        real key[SPH_GROUP], qx[SPH_GROUP], qy[SPH_GROUP], qz[SPH_GROUP];
+                        bool any_inside = false;
                         #pragma unroll
                         for (int g = 0; g < SPH_GROUP; ++g) {
-                            const real key = box_key(row, px[g], py[g], pz[g]);
-                            if (key < kmin[g]) { kmin[g] = key; kidx[g] = b; }
+                            key[g] = box_key_outside(row, px[g], py[g], pz[g], qx[g], qy[g], qz[g]);
+                            any_inside |= !(key[g] > real(0));
                         }
+                        if (any_inside) {       // rare: some centre is inside (or on) this box -- one branch per row
+                            #pragma unroll
+                            for (int g = 0; g < SPH_GROUP; ++g)
+                                if (!(key[g] > real(0))) key[g] = box_inside_key(qx[g], qy[g], qz[g]);
+                        }
+                        #pragma unroll
+                        for (int g = 0; g < SPH_GROUP; ++g)
+                            if (key[g] < kmin[g]) { kmin[g] = key[g]; kidx[g] = b; }
                     }
                     #pragma unroll
                     for (int g = 0; g < SPH_GROUP; ++g) {

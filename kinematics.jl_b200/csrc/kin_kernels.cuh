@@ -153,11 +153,21 @@ template <typename real>
 __device__ __forceinline__ void box_gradient(const BoxRow<real> &b, int grad_mode, real px, real py, real pz, real dmin, real g[3]) {
     if (grad_mode == 0) {
         // (f(p + eps e_i) - f(p)) / eps with eps = 1e-7; the division is done as a multiplication by 1e7
-        // (differs from x / 1e-7 by at most 1 ulp of the quotient, far below the FD truncation error)
+        // (differs from x / 1e-7 by at most 1 ulp of the quotient, far below the FD truncation error).
+        // The three evaluations share ONE rare "inside the box" branch so that their dependency chains
+        // interleave (a data-dependent branch per evaluation costs ~35 cycles and serialises them).
         const real eps = real(1e-7), ieps = real(1e7);
-        g[0] = (key_to_dist(box_key(b, px + eps, py, pz)) - dmin) * ieps;
-        g[1] = (key_to_dist(box_key(b, px, py + eps, pz)) - dmin) * ieps;
-        g[2] = (key_to_dist(box_key(b, px, py, pz + eps)) - dmin) * ieps;
+        real k[3], qx[3], qy[3], qz[3];
+        k[0] = box_key_outside(b, px + eps, py, pz, qx[0], qy[0], qz[0]);
+        k[1] = box_key_outside(b, px, py + eps, pz, qx[1], qy[1], qz[1]);
+        k[2] = box_key_outside(b, px, py, pz + eps, qx[2], qy[2], qz[2]);
+        if (!(k[0] > real(0)) || !(k[1] > real(0)) || !(k[2] > real(0))) {
+            #pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (!(k[i] > real(0))) k[i] = box_inside_key(qx[i], qy[i], qz[i]);
+        }
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) g[i] = (key_to_dist(k[i]) - dmin) * ieps;
     } else {
         box_grad_analytic(b, px, py, pz, g);
     }

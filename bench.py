@@ -297,6 +297,17 @@ def main():
         cc2.grad_mode, cc2.scratch_mode = L.GRAD_ANALYTIC, L.SCRATCH_CLEAN
         variant("collision_cost_grad(S=16,B=7,analytic,clean-scratch)", 8 * N_DOF + 8 * N_SPH + 8 * N_SPH * N_DOF, cc2)
         del V, G
+        # the tiled (AoSoA-32) layout: one contiguous block per warp
+        Qt = Q.t().reshape(N // 32, 32, N_DOF).permute(0, 2, 1).contiguous()
+        Tt = torch.empty((N // 32, N_LINKS * 12, 32), dtype=torch.float64, device=dev)
+        Jt = torch.empty((N // 32, 6 * N_DOF, 32), dtype=torch.float64, device=dev)
+        ct = make_call(N, Qt.data_ptr(), Tt.data_ptr(), Jt.data_ptr(), layout=L.TILED32)
+        variant("fk_all_links+gripper_jacobian_tiled32_layout", BYTES_FKJ, ct)
+        Vt = torch.empty((N // 32, N_SPH, 32), dtype=torch.float64, device=dev)
+        Gt = torch.empty((N // 32, N_SPH * N_DOF, 32), dtype=torch.float64, device=dev)
+        ctf = make_call(N, Qt.data_ptr(), Tt.data_ptr(), Jt.data_ptr(), Vt.data_ptr(), Gt.data_ptr(), layout=L.TILED32)
+        variant("fused_tiled32_layout", BYTES_FUSED, ctf)
+        del Qt, Tt, Jt, Vt, Gt
         # the fused step in the AoS layout (one contiguous record per configuration, planning.jl:58)
         Na = min(N, 1 << 22)
         Qa = Q[:, :Na].t().contiguous()

@@ -26,6 +26,9 @@
  *                       = Julia Array of size (n_dof, N), (3, 4, L, N), (rows, cols, n_req, N), (n_dof, S, N)
  *                         i.e. the per-configuration arrays of the reference stacked along a last axis
  *                         (xi of planning.jl:58 is exactly (n_dof, n_wp)).
+ *       KIN_LAYOUT_TILED32  AoSoA with 32 configurations per tile: x[((n / 32) * rec + comp) * 32 + n % 32]
+ *                       = Julia Array of size (32, rec, cld(N, 32)); every buffer holds whole tiles (N rounded up
+ *                         to a multiple of 32).  One warp reads / writes one contiguous block: the fastest layout.
  *     `ld` (batch_stride) is the SoA distance between consecutive components, >= N; 0 means N.
  *   - a transform is written as 3x4 column-major (k = col*3 + row: R columns then t); the constant
  *     bottom row of the reference's 4x4 is not materialised.
@@ -65,7 +68,7 @@ typedef enum {
 } KinStatus;
 
 typedef enum { KIN_F64 = 0, KIN_F32 = 1 } KinPrecision;
-typedef enum { KIN_LAYOUT_SOA = 0, KIN_LAYOUT_AOS = 1 } KinLayout;
+typedef enum { KIN_LAYOUT_SOA = 0, KIN_LAYOUT_AOS = 1, KIN_LAYOUT_TILED32 = 2 } KinLayout;
 typedef enum { KIN_JOINT_FIXED = 0, KIN_JOINT_REVOLUTE = 1, KIN_JOINT_PRISMATIC = 2 } KinJointType;
 /* sdf.jl:34-41,116-119 is a forward difference (eps 1e-7) on the argmin box; KIN_GRAD_ANALYTIC is
  * the closed form of the same box (an extension, off by default). */

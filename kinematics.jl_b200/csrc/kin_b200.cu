@@ -40,9 +40,9 @@ struct DeviceProgram {
     double *d_r64 = nullptr;
     float *d_r32 = nullptr;
     // launch configuration per (precision, layout)
-    int block[2][2] = {{0, 0}, {0, 0}}, occ[2][2] = {{0, 0}, {0, 0}}, regs[2][2] = {{0, 0}, {0, 0}};
-    int bs_index[2][2] = {{0, 0}, {0, 0}};
-    size_t smem[2][2] = {{0, 0}, {0, 0}};
+    int block[2][3] = {{0, 0, 0}, {0, 0, 0}}, occ[2][3] = {{0, 0, 0}, {0, 0, 0}}, regs[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    int bs_index[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    size_t smem[2][3] = {{0, 0, 0}, {0, 0, 0}};
 };
 
 struct HostStage {          // resources of kin_eval_host, created on first use
@@ -138,12 +138,12 @@ constexpr int kNumBS = 4;
 const int kBS[kNumBS] = {128, 96, 64, 32};
 
 // [precision][layout][block size][collision][joint frames in registers]
-#define KIN_K(real, aos, bs, coll) {kin::kin_eval_kernel<real, aos, bs, coll, 0>, kin::kin_eval_kernel<real, aos, bs, coll, kin::JF_REGS>}
+#define KIN_K(real, lay, bs, coll) {kin::kin_eval_kernel<real, lay, bs, coll, 0>, kin::kin_eval_kernel<real, lay, bs, coll, kin::JF_REGS>}
 #define KIN_BS_ROW(real, aos) \
     {{KIN_K(real, aos, 128, false), KIN_K(real, aos, 128, true)}, {KIN_K(real, aos, 96, false), KIN_K(real, aos, 96, true)}, \
      {KIN_K(real, aos, 64, false), KIN_K(real, aos, 64, true)}, {KIN_K(real, aos, 32, false), KIN_K(real, aos, 32, true)}}
-const KernelFn kKernels[2][2][kNumBS][2][2] = {{KIN_BS_ROW(double, false), KIN_BS_ROW(double, true)},
-                                               {KIN_BS_ROW(float, false), KIN_BS_ROW(float, true)}};
+const KernelFn kKernels[2][3][kNumBS][2][2] = {{KIN_BS_ROW(double, 0), KIN_BS_ROW(double, 1), KIN_BS_ROW(double, 2)},
+                                               {KIN_BS_ROW(float, 0), KIN_BS_ROW(float, 1), KIN_BS_ROW(float, 2)}};
 
 int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
     const kin::ProgHeader &h = dp->prog.h;
@@ -215,7 +215,7 @@ int get_program(KinModel *m, const KinCall *c, DeviceProgram **out) {
         it = m->cache.emplace(key, dp).first;
     }
     DeviceProgram *dp = it->second;
-    const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout == KIN_LAYOUT_AOS ? 1 : 0;
+    const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
     if (dp->block[pi][li] == 0) {
         int rc = configure(m, dp, pi, li);
         if (rc != KIN_OK) return rc;
@@ -227,7 +227,7 @@ int get_program(KinModel *m, const KinCall *c, DeviceProgram **out) {
 int validate_call(const KinModel *m, const KinCall *c) {
     if (!m || !c) return fail(KIN_ERR_INVALID_ARGUMENT, "null model or call");
     if (c->precision != KIN_F64 && c->precision != KIN_F32) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown precision");
-    if (c->layout != KIN_LAYOUT_SOA && c->layout != KIN_LAYOUT_AOS) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown layout");
+    if (c->layout != KIN_LAYOUT_SOA && c->layout != KIN_LAYOUT_AOS && c->layout != KIN_LAYOUT_TILED32) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown layout");
     if (c->n < 0) return fail(KIN_ERR_INVALID_ARGUMENT, "negative batch size");
     if (c->n > 0 && !c->q) return fail(KIN_ERR_INVALID_ARGUMENT, "q is null");
     if (c->batch_stride != 0 && c->batch_stride < c->n) return fail(KIN_ERR_INVALID_ARGUMENT, "batch_stride < n");
@@ -244,7 +244,7 @@ int validate_call(const KinModel *m, const KinCall *c) {
 }
 
 int launch(KinModel *m, const KinCall *c, DeviceProgram *dp, cudaStream_t stream) {
-    const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout == KIN_LAYOUT_AOS ? 1 : 0;
+    const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
     kin::KernelArgs a;
     std::memset(&a, 0, sizeof a);
     a.h = dp->prog.h;
@@ -368,7 +368,7 @@ int kin_query_launch(KinModel *m, const KinCall *c, int32_t *regs, int32_t *smem
     DeviceProgram *dp = nullptr;
     rc = get_program(m, c, &dp);
     if (rc != KIN_OK) return rc;
-    const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout == KIN_LAYOUT_AOS ? 1 : 0;
+    const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
     const int b = dp->block[pi][li];
     long long tiles = (c->n + b - 1) / b, g = (long long)dp->occ[pi][li] * m->n_sm;
     if (g > tiles) g = tiles;
@@ -416,7 +416,8 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
         if (!st.stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&st.stream[i], cudaStreamNonBlocking));
 
     const long long N = c->n, ldh = c->batch_stride ? c->batch_stride : N;
-    const bool aos = c->layout == KIN_LAYOUT_AOS;
+    const bool aos = c->layout != KIN_LAYOUT_SOA;          // AoS and tiled: one contiguous block per chunk
+    const bool tiled = c->layout == KIN_LAYOUT_TILED32;
     int k = 0;
     for (long long n0 = 0; n0 < N; n0 += chunk, k = (k + 1) % HostStage::kStreams) {
         const long long mcount = (N - n0 < chunk) ? N - n0 : chunk;
@@ -430,7 +431,8 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
         auto copy = [&](void *dev, const void *host_c, void *host_m, size_t comps, size_t esz, bool to_dev) -> cudaError_t {
             if (comps == 0) return cudaSuccess;
             if (aos) {
-                const size_t bytes = esz * comps * mcount, hoff = esz * comps * n0;
+                const size_t cnt = tiled ? (size_t)((mcount + 31) / 32 * 32) : (size_t)mcount;   // chunk starts are multiples of 32
+                const size_t bytes = esz * comps * cnt, hoff = esz * comps * n0;
                 return to_dev ? cudaMemcpyAsync(dev, (const unsigned char *)host_c + hoff, bytes, cudaMemcpyHostToDevice, s)
                               : cudaMemcpyAsync((unsigned char *)host_m + hoff, dev, bytes, cudaMemcpyDeviceToHost, s);
             }
@@ -510,6 +512,7 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
     if (!m) return fail(KIN_ERR_INVALID_ARGUMENT, "null model");
     if (n < 0 || (n > 0 && (!q || !target || !val_out || !jac_out))) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
     if (mode != KIN_POSE_IK_OBJECTIVE && mode != KIN_POSE_CONSTRAINT) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown pose mode");
+    if (layout != KIN_LAYOUT_SOA && layout != KIN_LAYOUT_AOS) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_pose_residual supports the SoA and AoS layouts");
     if (n == 0) return KIN_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t es = precision == KIN_F32 ? 4 : 8;

@@ -227,9 +227,12 @@ __device__ __forceinline__ void jac_col(const JFrame<real> &f, bool revolute, re
 // of 64 threads, 2 warps per sub-partition) may use up to 255 registers per thread, while a 9th warp
 // would cap every thread at 168 and spill.  With the frames in registers the collision kernel is
 // therefore built for 4 x 64 threads per SM.
-template <typename real, bool AOS, int BS, bool COLL, int JR>
+template <typename real, int LAY, int BS, bool COLL, int JR>
 __global__ void __launch_bounds__(BS, (JR > 0 && COLL) ? (BS == 64 ? 4 : BS == 128 ? 2 : BS == 32 ? 8 : 2) : 1)
 kin_eval_kernel(const __grid_constant__ KernelArgs A) {
+    // LAY: 0 = SoA (x[comp * ld + n]), 1 = AoS (x[n * rec + comp]), 2 = tiled (AoSoA-32:
+    // x[((n / 32) * rec + comp) * 32 + n % 32], one contiguous block per warp, immediate offsets)
+    constexpr bool AOS = LAY == 1, TILED = LAY == 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ProgHeader &h = A.h;
     int32_t *ti = reinterpret_cast<int32_t *>(smem_raw);
@@ -262,7 +265,11 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     real *stale0 = &SCR(h.so_stale);
     const int rows = A.with_rot ? 6 : 3;
     // distance between consecutive components of one configuration's record
-    const size_t es = AOS ? size_t(1) : (size_t)A.ld;
+    const size_t es = AOS ? size_t(1) : TILED ? size_t(32) : (size_t)A.ld;
+    // offset of component 0 of configuration n_ in an array with `rec` components per configuration
+    auto rec_base = [&](long long n_, long long rec) -> long long {
+        return AOS ? n_ * rec : TILED ? (n_ >> 5) * (rec * 32) + (n_ & 31) : n_;
+    };
 
     // frame of column j: registers (j is a compile-time constant after unrolling) or scratch
     JFrame<real> jfr[JR > 0 ? JR : 1];
@@ -279,7 +286,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     auto prefetch_q = [&](long long tile_, int buf) {
         const long long n_ = tile_ * BS + tid;
         if (n_ < A.n) {
-            const real *qn = reinterpret_cast<const real *>(A.q) + (AOS ? n_ * ND : n_);
+            const real *qn = reinterpret_cast<const real *>(A.q) + rec_base(n_, ND);
             real *dst = &SCR(h.so_q + buf * q_stride);
             for (int c = 0; c < ND; ++c) cp_async_elem(dst + c * BS, qn + c * es);
         }
@@ -294,8 +301,8 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
         else cp_async_wait<0>();
         if (n >= A.n) continue;      // no block-level sync below this point
         const int so_q = h.so_q + buf * q_stride;
-        real *Tn = reinterpret_cast<real *>(A.T_out) + (AOS ? n * (12 * n_fk) : n);
-        real *Jn = reinterpret_cast<real *>(A.J_out) + (AOS ? n * (rows * ND * h.n_jac) : n);
+        real *Tn = reinterpret_cast<real *>(A.T_out) + rec_base(n, 12 * n_fk);
+        real *Jn = reinterpret_cast<real *>(A.J_out) + rec_base(n, rows * ND * h.n_jac);
 
         Tf<real> T;                   // running world transform of the current node
 
@@ -474,9 +481,9 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
             const real trunc = (real)A.truncation_dist, voff = (real)A.vals_offset;
             if (stale)
                 for (int i = 0; i < 3 * ND; ++i) stale0[i * BS] = real(0);   // jac = zeros(3, n_dof), collision.jl:76
-            real *Vp = reinterpret_cast<real *>(A.vals_out) + (AOS ? n * S : n);
-            real *Gp = reinterpret_cast<real *>(A.grads_out) + (AOS ? n * ((long long)ND * S) : n);
-            int32_t *Ap = A.argmin_out ? A.argmin_out + (AOS ? n * S : n) : nullptr;
+            real *Vp = reinterpret_cast<real *>(A.vals_out) + rec_base(n, S);
+            real *Gp = reinterpret_cast<real *>(A.grads_out) + rec_base(n, (long long)ND * S);
+            int32_t *Ap = A.argmin_out ? A.argmin_out + rec_base(n, S) : nullptr;
             real *hand = &SCR(so_q);      // q is dead: (dmin, argmin) of the current sphere group
 
             for (int s0 = 0; s0 < S; s0 += SPH_GROUP) {

@@ -149,6 +149,22 @@ def current_q(m: Mechanism, dtype=None):
     return Q.contiguous(), _lib.AOS, N
 
 
+def tile32(x):
+    """(N, rec) batch-first tensor -> tiled storage (ceil(N/32), rec, 32) (KIN_LAYOUT_TILED32), zero padded."""
+    import torch
+    N, rec = x.shape
+    NT = (N + 31) // 32
+    out = torch.zeros((NT * 32, rec), dtype=x.dtype, device=x.device)
+    out[:N] = x
+    return out.reshape(NT, 32, rec).permute(0, 2, 1).contiguous()
+
+
+def untile32(x, N):
+    """tiled storage (NT, ..., 32) -> batch-first (N, ...) copy."""
+    nd = x.dim()
+    return x.permute(0, nd - 1, *range(1, nd - 1)).reshape((x.shape[0] * 32,) + tuple(x.shape[1:-1]))[:N]
+
+
 def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac_links=None, with_rot=True,
              rpy_jac=False, keep_irrelevant=False, J_into=None, collision=False, with_grads=True,
              truncation_dist=np.inf, grad_mode=_lib.GRAD_FD, scratch_mode=_lib.SCRATCH_REFERENCE,
@@ -158,7 +174,11 @@ def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac
     grads (N, n_dof, S), argmin (N, S)."""
     import torch
     layout = q_layout if layout is None else layout
-    if layout != q_layout:                  # one layout per call: bring q to the output layout
+    tiled = layout == _lib.TILED32
+    NT = (N + 31) // 32
+    if tiled:                               # Q arrives batch-first (N, n_dof); re-tile it
+        Q = tile32(Q.contiguous() if q_layout == _lib.AOS else Q)
+    elif layout != q_layout:                # one layout per call: bring q to the output layout
         Q = Q.t().contiguous().t() if layout == _lib.SOA else Q.contiguous()
     dt = Q.dtype
     dev = Q.device
@@ -177,7 +197,17 @@ def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac
     keep = []
 
     def alloc(shape_soa, shape_aos, dtype=dt):
+        if tiled:                            # (NT, components..., 32): the SoA component order inside each tile
+            return torch.empty((NT,) + tuple(shape_soa[:-1]) + (32,), dtype=dtype, device=dev)
         return torch.empty(shape_soa if layout == _lib.SOA else shape_aos, dtype=dtype, device=dev)
+
+    pending = []                             # (key, storage, perm_soa, perm_aos): views are built after the launch
+
+    def view(x, perm_soa, perm_aos):
+        if tiled:                            # batch-first COPY of the tiled storage (N, c1, ..., ck), then the SoA
+            y = untile32(x, N)               # reordering of the component axes (indices shifted by one)
+            return y.permute(0, *[p + 1 for p in perm_soa[1:]])
+        return x.permute(*perm_soa) if layout == _lib.SOA else x.permute(*perm_aos)
 
     if fk_links is not None and len(fk_links):
         ids = np.ascontiguousarray(fk_links, dtype=np.int32)
@@ -185,7 +215,7 @@ def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac
         n = len(ids)
         T = alloc((n, 4, 3, N), (N, n, 4, 3))
         c.n_fk_links, c.fk_links, c.T_out = n, _iptr(ids), T.data_ptr()
-        out["T"] = T.permute(3, 0, 2, 1) if layout == _lib.SOA else T.permute(0, 1, 3, 2)
+        pending.append(("T", T, (3, 0, 2, 1), (0, 1, 3, 2)))
     if jac_links is not None and len(jac_links):
         ids = np.ascontiguousarray(jac_links, dtype=np.int32)
         keep.append(ids)
@@ -196,19 +226,21 @@ def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac
             J = alloc((n, nd, rows, N), (N, n, nd, rows))
         c.n_jac_links, c.jac_links, c.J_out = n, _iptr(ids), J.data_ptr()
         c.with_rot, c.rpy_jac, c.keep_irrelevant = int(with_rot), int(rpy_jac), int(keep_irrelevant)
-        out["J"] = J.permute(3, 0, 2, 1) if layout == _lib.SOA else J.permute(0, 1, 3, 2)
+        pending.append(("J", J, (3, 0, 2, 1), (0, 1, 3, 2)))
     if collision:
         S = dm.n_spheres
         V = alloc((S, N), (N, S))
         c.vals_out = V.data_ptr()
-        out["vals"] = V.t() if layout == _lib.SOA else V
+        pending.append(("vals", V, (1, 0), (0, 1)))
         if with_grads:
             G = alloc((S, nd, N), (N, S, nd))
             c.grads_out = G.data_ptr()
-            out["grads"] = G.permute(2, 1, 0) if layout == _lib.SOA else G.permute(0, 2, 1)
+            pending.append(("grads", G, (2, 1, 0), (0, 2, 1)))
         if want_argmin:
             Am = alloc((S, N), (N, S), torch.int32)
             c.argmin_out = Am.data_ptr()
-            out["argmin"] = Am.t() if layout == _lib.SOA else Am
+            pending.append(("argmin", Am, (1, 0), (0, 1)))
     _lib.check(_lib.lib().kin_eval(dm.h, C.byref(c)))
+    for key, store, perm_soa, perm_aos in pending:
+        out[key] = view(store, perm_soa, perm_aos)
     return out

@@ -11,7 +11,7 @@ SO_PATH = os.path.join(HERE, "libkin_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
 F64, F32 = 0, 1
-SOA, AOS = 0, 1
+SOA, AOS, TILED32 = 0, 1, 2
 FIXED, REVOLUTE, PRISMATIC = 0, 1, 2
 GRAD_FD, GRAD_ANALYTIC = 0, 1
 SCRATCH_REFERENCE, SCRATCH_CLEAN = 0, 1

@@ -381,3 +381,24 @@ def test_full_size_properties():
     K.set_joint_angles(m, joints, sub.t().contiguous())
     v_aos = K.compute_coll_dists(sscc, joints, sdf)
     assert torch.equal(v_soa, v_aos)
+
+
+# ------------------------------------------------------------------------------------------------
+# tiled (AoSoA-32) layout: same kernel, one contiguous block per warp
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("with_base", [False, True])
+def test_tiled_layout_matches_soa_bitwise(with_base):
+    from kinematics_jl_b200.device import current_q, evaluate
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(with_base)
+    q = scenes.random_configs(jo, 1000, with_base, seed=81)         # ragged: 1000 = 31 tiles + 8
+    K.set_joint_angles(m, joints, dev(q))
+    K.compute_coll_dists(sscc, joints, sdf)                         # uploads sphere / box tables
+    dm = device_model(m)
+    Q, ql, N = current_q(m)
+    kw = dict(fk_links=[l.id for l in m.links[:25]], jac_links=[K.find_link(m, "gripper_link").id], with_rot=True,
+              collision=True, with_grads=True, want_argmin=True)
+    a = evaluate(dm, Q, ql, N, layout=L.SOA, **kw)
+    b = evaluate(dm, Q, ql, N, layout=L.TILED32, **kw)
+    for k in ("T", "J", "vals", "grads", "argmin"):
+        assert torch.equal(a[k].contiguous(), b[k].contiguous()), k
+    np.testing.assert_allclose(host(b["T"]), R.batch_fk(mo, jo, q, mo.links[:25])[:, :, :3, :], rtol=RTOL, atol=ATOL)

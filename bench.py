@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--configs-e2e", dest="n_e2e", type=int, default=1 << 21, help="configurations per e2e step (host buffers)")
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-north-star", dest="no_north_star", action="store_true")
+    ap.add_argument("--skip-variants", dest="no_variants", action="store_true", help="skip the other BASELINE.md rows / layouts")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_main(args)
@@ -277,7 +278,7 @@ def main():
 
     # ---- other rows of BASELINE.md section 3, same batch (reported, not the headline) ----
     variants = {}
-    if not args.no_north_star:
+    if not args.no_variants:
         def variant(name, bytes_per_cfg, call_):
             tms_, per_, _ = timed(call_, max(3, args.steps // 2), W)
             ms_ = float(np.mean(per_))

@@ -284,8 +284,8 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     // configuration -> scratch with cp.async, double-buffered across tiles (buffers so_q / so_q2)
     const int q_stride = h.so_q2 - h.so_q;
     auto prefetch_q = [&](long long tile_, int buf) {
-        const long long n_ = tile_ * BS + tid;
-        if (n_ < A.n) {
+        const long long n_ = min(tile_ * BS + tid, (long long)A.n - 1);
+        {
             const real *qn = reinterpret_cast<const real *>(A.q) + rec_base(n_, ND);
             real *dst = &SCR(h.so_q + buf * q_stride);
             for (int c = 0; c < ND; ++c) cp_async_elem(dst + c * BS, qn + c * es);
@@ -296,11 +296,13 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     if ((long long)blockIdx.x < n_tiles) prefetch_q(blockIdx.x, 0);
     int buf = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-        const long long n = tile * BS + tid;
+        // threads past the end of the batch redo the last configuration (identical values, benign duplicate
+        // stores) so that the whole CTA can meet at the phase barriers below
+        const long long n = min(tile * BS + tid, (long long)A.n - 1);
         if (tile + gridDim.x < n_tiles) { prefetch_q(tile + gridDim.x, buf ^ 1); cp_async_wait<1>(); }
         else cp_async_wait<0>();
-        if (n >= A.n) continue;      // no block-level sync below this point
         const int so_q = h.so_q + buf * q_stride;
+        __syncthreads();             // the CTA's warps walk each phase together: one instruction fetch serves all
         real *Tn = reinterpret_cast<real *>(A.T_out) + rec_base(n, 12 * n_fk);
         real *Jn = reinterpret_cast<real *>(A.J_out) + rec_base(n, rows * ND * h.n_jac);
 
@@ -476,6 +478,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
 
         // =========================== phase 2 ===========================
         if (COLL) {
+            __syncthreads();
             const bool want_grads = A.grads_out != nullptr;
             const bool stale = want_grads && A.scratch_ref;
             const real trunc = (real)A.truncation_dist, voff = (real)A.vals_offset;

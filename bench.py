@@ -323,6 +323,71 @@ def main():
                                         "hbm_frac": BYTES_FUSED * Na / (ms_ * 1e-3) / 1e9 / peak, "launch": launch_info(ca)}
         del Qa, Ta, Ja, Va, Ga
 
+    # ---- configs 4 and 5 of BASELINE.json (caller-side rows of SURVEY 8f), through the host mirror ----
+    callers = {}
+    if not args.no_variants:
+        def ev_time(fn, reps):
+            fn()
+            torch.cuda.synchronize(dev)
+            if dist is not None:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                r = fn()
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = a.elapsed_time(b) / reps
+            if dist is not None:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms, r
+        # config 5: 4096 problems x 64 waypoints, straight-line initial trajectories, IneqConst stack
+        # (margin 0.03, truncation 0.08), problems sharded over the ranks, stacked outputs all-gathered
+        P, n_wp = 4096, 64
+        p0, p1 = K.shard_range(P, rank, world)
+        gq = torch.Generator(device=dev).manual_seed(1234)
+        qs = lo + (hi - lo) * torch.rand((P, N_DOF), generator=gq, device=dev, dtype=torch.float64)
+        qg = lo + (hi - lo) * torch.rand((P, N_DOF), generator=gq, device=dev, dtype=torch.float64)
+        X = K.create_straight_trajectory(qs[p0:p1], qg[p0:p1], n_wp)
+        G5 = K.IneqConst(sscc, joints, sdf, n_wp, 0.03)
+        ms_eval, (v5, g5) = ev_time(lambda: G5(X), 5)
+        ms_all, _ = ev_time(lambda: K.gather_stacked(*G5(X)), 5)
+        callers["trajectory_stack(4096x64)"] = {
+            "waypoint_configs_per_s_eval_only": P * n_wp / (ms_eval * 1e-3), "waypoint_configs_per_s_with_allgather": P * n_wp / (ms_all * 1e-3),
+            "ms_eval": ms_eval, "ms_eval_plus_allgather": ms_all, "n_gpus": world,
+            "gathered_bytes": 8 * P * n_wp * (N_SPH + N_SPH * N_DOF), "collective": "NCCL all_gather of vals/grads slabs" if world > 1 else "none (1 rank)"}
+        del X, v5, g5
+        # config 4: 2^20 independent gripper pose targets (FK of random in-limit configurations), LM iterations
+        Nik = 1 << 20
+        qt = lo + (hi - lo) * torch.rand((Nik, N_DOF), generator=gq, device=dev, dtype=torch.float64)
+        K.set_joint_angles(m, joints, qt)
+        gl = K.find_link(m, "gripper_link")
+        Tg = K.get_transform(m, gl)
+        c1 = torch.cos(torch.atan2(Tg[:, 1, 0], Tg[:, 0, 0]))
+        yaw = torch.atan2(Tg[:, 1, 0], Tg[:, 0, 0])
+        pitch = torch.atan2(-Tg[:, 2, 0], torch.sqrt(Tg[:, 2, 1] ** 2 + Tg[:, 2, 2] ** 2))
+        roll = torch.atan2(Tg[:, 0, 2] * torch.sin(yaw) - Tg[:, 1, 2] * c1, Tg[:, 1, 1] * c1 - Tg[:, 0, 1] * torch.sin(yaw))
+        tg = torch.cat([Tg[:, :, 3], roll[:, None], pitch[:, None], yaw[:, None]], dim=1).contiguous()
+        q0 = torch.tensor([0.2, 0, 0, 0, 0.5, 0, 0.5, 0], device=dev, dtype=torch.float64).repeat(Nik, 1)
+        K.set_joint_angles(m, joints, q0)
+        ms_it, _ = ev_time(lambda: K.pose_constraint(m, gl, joints, tg, True), 5)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        qsol, fsol = K.inverse_kinematics_batch(m, gl, joints, tg, q0, with_rot=True, iters=40)
+        torch.cuda.synchronize(dev)
+        t_solve = time.perf_counter() - t0
+        K.set_joint_angles(m, joints, qsol)
+        vv, _ = K.pose_constraint(m, gl, joints, tg, True)
+        vv[:, 3:] = torch.remainder(vv[:, 3:] + np.pi, 2 * np.pi) - np.pi
+        ok = float((vv.abs().amax(dim=1) < 1e-3).double().mean())
+        callers["batched_ik(2^20 targets)"] = {"residual_and_jacobian_evals_per_s": world * Nik / (ms_it * 1e-3), "ms_per_evaluation": ms_it,
+                                               "solve_seconds_40_lm_iterations": t_solve, "targets_per_s": world * Nik / t_solve,
+                                               "fraction_within_1e-3": ok, "n_gpus": world}
+        del qt, Tg, tg, q0, qsol, fsol, vv
+        K.set_joint_angles(m, joints, torch.zeros((1, N_DOF), dtype=torch.float64, device=dev))
+
     # ---- e2e: the C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region ----
     Ne = min(args.n_e2e, N)
     qh = torch.empty((N_DOF, Ne), dtype=torch.float64).pin_memory()
@@ -363,7 +428,7 @@ def main():
                            "n_dof": N_DOF, "configs_per_gpu": N, "layout": "soa", "parallelism": "batch-shard x%d, no collective" % world,
                            "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % (BYTES_FKJ * N / 1e9)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "north_star": north, "variants": variants}
+                "north_star": north, "variants": variants, "callers": callers}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

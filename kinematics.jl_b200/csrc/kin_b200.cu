@@ -57,6 +57,7 @@ struct HostStage {          // resources of kin_eval_host, created on first use
 struct KinModel {
     kin::HostModel hm;
     int device = 0, n_sm = 0;
+    cudaMemPool_t pool = nullptr;   // stream-ordered workspace pool that keeps its memory between calls
     std::mutex mu;
     std::map<std::vector<int>, DeviceProgram *> cache;
     HostStage stage;
@@ -291,6 +292,22 @@ int kin_model_create(const KinModelDesc *d, KinModel **out) {
     if (rc != KIN_OK) { delete m; return rc; }
     cudaError_t e = cudaGetDevice(&m->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, m->device);
+    if (e == cudaSuccess) {
+        // workspaces (kin_pose_residual, kin_sdf_points) come from a private pool whose release threshold is
+        // "never": the default pool hands memory back at every synchronisation and re-mapping hundreds of MB
+        // per call costs milliseconds
+        cudaMemPoolProps props;
+        std::memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = m->device;
+        e = cudaMemPoolCreate(&m->pool, &props);
+        if (e == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            e = cudaMemPoolSetAttribute(m->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (e != cudaSuccess) { delete m; return fail_cuda(e, "querying the device"); }
     *out = m;
     return KIN_OK;
@@ -327,6 +344,7 @@ int kin_model_destroy(KinModel *m) {
         if (m->stage.stream[i]) cudaStreamDestroy(m->stage.stream[i]);
         if (m->stage.buf[i]) cudaFree(m->stage.buf[i]);
     }
+    if (m->pool) cudaMemPoolDestroy(m->pool);
     delete m;
     return KIN_OK;
 }
@@ -519,7 +537,7 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
     const int nd = m->hm.n_dof(), rows = with_rot ? 6 : 3;
     void *ws = nullptr;
     const size_t tb = es * 12 * (size_t)n, jb = es * (size_t)rows * nd * (size_t)n;
-    CUDA_TRY(cudaMallocAsync(&ws, tb + jb, stream));
+    CUDA_TRY(cudaMallocFromPoolAsync(&ws, tb + jb, m->pool, stream));
     KinCall c;
     std::memset(&c, 0, sizeof c);
     c.precision = precision; c.layout = layout; c.n = n; c.q = q;

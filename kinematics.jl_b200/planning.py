@@ -47,8 +47,10 @@ class IneqConst:
             X = xi
         P = X.shape[0]
         set_joint_angles(self.sscc.mech, self.joints, X.reshape(P * self.n_wp, self.n_dof))
+        # evaluated in the SoA layout (coalesced stores); the batch-first views below hide the storage order
         vals, grads = compute_coll_dists_and_grads(self.sscc, self.joints, self.sdf, truncation_dist=self.margin + 0.05,
-                                                   grad_mode=grad_mode, scratch_mode=scratch_mode, vals_offset=self.margin)
+                                                   grad_mode=grad_mode, scratch_mode=scratch_mode, vals_offset=self.margin,
+                                                   layout=_lib.SOA)
         vals = vals.reshape(P, self.n_wp, self.n_coll)
         grads = grads.reshape(P, self.n_wp, self.n_dof, self.n_coll)
         if single:

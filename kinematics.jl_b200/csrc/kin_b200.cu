@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -155,8 +156,10 @@ int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
     CUDA_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
     int best = -1, best_threads = 0, best_occ = 0;
     size_t best_smem = 0;
+    const char *force = std::getenv("KIN_FORCE_BS");     // tuning aid: pin the CTA size
     for (int bi = 0; bi < kNumBS; ++bi) {
         const int b = kBS[bi];
+        if (force && std::atoi(force) != b) continue;
         const size_t smem = tab + rs * (size_t)h.n_slots * b;
         if (smem > (size_t)dev_smem) continue;
         KernelFn k = kKernels[pi][li][bi][coll][jr];

@@ -142,3 +142,33 @@ def test_program_collision_vs_oracle(with_base, truncation):
         if not scratch_ref:        # analytic oracle: the FD gradient is within FD error of it
             _, ga, _ = R.batch_collision(so, jo, sdf_o, q, truncation, R.GRAD_ANALYTIC, mode)
             assert np.abs(out["grads"] - ga.transpose(0, 2, 1)).max() < 1e-4
+
+
+@pytest.mark.parametrize("with_base", [False, True])
+@pytest.mark.parametrize("n_ctrl", [None, 4])
+def test_program_synthetic_branching_tree(with_base, n_ctrl):
+    """Branching tree, general axes, rpy origins, negative axes, frozen joints at non-zero angles, shuffled
+    column order: exercises save slots, the Rodrigues path, general offsets and attachment folding."""
+    import scenes_synthetic as SS
+    m, joints, sscc, sdf = SS.product(with_base, n_ctrl)
+    mo, jo, so, sdf_o = SS.oracle(with_base, n_ctrl)
+    if n_ctrl is not None:          # the joints that are not controlled sit at non-zero angles
+        for name, a in zip(SS.JOINTS[n_ctrl:], [0.3, -0.4, 0.5, 0.1, -0.2]):
+            K.set_joint_angle(m, K.find_joint(m, name), a)
+            R.set_joint_angles(mo, [R.find_joint(mo, name)], [a] + ([0, 0, 0] if with_base else []))
+    q = SS.random_q(jo, 80, with_base, seed=5)
+    ids = [l.id for l in m.links]
+    h, ti, tr = dump_program(m, [j.id for j in joints], ids, ids, (sscc._parents, sscc._centers, sscc.sphere_radii),
+                             (np.stack(SS.BOX_POSES), np.array(SS.BOX_WIDTHS)))
+    if n_ctrl is None and not with_base:
+        assert h["so_jf"] > h["so_save"]          # a branching tree needs at least one save slot
+    T_ref = R.batch_fk(mo, jo, q, mo.links)
+    out = run_program(h, ti, tr, q, with_rot=True, rpy_jac=True)
+    np.testing.assert_allclose(out["T"], T_ref[:, :, :3, :], rtol=0, atol=5e-14)
+    np.testing.assert_allclose(out["J"], R.batch_jacobian(mo, jo, q, mo.links, True, True), rtol=1e-11, atol=1e-11)
+    for scratch_ref, mode in ((True, R.SCRATCH_REFERENCE), (False, R.SCRATCH_CLEAN)):
+        o2 = run_program(h, ti, tr, q, truncation=0.3, scratch_ref=scratch_ref)
+        vals, grads, am = R.batch_collision(so, jo, sdf_o, q, 0.3, R.GRAD_FD, mode)
+        np.testing.assert_allclose(o2["vals"], vals, rtol=1e-12, atol=1e-13)
+        assert np.array_equal(o2["argmin"], am)
+        np.testing.assert_allclose(o2["grads"], grads.transpose(0, 2, 1), rtol=0, atol=1e-7)

@@ -402,3 +402,36 @@ def test_tiled_layout_matches_soa_bitwise(with_base):
     for k in ("T", "J", "vals", "grads", "argmin"):
         assert torch.equal(a[k].contiguous(), b[k].contiguous()), k
     np.testing.assert_allclose(host(b["T"]), R.batch_fk(mo, jo, q, mo.links[:25])[:, :, :3, :], rtol=RTOL, atol=ATOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# generality: branching tree, general joint axes, rpy joint origins, frozen joints, shuffled columns
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("with_base", [False, True])
+@pytest.mark.parametrize("n_ctrl", [None, 4])          # 9 columns: frames in shared scratch; 4: frames in registers
+@pytest.mark.parametrize("layout", [L.SOA, L.AOS, L.TILED32])
+def test_synthetic_branching_tree(with_base, n_ctrl, layout):
+    import scenes_synthetic as SS
+    from kinematics_jl_b200.device import current_q, evaluate
+    m, joints, sscc, sdf = SS.product(with_base, n_ctrl)
+    mo, jo, so, sdf_o = SS.oracle(with_base, n_ctrl)
+    if n_ctrl is not None:
+        for name, a in zip(SS.JOINTS[n_ctrl:], [0.3, -0.4, 0.5, 0.1, -0.2]):
+            K.set_joint_angle(m, K.find_joint(m, name), a)
+            R.set_joint_angles(mo, [R.find_joint(mo, name)], [a] + ([0, 0, 0] if with_base else []))
+    q = SS.random_q(jo, 333, with_base, seed=7)
+    K.set_joint_angles(m, joints, dev(q))
+    K.compute_coll_dists(sscc, joints, sdf)
+    dm = device_model(m)
+    Q, ql, N = current_q(m)
+    ids = [l.id for l in m.links]
+    for rpy_jac in (False, True):
+        for scratch, scratch_o in ((K.SCRATCH_REFERENCE, R.SCRATCH_REFERENCE), (K.SCRATCH_CLEAN, R.SCRATCH_CLEAN)):
+            out = evaluate(dm, Q, ql, N, layout=layout, fk_links=ids, jac_links=ids, with_rot=True, rpy_jac=rpy_jac,
+                           collision=True, with_grads=True, want_argmin=True, truncation_dist=0.3, scratch_mode=scratch)
+            np.testing.assert_allclose(host(out["T"]), R.batch_fk(mo, jo, q, mo.links)[:, :, :3, :], rtol=RTOL, atol=ATOL)
+            np.testing.assert_allclose(host(out["J"]), R.batch_jacobian(mo, jo, q, mo.links, True, rpy_jac), rtol=1e-11, atol=1e-11)
+            v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, q, 0.3, R.GRAD_FD, scratch_o)
+            np.testing.assert_allclose(host(out["vals"]), v_ref, rtol=RTOL, atol=ATOL)
+            assert np.array_equal(out["argmin"].cpu().numpy(), am_ref)
+            np.testing.assert_allclose(host(out["grads"]), g_ref.transpose(0, 2, 1), rtol=0, atol=1e-7)

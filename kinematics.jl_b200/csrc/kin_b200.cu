@@ -160,7 +160,8 @@ int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
     for (int bi = 0; bi < kNumBS; ++bi) {
         const int b = kBS[bi];
         if (force && std::atoi(force) != b) continue;
-        const size_t smem = tab + rs * (size_t)h.n_slots * b;
+        size_t smem = tab + rs * (size_t)h.n_slots * b;
+        if (li == KIN_LAYOUT_AOS) smem += rs * (size_t)kin::AOS_STAGE_REALS * (b / 32);   // warp-private staging
         if (smem > (size_t)dev_smem) continue;
         KernelFn k = kKernels[pi][li][bi][coll][jr];
         CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_smem));

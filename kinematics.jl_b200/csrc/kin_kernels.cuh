@@ -204,6 +204,31 @@ __device__ __forceinline__ void cp_async_elem(float *smem_dst, const float *gsrc
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// AoS layout only.  A thread owns one record, so a plain store of component k by 32 lanes hits 32
+// different sectors.  Instead the warp stages R values per lane in a warp-private shared buffer
+// ([k][33] padded) and writes the 32 x R block with the lanes running ALONG the records: consecutive
+// lanes write consecutive addresses, every sector is written whole.  `rec0` = address of the block's
+// first component in the record of the warp's first configuration, `rec` = record stride (elements),
+// `n_valid` = number of lanes whose record exists (lanes past the end re-write the last one).
+constexpr int AOS_STAGE_ROWS = 12;
+constexpr int AOS_STAGE_REALS = AOS_STAGE_ROWS * 33;
+template <typename real, int RMAX>
+__device__ __forceinline__ void warp_store_records(real *stage, real *rec0, size_t rec, const real (&v)[RMAX], int R, int lane, int n_valid) {
+    #pragma unroll
+    for (int k = 0; k < RMAX; ++k)
+        if (k < R) stage[k * 33 + lane] = v[k];
+    __syncwarp();
+    int c = lane / R, k = lane - c * R;          // element e = i * 32 + lane of the block: record e / R, component e % R
+    const int dc = 32 / R, dk = 32 - dc * R;
+    for (int i = 0; i < R; ++i) {
+        const int cc = min(c, n_valid - 1);
+        rec0[(size_t)cc * rec + k] = stage[k * 33 + cc];
+        c += dc; k += dk;
+        if (k >= R) { k -= R; ++c; }
+    }
+    __syncwarp();
+}
+
 constexpr int SPH_GROUP = 4;   // spheres evaluated together against each box row (register blocking)
 constexpr int JF_REGS = 8;     // joint frames kept in registers when the model has at most this many columns
 static_assert(JF_REGS == 8, "the switch statements in kin_eval_kernel enumerate 8 cases");
@@ -240,6 +265,9 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
     const int tid = threadIdx.x;
     real *scr = tr + h.n_real + tid;                   // [slot][thread]: SCR(slot) = scr[slot * BS]
     #define SCR(slot) scr[(slot) * BS]
+    // AoS: warp-private staging buffer behind the scratch
+    const int lane = tid & 31;
+    real *stage = tr + h.n_real + (size_t)h.n_slots * BS + (tid >> 5) * AOS_STAGE_REALS;
 
     // ---- stage the program tables once per CTA ----
     {
@@ -302,6 +330,9 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
         if (tile + gridDim.x < n_tiles) { prefetch_q(tile + gridDim.x, buf ^ 1); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         const int so_q = h.so_q + buf * q_stride;
+        // AoS staging: first configuration of this warp and how many of its 32 records exist
+        const long long n_w0 = min(tile * BS + (tid & ~31), (long long)A.n - 1);
+        const int n_valid = (int)min((long long)32, A.n - n_w0);
         __syncthreads();             // the CTA's warps walk each phase together: one instruction fetch serves all
         real *Tn = reinterpret_cast<real *>(A.T_out) + rec_base(n, 12 * n_fk);
         real *Jn = reinterpret_cast<real *>(A.J_out) + rec_base(n, rows * ND * h.n_jac);
@@ -405,13 +436,25 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 Tf<real> Tl;
                 tf_mul_const(T, ar, ai[1] & AF_R_IDENTITY, Tl);
                 if (ai[0] >= 0 && A.T_out) {       // get_transform, as 3x4 column-major
-                    real *o = Tn + (size_t)(12 * ai[0]) * es;
-                    #pragma unroll
-                    for (int c = 0; c < 3; ++c)
+                    if (AOS) {                     // staged: lanes run along the records
+                        real v[12];
                         #pragma unroll
-                        for (int r = 0; r < 3; ++r) o[(c * 3 + r) * es] = Tl.r[r * 3 + c];
-                    #pragma unroll
-                    for (int r = 0; r < 3; ++r) o[(9 + r) * es] = Tl.p[r];
+                        for (int c = 0; c < 3; ++c)
+                            #pragma unroll
+                            for (int r = 0; r < 3; ++r) v[c * 3 + r] = Tl.r[r * 3 + c];
+                        #pragma unroll
+                        for (int r = 0; r < 3; ++r) v[9 + r] = Tl.p[r];
+                        const size_t rec = (size_t)12 * n_fk;
+                        warp_store_records<real, 12>(stage, reinterpret_cast<real *>(A.T_out) + n_w0 * rec + 12 * ai[0], rec, v, 12, lane, n_valid);
+                    } else {
+                        real *o = Tn + (size_t)(12 * ai[0]) * es;
+                        #pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            #pragma unroll
+                            for (int r = 0; r < 3; ++r) o[(c * 3 + r) * es] = Tl.r[r * 3 + c];
+                        #pragma unroll
+                        for (int r = 0; r < 3; ++r) o[(9 + r) * es] = Tl.p[r];
+                    }
                 }
                 if (ai[2] >= 0 && A.J_out) {       // get_jacobian, algorithm.jl:83-114
                     real *o = Jn + (size_t)(ai[2] * rows * ND) * es;
@@ -538,6 +581,41 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     *Vp = (truncated ? trunc : dist0) - voff;
                     Vp += es;
                     if (Ap) { *Ap = kmin + 1; Ap += es; }
+                    if (!want_grads) continue;
+                    if (AOS && JR > 0) {
+                        // AoS: the n_dof gradients of this sphere are collected in registers and written by the
+                        // whole warp (truncated lanes contribute zeros: collision.jl:84-86), so control flow
+                        // stays convergent up to the staged store
+                        real gv[JR > 0 ? JR : 1];
+                        #pragma unroll
+                        for (int j = 0; j < (JR > 0 ? JR : 1); ++j) gv[j] = real(0);
+                        if (!truncated) {
+                            const real *cs = &SCR(so_cent + 3 * s);
+                            const real px = cs[0], py = cs[BS], pz = cs[2 * BS];
+                            real grad[3];
+                            {
+                                BoxRow<real> row;
+                                load_box(tr + ro_box + kmin * BOX_REALS, row);
+                                box_gradient(row, A.grad_mode, px, py, pz, dmin, grad);
+                            }
+                            const unsigned mask = (unsigned)ti[io_sph_mask + s];
+                            real *st = stale0;
+                            FOR_COLUMNS(j) {
+                                real cx, cy, cz;
+                                if ((mask >> j) & 1u) {
+                                    jac_col(jfr[j], (rev_mask >> j) & 1u, px, py, pz, cx, cy, cz);
+                                    if (stale) { st[0] = cx; st[BS] = cy; st[2 * BS] = cz; }
+                                } else if (stale) { cx = st[0]; cy = st[BS]; cz = st[2 * BS]; }
+                                else { cx = cy = cz = real(0); }
+                                gv[j] = fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz));
+                                st += 3 * BS;
+                            }
+                        }
+                        const size_t rec = (size_t)ND * S;
+                        warp_store_records<real, (JR > 0 ? JR : 1)>(stage, reinterpret_cast<real *>(A.grads_out) + n_w0 * rec + (size_t)s * ND,
+                                                                    rec, gv, ND, lane, n_valid);
+                        continue;
+                    }
                     if (!want_grads) continue;
                     if (truncated) {            // collision.jl:84-86
                         for (int j = 0; j < ND; ++j, Gp += es) *Gp = real(0);

@@ -64,21 +64,32 @@ def ik_objective(m: Mechanism, link, joints, target_pose, with_rot=True):
     return f, g
 
 
-def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=True, iters=100, ftol=1e-10):
+def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=True, iters=100, ftol=1e-10,
+                             sscc=None, sdf=None, margin=0.02, coll_weight=100.0, use_bistage=True):
     """Batched IK for N independent pose targets (config 4 of BASELINE.json): Levenberg-Marquardt with
-    per-problem adaptive damping and an active set for the joint limits on the reference's objective f = |[p - p_t; rpy - rpy_t]|^2
-    (inverse_kinematics.jl:38-50), iterates clamped to the joint limits (:52-63).  Every evaluation of the
-    residual and of its Euler-rate Jacobian is one libkin_b200 call over the whole batch; the 8x8 normal
-    equations are solved with torch.  Angle residuals are wrapped to (-pi, pi] for stepping.
-    ``targets`` (N, 6) [x y z roll pitch yaw], ``q0`` (N, n_dof).  Returns (q, f)."""
+    per-problem adaptive damping and an active set for the joint limits on the reference's objective
+    f = |[p - p_t; rpy - rpy_t]|^2 (inverse_kinematics.jl:38-50), iterates clamped to the joint limits
+    (:52-63).  With ``sscc`` and ``sdf`` the reference's collision constraint ``dists - margin >= 0`` of the
+    two-stage driver (inverse_kinematics.jl:1-21, IneqConst with margin 0.02) enters as a quadratic penalty
+    coll_weight * sum(max(0, margin - d_s)^2): its residual rows and Jacobian rows come from
+    compute_coll_dists_and_grads (truncation margin + 0.05, as planning.jl:56).  Every evaluation of the
+    residuals and Jacobians is a libkin_b200 call over the whole batch; the small normal equations are
+    solved with torch.  Angle residuals are wrapped to (-pi, pi] for stepping.
+    ``targets`` (N, 6) [x y z roll pitch yaw], ``q0`` (N, n_dof).  Returns (q, f) with f the pose objective."""
     import torch
+    from .collision import compute_coll_dists_and_grads
     from .planning import pose_constraint
+    if sscc is not None and sdf is not None and use_bistage:
+        # inverse_kinematics.jl:8-13: solve the collision-free problem first and use it as the seed
+        q0, _ = inverse_kinematics_batch(m, link, joints, targets, q0, with_rot=with_rot, iters=iters, ftol=ftol)
     nb = 3 if m.with_base else 0
     lo = torch.tensor([j.lower_limit for j in joints] + [-np.inf] * nb, device="cuda", dtype=torch.float64)
     hi = torch.tensor([j.upper_limit for j in joints] + [np.inf] * nb, device="cuda", dtype=torch.float64)
     q = torch.as_tensor(q0, dtype=torch.float64, device="cuda").clone()
     N, nd = q.shape
     eye = torch.eye(nd, dtype=torch.float64, device="cuda")
+    collide = sscc is not None and sdf is not None
+    sw = float(np.sqrt(coll_weight))
 
     def evaluate(qq):
         set_joint_angles(m, joints, qq)
@@ -86,9 +97,16 @@ def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=T
         e = e.clone()
         if with_rot:
             e[:, 3:] = torch.remainder(e[:, 3:] + np.pi, 2 * np.pi) - np.pi
-        return e, JT, (e * e).sum(dim=1)
+        f_pose = (e * e).sum(dim=1)
+        if collide:     # penalty rows r_s = sw * max(0, margin - d_s); d r_s / d q = -sw * grads[:, s] where active
+            d, g = compute_coll_dists_and_grads(sscc, joints, sdf, truncation_dist=margin + 0.05)
+            act = (d < margin).to(q.dtype)
+            r = sw * (margin - d) * act
+            e = torch.cat([e, r], dim=1)
+            JT = torch.cat([JT, -sw * g * act[:, None, :]], dim=2)
+        return e, JT, (e * e).sum(dim=1), f_pose
 
-    e, JT, f = evaluate(q)
+    e, JT, f, f_pose = evaluate(q)
     lam = torch.full((N,), 1e-2, dtype=torch.float64, device="cuda")
     for _ in range(iters):
         H = JT @ JT.transpose(1, 2)
@@ -100,14 +118,15 @@ def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=T
         H = H * (fm[:, :, None] * fm[:, None, :]) + torch.diag_embed(1.0 - fm)
         step = torch.linalg.solve(H, (g * fm).unsqueeze(-1)).squeeze(-1)
         q_new = torch.minimum(torch.maximum(q - step, lo), hi)
-        e_new, JT_new, f_new = evaluate(q_new)
+        e_new, JT_new, f_new, fp_new = evaluate(q_new)
         ok = f_new < f
         q = torch.where(ok[:, None], q_new, q)
         e = torch.where(ok[:, None], e_new, e)
         JT = torch.where(ok[:, None, None], JT_new, JT)
         f = torch.where(ok, f_new, f)
+        f_pose = torch.where(ok, fp_new, f_pose)
         lam = torch.where(ok, lam * 0.3, lam * 4.0).clamp(1e-9, 1e4)
         if float(f.max()) < ftol:
             break
     set_joint_angles(m, joints, q)
-    return q, f
+    return q, f_pose

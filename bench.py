@@ -34,6 +34,10 @@ N_LINKS, N_DOF, N_SPH = 25, 8, 16
 # S distances + S x n_dof gradients
 BYTES_FKJ = 8 * N_DOF + 8 * 12 * N_LINKS + 8 * 6 * N_DOF                   # 2848
 BYTES_FUSED = BYTES_FKJ + 8 * N_SPH + 8 * N_SPH * N_DOF                     # 4000
+# DRAM bytes per configuration measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one
+# `--set full` capture of a 4 194 304-configuration launch, profiles/r01_final_{fkj,fused}_ncu_summary.txt)
+NCU_DRAM_BYTES_PER_CONFIG_FKJ = (268483072 + 11620233000) / 4194304          # 2834.5
+NCU_DRAM_BYTES_PER_CONFIG_FUSED = (269890816 + 16454000000) / 4194304        # 3987.3
 METRIC = "fetch_fk_jacobian_configs_per_s"
 UNIT = "configs/s"
 
@@ -257,7 +261,9 @@ def main():
     achieved = BYTES_FKJ * N / (kern_ms * 1e-3) / 1e9
     info = launch_info(call)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "kin_eval_kernel<double,SoA>",
+                "traffic": NCU_DRAM_BYTES_PER_CONFIG_FKJ * N, "traffic_source": "ncu dram__bytes_read+write per configuration "
+                "(profiles/r01_final_fkj_ncu_summary.txt, 2^22-configuration launch) x configurations per launch",
+                "peak_source": peak_src, "kernel": "kin_eval_kernel<double,SoA>",
                 "algorithmic_bytes_per_config": BYTES_FKJ, "launch_ms": kern_ms, "launch": info}
 
     # ---- north star: fused FK-all + Jacobian + collision cost/grad ----
@@ -273,6 +279,7 @@ def main():
                  "value": world * N / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f,
                  "roofline": {"bound": "hbm-or-fp64 (see DESIGN.md)", "achieved": ach_f, "peak": peak, "unit": "GB/s",
                               "frac": ach_f / peak, "algorithmic_bytes_per_config": BYTES_FUSED,
+                              "traffic": NCU_DRAM_BYTES_PER_CONFIG_FUSED * N,
                               "launch": launch_info(callf)}}
         del V, G
 

@@ -216,6 +216,21 @@ KIN_API int kin_pose_residual(KinModel *model, int32_t precision, int32_t layout
                               int32_t link_id, const void *target, int32_t target_per_config, int32_t with_rot,
                               int32_t mode, void *val_out, void *jac_out, void *stream);
 
+/* Batched Levenberg-Marquardt iteration of the IK driver built on kin_pose_residual / kin_eval (config 4;
+ * the reference drives the same evaluations with NLopt SLSQP, inverse_kinematics.jl:1-30, which is third
+ * party).  One thread per problem, everything per-problem contiguous (AoS), FP64, DEVICE pointers:
+ *   q[n][n_dof], e[n][dim] residual, J[n][dim][n_dof] = d e / d q, lambda[n], f[n] = |e|^2,
+ *   lo / hi [n_dof] joint limits (+-inf allowed).
+ * kin_lm_step:   q_try = clamp(q - (J'J + lambda (I + diag J'J))^-1 J'e) with the joints that sit on a limit
+ *                and are pushed outward frozen (active set); Cholesky in registers / local memory.
+ * kin_lm_accept: where f_try < f the trial point (q, e, J, f) replaces the current one and lambda *= 0.3,
+ *                elsewhere lambda *= 4 (clamped to [1e-9, 1e4]). */
+KIN_API int kin_lm_step(int64_t n, int32_t n_dof, int32_t dim, const double *q, const double *e, const double *J,
+                        const double *lambda, const double *lo, const double *hi, double *q_try, void *stream);
+KIN_API int kin_lm_accept(int64_t n, int32_t n_dof, int32_t dim, const double *q_try, const double *e_try,
+                          const double *J_try, const double *f_try, double *q, double *e, double *J, double *f,
+                          double *lambda, void *stream);
+
 /* Diagnostics for bench.py / tests: kernel launches issued by this library since load, and the
  * static resources of the kernel a call would use (registers / thread, dynamic shared memory bytes /
  * CTA, threads / CTA, CTAs in the grid).  */

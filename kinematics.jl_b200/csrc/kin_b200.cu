@@ -569,6 +569,28 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
     return KIN_OK;
 }
 
+int kin_lm_step(int64_t n, int32_t n_dof, int32_t dim, const double *q, const double *e, const double *J,
+                const double *lambda, const double *lo, const double *hi, double *q_try, void *stream) {
+    if (n < 0 || n_dof < 1 || n_dof > kin::LM_MAX_DOF || dim < 1) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_lm_step: bad sizes (n_dof <= 16)");
+    if (n > 0 && (!q || !e || !J || !lambda || !lo || !hi || !q_try)) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0) return KIN_OK;
+    kin::lm_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, n_dof, dim, q, e, J, lambda, lo, hi, q_try);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return KIN_OK;
+}
+
+int kin_lm_accept(int64_t n, int32_t n_dof, int32_t dim, const double *q_try, const double *e_try, const double *J_try,
+                  const double *f_try, double *q, double *e, double *J, double *f, double *lambda, void *stream) {
+    if (n < 0 || n_dof < 1 || dim < 1) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_lm_accept: bad sizes");
+    if (n > 0 && (!q_try || !e_try || !J_try || !f_try || !q || !e || !J || !f || !lambda)) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
+    if (n == 0) return KIN_OK;
+    kin::lm_accept_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, n_dof, dim, q_try, e_try, J_try, f_try, q, e, J, f, lambda);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return KIN_OK;
+}
+
 int kin_fk_links(KinModel *m, int32_t precision, int32_t layout, const void *q, int64_t n, const int32_t *link_ids,
                  int32_t n_req, void *T_out, void *stream) {
     KinCall c;

@@ -73,8 +73,9 @@ def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=T
     two-stage driver (inverse_kinematics.jl:1-21, IneqConst with margin 0.02) enters as a quadratic penalty
     coll_weight * sum(max(0, margin - d_s)^2): its residual rows and Jacobian rows come from
     compute_coll_dists_and_grads (truncation margin + 0.05, as planning.jl:56).  Every evaluation of the
-    residuals and Jacobians is a libkin_b200 call over the whole batch; the small normal equations are
-    solved with torch.  Angle residuals are wrapped to (-pi, pi] for stepping.
+    residuals and Jacobians is a libkin_b200 call over the whole batch, and so are the LM step (normal
+    equations + Cholesky per problem, kin_lm_step) and the accept / damping update (kin_lm_accept).
+    Angle residuals are wrapped to (-pi, pi] for stepping.
     ``targets`` (N, 6) [x y z roll pitch yaw], ``q0`` (N, n_dof).  Returns (q, f) with f the pose objective."""
     import torch
     from .collision import compute_coll_dists_and_grads
@@ -85,47 +86,42 @@ def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=T
     nb = 3 if m.with_base else 0
     lo = torch.tensor([j.lower_limit for j in joints] + [-np.inf] * nb, device="cuda", dtype=torch.float64)
     hi = torch.tensor([j.upper_limit for j in joints] + [np.inf] * nb, device="cuda", dtype=torch.float64)
-    q = torch.as_tensor(q0, dtype=torch.float64, device="cuda").clone()
+    q = torch.as_tensor(q0, dtype=torch.float64, device="cuda").contiguous().clone()
     N, nd = q.shape
-    eye = torch.eye(nd, dtype=torch.float64, device="cuda")
     collide = sscc is not None and sdf is not None
     sw = float(np.sqrt(coll_weight))
+    L_ = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
 
     def evaluate(qq):
+        """-> e (N, dim), J (N, dim, n_dof) = d e / d q (both contiguous), f = |e|^2, f_pose"""
         set_joint_angles(m, joints, qq)
-        e, JT = pose_constraint(m, link, joints, targets, with_rot)     # e (N, dim) = now - target, JT (N, nd, dim)
-        e = e.clone()
+        e, JT = pose_constraint(m, link, joints, targets, with_rot)     # e (N, rows) = now - target, JT (N, nd, rows) view
+        J = JT.permute(0, 2, 1)                                          # the AoS storage itself: (N, rows, nd)
         if with_rot:
             e[:, 3:] = torch.remainder(e[:, 3:] + np.pi, 2 * np.pi) - np.pi
         f_pose = (e * e).sum(dim=1)
-        if collide:     # penalty rows r_s = sw * max(0, margin - d_s); d r_s / d q = -sw * grads[:, s] where active
-            d, g = compute_coll_dists_and_grads(sscc, joints, sdf, truncation_dist=margin + 0.05)
-            act = (d < margin).to(q.dtype)
-            r = sw * (margin - d) * act
-            e = torch.cat([e, r], dim=1)
-            JT = torch.cat([JT, -sw * g * act[:, None, :]], dim=2)
-        return e, JT, (e * e).sum(dim=1), f_pose
+        if not collide:
+            return e, J.contiguous(), f_pose, f_pose
+        # penalty rows r_s = sw * max(0, margin - d_s); d r_s / d q = -sw * grads[:, s] where active
+        d, g = compute_coll_dists_and_grads(sscc, joints, sdf, truncation_dist=margin + 0.05)
+        act = (d < margin).to(q.dtype)
+        e = torch.cat([e, sw * (margin - d) * act], dim=1)
+        J = torch.cat([J, (-sw * g * act[:, None, :]).permute(0, 2, 1)], dim=1).contiguous()
+        return e, J, (e * e).sum(dim=1), f_pose
 
-    e, JT, f, f_pose = evaluate(q)
+    e, J, f, f_pose = evaluate(q)
+    e, J = e.contiguous(), J.contiguous()
+    dim = e.shape[1]
     lam = torch.full((N,), 1e-2, dtype=torch.float64, device="cuda")
+    q_try = torch.empty_like(q)
     for _ in range(iters):
-        H = JT @ JT.transpose(1, 2)
-        g = (JT @ e.unsqueeze(-1)).squeeze(-1)
-        # projected step: a joint sitting on a limit whose gradient pushes outward is frozen (active set)
-        free = ~(((q <= lo + 1e-12) & (g > 0)) | ((q >= hi - 1e-12) & (g < 0)))
-        fm = free.to(q.dtype)
-        H = H + lam[:, None, None] * (eye + torch.diag_embed(torch.diagonal(H, dim1=1, dim2=2)))
-        H = H * (fm[:, :, None] * fm[:, None, :]) + torch.diag_embed(1.0 - fm)
-        step = torch.linalg.solve(H, (g * fm).unsqueeze(-1)).squeeze(-1)
-        q_new = torch.minimum(torch.maximum(q - step, lo), hi)
-        e_new, JT_new, f_new, fp_new = evaluate(q_new)
-        ok = f_new < f
-        q = torch.where(ok[:, None], q_new, q)
-        e = torch.where(ok[:, None], e_new, e)
-        JT = torch.where(ok[:, None, None], JT_new, JT)
-        f = torch.where(ok, f_new, f)
-        f_pose = torch.where(ok, fp_new, f_pose)
-        lam = torch.where(ok, lam * 0.3, lam * 4.0).clamp(1e-9, 1e4)
+        _lib.check(L_.kin_lm_step(N, nd, dim, q.data_ptr(), e.data_ptr(), J.data_ptr(), lam.data_ptr(), lo.data_ptr(),
+                                  hi.data_ptr(), q_try.data_ptr(), stream))
+        e_t, J_t, f_t, fp_t = evaluate(q_try)
+        f_pose = torch.where(f_t < f, fp_t, f_pose)
+        _lib.check(L_.kin_lm_accept(N, nd, dim, q_try.data_ptr(), e_t.contiguous().data_ptr(), J_t.data_ptr(), f_t.data_ptr(),
+                                    q.data_ptr(), e.data_ptr(), J.data_ptr(), f.data_ptr(), lam.data_ptr(), stream))
         if float(f.max()) < ftol:
             break
     set_joint_angles(m, joints, q)

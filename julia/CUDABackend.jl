@@ -20,7 +20,7 @@ import ..Kinematics: get_transform, get_jacobian, compute_coll_dists, compute_co
 const libkin = get(ENV, "KIN_B200_LIB", "libkin_b200.so")
 
 const KIN_F64, KIN_F32 = Cint(0), Cint(1)
-const KIN_LAYOUT_SOA, KIN_LAYOUT_AOS = Cint(0), Cint(1)
+const KIN_LAYOUT_SOA, KIN_LAYOUT_AOS, KIN_LAYOUT_TILED32 = Cint(0), Cint(1), Cint(2)
 const KIN_GRAD_FD, KIN_GRAD_ANALYTIC = Cint(0), Cint(1)
 const KIN_SCRATCH_REFERENCE, KIN_SCRATCH_CLEAN = Cint(0), Cint(1)
 

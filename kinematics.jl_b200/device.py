@@ -228,6 +228,9 @@ def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac
         c.with_rot, c.rpy_jac, c.keep_irrelevant = int(with_rot), int(rpy_jac), int(keep_irrelevant)
         pending.append(("J", J, (3, 0, 2, 1), (0, 1, 3, 2)))
     if collision:
+        if dm.n_spheres == 0 or dm.n_boxes == 0:
+            raise _lib.KinError("collision requested but the device model has no spheres / no boxes "
+                                "(add_coll_links and pass an SDF first)")
         S = dm.n_spheres
         V = alloc((S, N), (N, S))
         c.vals_out = V.data_ptr()

@@ -435,3 +435,48 @@ def test_synthetic_branching_tree(with_base, n_ctrl, layout):
             np.testing.assert_allclose(host(out["vals"]), v_ref, rtol=RTOL, atol=ATOL)
             assert np.array_equal(out["argmin"].cpu().numpy(), am_ref)
             np.testing.assert_allclose(host(out["grads"]), g_ref.transpose(0, 2, 1), rtol=0, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases and error behaviour of the C ABI
+# ------------------------------------------------------------------------------------------------
+def test_edge_cases_and_errors():
+    from kinematics_jl_b200.device import current_q, evaluate
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
+    # tiny and ragged batches in every layout
+    for N in (1, 2, 31, 33, 129):
+        q = scenes.random_configs(jo, N, False, seed=N)
+        K.set_joint_angles(m, joints, dev(q))
+        K.compute_coll_dists(sscc, joints, sdf)
+        dm = device_model(m)
+        Q, ql, n = current_q(m)
+        ref_T = R.batch_fk(mo, jo, q, mo.links[:25])[:, :, :3, :]
+        ref_v = R.batch_collision(so, jo, sdf_o, q, with_grads=False)[0]
+        for layout in (L.SOA, L.AOS, L.TILED32):
+            o = evaluate(dm, Q, ql, n, layout=layout, fk_links=[l.id for l in m.links[:25]], collision=True, with_grads=True)
+            np.testing.assert_allclose(host(o["T"]), ref_T, rtol=RTOL, atol=ATOL)
+            np.testing.assert_allclose(host(o["vals"]), ref_v, rtol=RTOL, atol=ATOL)
+    # no control joints at all: every link is a constant; with a base: three columns only
+    for with_base in (False, True):
+        mm, _, _ = scenes.product_fetch(with_base)
+        mmo, _, _ = scenes.oracle_fetch(with_base)
+        K.set_joint_angle(mm, K.find_joint(mm, "head_pan_joint"), 0.3)
+        R.set_joint_angles(mmo, [R.find_joint(mmo, "head_pan_joint")], [0.3] + ([0, 0, 0] if with_base else []))
+        qb = np.array([[0.4, -0.2, 1.1], [0.0, 0.0, 0.0]]) if with_base else np.zeros((2, 0))
+        K.set_joint_angles(mm, [], dev(qb) if with_base else torch.zeros((2, 0), dtype=torch.float64, device="cuda"))
+        T = host(K.get_transform(mm, mm.links[:25]))
+        np.testing.assert_allclose(T, R.batch_fk(mmo, [], qb, mmo.links[:25])[:, :, :3, :], rtol=RTOL, atol=ATOL)
+    # errors are exceptions carrying kin_last_error(), never crashes
+    K.set_joint_angles(m, joints, dev(scenes.random_configs(jo, 4, False, seed=1)))
+    dm = device_model(m)
+    Q, ql, n = current_q(m)
+    with pytest.raises(K.KinError):
+        evaluate(dm, Q, ql, n, fk_links=[0])                      # ids are 1-based
+    with pytest.raises(K.KinError):
+        evaluate(dm, Q, ql, n, fk_links=[len(m.links) + 1])
+    m2, joints2, _ = scenes.product_fetch(False, sphere_links=[])
+    K.set_joint_angles(m2, joints2, dev(scenes.random_configs(jo, 4, False, seed=1)))
+    with pytest.raises(K.KinError):                               # collision without spheres / boxes
+        evaluate(device_model(m2), *current_q(m2), collision=True)
+    with pytest.raises(ValueError):                               # joints must be the ones of set_joint_angles
+        K.get_jacobian(m, K.find_link(m, "gripper_link"), joints[:3], True)

@@ -316,6 +316,17 @@ def main():
         ctf = make_call(N, Qt.data_ptr(), Tt.data_ptr(), Jt.data_ptr(), Vt.data_ptr(), Gt.data_ptr(), layout=L.TILED32)
         variant("fused_tiled32_layout", BYTES_FUSED, ctf)
         del Qt, Tt, Jt, Vt, Gt
+        # the optional FP32 mode (1e-5 tolerance), fused step, SoA
+        Q32 = Q.float()
+        T32 = torch.empty((N_LINKS * 12, N), dtype=torch.float32, device=dev)
+        J32 = torch.empty((6 * N_DOF, N), dtype=torch.float32, device=dev)
+        V32 = torch.empty((N_SPH, N), dtype=torch.float32, device=dev)
+        G32 = torch.empty((N_SPH * N_DOF, N), dtype=torch.float32, device=dev)
+        c32 = make_call(N, Q32.data_ptr(), T32.data_ptr(), J32.data_ptr(), V32.data_ptr(), G32.data_ptr())
+        c32.precision = L.F32
+        c32.grad_mode = L.GRAD_ANALYTIC          # a 1e-7 forward difference is meaningless in FP32
+        variant("fused_fp32_mode(analytic gradient)", BYTES_FUSED // 2, c32)
+        del Q32, T32, J32, V32, G32
         # the fused step in the AoS layout (one contiguous record per configuration, planning.jl:58)
         Na = min(N, 1 << 22)
         Qa = Q[:, :Na].t().contiguous()

@@ -77,23 +77,18 @@ class BoxSDF(AbstractSDF):
         return self.world_pose()[None], self.width[None]
 
 
-_OBST_CACHE = {}
-
-
 def _obstacle_transform(mech: Mechanism, link: Link):
     """World pose of an attached SDF link at the obstacle mechanism's current state (FK runs on the GPU,
-    N = 1), memoised per state version like the reference memoises inv_pose (sdf.jl:14-20)."""
+    N = 1), memoised on the mechanism per state version like the reference memoises inv_pose (sdf.jl:14-20)."""
     from .algorithm import get_transform
-    key = id(mech)
-    ent = _OBST_CACHE.get(key)
-    if ent is None or ent[0] != (mech._state_version, mech._structure_version):
-        ent = ((mech._state_version, mech._structure_version), {})
-        _OBST_CACHE[key] = ent
-    if link.id not in ent[1]:
-        single, Q = mech._single, mech._Q
-        assert single, "an obstacle mechanism must hold a single configuration"
-        ent[1][link.id] = get_transform(mech, link).mat
-    return ent[1][link.id]
+    version = (mech._state_version, mech._structure_version)
+    cache = getattr(mech, "_sdf_pose_cache", None)
+    if cache is None or cache[0] != version:
+        cache = mech._sdf_pose_cache = (version, {})
+    if link.id not in cache[1]:
+        assert mech._single, "an obstacle mechanism must hold a single configuration"
+        cache[1][link.id] = get_transform(mech, link).mat
+    return cache[1][link.id]
 
 
 class UnionSDF(AbstractSDF):

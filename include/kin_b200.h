@@ -70,9 +70,14 @@ typedef enum {
 typedef enum { KIN_F64 = 0, KIN_F32 = 1 } KinPrecision;
 typedef enum { KIN_LAYOUT_SOA = 0, KIN_LAYOUT_AOS = 1, KIN_LAYOUT_TILED32 = 2 } KinLayout;
 typedef enum { KIN_JOINT_FIXED = 0, KIN_JOINT_REVOLUTE = 1, KIN_JOINT_PRISMATIC = 2 } KinJointType;
-/* sdf.jl:34-41,116-119 is a forward difference (eps 1e-7) on the argmin box; KIN_GRAD_ANALYTIC is
- * the closed form of the same box (an extension, off by default). */
-typedef enum { KIN_GRAD_FD = 0, KIN_GRAD_ANALYTIC = 1 } KinGradMode;
+/* sdf.jl:34-41,116-119 is a forward difference (eps 1e-7) on the argmin box.
+ *   KIN_GRAD_FD         the reference's FD quotient.  Away from the kinks of the box SDF it is computed from the
+ *                       closed form of the quotient (series in eps / f, truncation < 1e-12); within 2 eps of a
+ *                       kink or 1e-3 of the surface the three perturbed points are evaluated directly.
+ *   KIN_GRAD_FD_DIRECT  always evaluates the three perturbed points (what the reference literally does;
+ *                       ~10 % slower, agrees with KIN_GRAD_FD to the rounding noise of the FD, ~1e-9).
+ *   KIN_GRAD_ANALYTIC   the closed-form gradient of the same box (an extension, off by default). */
+typedef enum { KIN_GRAD_FD = 0, KIN_GRAD_ANALYTIC = 1, KIN_GRAD_FD_DIRECT = 2 } KinGradMode;
 /* collision.jl:76,90 reuses ONE 3 x n_dof Jacobian scratch across the spheres of a call and
  * get_jacobian! (algorithm.jl:91-96) only overwrites relevant columns, so a sphere inherits the
  * columns of joints that do not move it from the previous non-truncated sphere.

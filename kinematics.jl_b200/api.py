@@ -1,6 +1,6 @@
 """Public surface of the B200 backend: the export list of the reference (Kinematics.jl:45-70) for the
 hot path, same names and argument meaning, evaluated by libkin_b200 (no CPU fallback)."""
-from .lib import (AOS, F32, F64, GRAD_ANALYTIC, GRAD_FD, SCRATCH_CLEAN, SCRATCH_REFERENCE, SOA, TILED32, KinError, build)
+from .lib import (AOS, F32, F64, GRAD_ANALYTIC, GRAD_FD, GRAD_FD_DIRECT, SCRATCH_CLEAN, SCRATCH_REFERENCE, SOA, TILED32, KinError, build)
 from .lib import lib as load_library
 from .transform import Transform, rotation, rpy, translation
 from .mechanism import (FIXED, PRISMATIC, REVOLUTE, BoxMetaData, Joint, Link, Mechanism, MeshMetaData, SphereMetaData,

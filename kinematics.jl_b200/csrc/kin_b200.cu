@@ -242,7 +242,7 @@ int validate_call(const KinModel *m, const KinCall *c) {
     if ((c->grads_out || c->argmin_out) && !c->vals_out) return fail(KIN_ERR_INVALID_ARGUMENT, "grads_out/argmin_out need vals_out");
     if (c->vals_out && m->hm.n_sph == 0) return fail(KIN_ERR_INVALID_ARGUMENT, "collision requested but the model has no spheres");
     if (c->vals_out && m->hm.n_box == 0) return fail(KIN_ERR_INVALID_ARGUMENT, "collision requested but the model has no boxes");
-    if (c->grad_mode != KIN_GRAD_FD && c->grad_mode != KIN_GRAD_ANALYTIC) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown grad_mode");
+    if (c->grad_mode != KIN_GRAD_FD && c->grad_mode != KIN_GRAD_ANALYTIC && c->grad_mode != KIN_GRAD_FD_DIRECT) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown grad_mode");
     if (c->scratch_mode != KIN_SCRATCH_REFERENCE && c->scratch_mode != KIN_SCRATCH_CLEAN) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown scratch_mode");
     if (std::isnan(c->truncation_dist)) return fail(KIN_ERR_INVALID_ARGUMENT, "truncation_dist is NaN");
     return KIN_OK;
@@ -486,7 +486,7 @@ int kin_sdf_points(int32_t n_boxes, const double *box_pose, const double *box_wi
     if (n_boxes <= 0) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_sdf_points needs at least one box");
     if (precision != KIN_F64 && precision != KIN_F32) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown precision");
     if (layout != KIN_LAYOUT_SOA && layout != KIN_LAYOUT_AOS) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown layout");
-    if (grad_mode != KIN_GRAD_FD && grad_mode != KIN_GRAD_ANALYTIC) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown grad_mode");
+    if (grad_mode != KIN_GRAD_FD && grad_mode != KIN_GRAD_ANALYTIC && grad_mode != KIN_GRAD_FD_DIRECT) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown grad_mode");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
         cudaGetLastError();

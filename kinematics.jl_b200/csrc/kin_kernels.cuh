@@ -152,29 +152,93 @@ __device__ __forceinline__ void box_grad_analytic(const BoxRow<real> &b, real px
     for (int r = 0; r < 3; ++r) g[r] = fma_(b.r[0 + r], gl[0], fma_(b.r[3 + r], gl[1], b.r[6 + r] * gl[2]));
 }
 
-// gradient!(sdf, p, out) on the argmin box (sdf.jl:34-41, 116-119)
+// The reference's forward difference  g_i = (f(p + eps e_i) - f(p)) / eps,  eps = 1e-7  (sdf.jl:34-41), evaluated
+// directly: three more box evaluations and three square roots.
 template <typename real>
-__device__ __forceinline__ void box_gradient(const BoxRow<real> &b, int grad_mode, real px, real py, real pz, real dmin, real g[3]) {
-    if (grad_mode == 0) {
-        // (f(p + eps e_i) - f(p)) / eps with eps = 1e-7; the division is done as a multiplication by 1e7
-        // (differs from x / 1e-7 by at most 1 ulp of the quotient, far below the FD truncation error).
-        // The three evaluations share ONE rare "inside the box" branch so that their dependency chains
-        // interleave (a data-dependent branch per evaluation costs ~35 cycles and serialises them).
-        const real eps = real(1e-7), ieps = real(1e7);
-        real k[3], qx[3], qy[3], qz[3];
-        k[0] = box_key_outside(b, px + eps, py, pz, qx[0], qy[0], qz[0]);
-        k[1] = box_key_outside(b, px, py + eps, pz, qx[1], qy[1], qz[1]);
-        k[2] = box_key_outside(b, px, py, pz + eps, qx[2], qy[2], qz[2]);
-        if (!(k[0] > real(0)) || !(k[1] > real(0)) || !(k[2] > real(0))) {
-            #pragma unroll
-            for (int i = 0; i < 3; ++i)
-                if (!(k[i] > real(0))) k[i] = box_inside_key(qx[i], qy[i], qz[i]);
+__device__ __forceinline__ void box_gradient_fd_direct(const BoxRow<real> &b, real px, real py, real pz, real dmin, real g[3]) {
+    // the division is done as a multiplication by 1e7 (differs from x / 1e-7 by at most 1 ulp of the quotient).
+    // The three evaluations share ONE rare "inside the box" branch so that their dependency chains interleave.
+    const real eps = real(1e-7), ieps = real(1e7);
+    real k[3], qx[3], qy[3], qz[3];
+    k[0] = box_key_outside(b, px + eps, py, pz, qx[0], qy[0], qz[0]);
+    k[1] = box_key_outside(b, px, py + eps, pz, qx[1], qy[1], qz[1]);
+    k[2] = box_key_outside(b, px, py, pz + eps, qx[2], qy[2], qz[2]);
+    if (!(k[0] > real(0)) || !(k[1] > real(0)) || !(k[2] > real(0))) {
+        #pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (!(k[i] > real(0))) k[i] = box_inside_key(qx[i], qy[i], qz[i]);
+    }
+    #pragma unroll
+    for (int i = 0; i < 3; ++i) g[i] = (key_to_dist(k[i]) - dmin) * ieps;
+}
+
+// The same forward-difference QUOTIENT from the closed form of the box distance (FP64 only).
+// With l = inv_pose * p, q_k = |l_k| - h_k, sigma_k = sign(l_k) and away from every kink of the SDF (no l_k
+// changes sign, no q_k crosses zero, the arg-max of q does not change within eps):
+//   outside (f = |max(q,0)| > 0):  f(p + eps e_i)^2 = f^2 + 2 a eps + v eps^2  with  a = sum_k m_k sigma_k R_ki,
+//     v = sum_{k: q_k > 0} R_ki^2, hence with u = a / f, w = eps / (2 f):
+//         (f(p + eps e_i) - f) / eps = u + (v - u^2) w (1 - 2 u w) + O((eps / f)^3)
+//     (first term = the analytic gradient, the rest = exactly the truncation error the reference's FD carries);
+//   inside  (f = max_k q_k = q_j < 0):  the quotient is sigma_j R_ji exactly.
+// For f > 1e-3 the neglected term is < 1e-12, far below the rounding noise of the direct evaluation itself
+// (~2 ulp(f) / eps ~ 1e-9).  Returns false when the point is within 2 eps of a kink, within 1e-3 of the surface
+// from outside, or the inside arg-max is not separated by 4 eps: the caller then evaluates the FD directly.
+__device__ __forceinline__ bool box_gradient_fd_series(const BoxRow<double> &b, double px, double py, double pz, double f, double g[3]) {
+    const double eps = 1e-7;
+    double l[3], q[3];
+    l[0] = fma(b.r[0], px, fma(b.r[1], py, fma(b.r[2], pz, b.t[0])));
+    l[1] = fma(b.r[3], px, fma(b.r[4], py, fma(b.r[5], pz, b.t[1])));
+    l[2] = fma(b.r[6], px, fma(b.r[7], py, fma(b.r[8], pz, b.t[2])));
+    const double two_eps = 2 * eps;
+    #pragma unroll
+    for (int k = 0; k < 3; ++k) q[k] = fabs(l[k]) - b.h[k];
+    // six DSETPs chained on one predicate (no short-circuit: '&', not '&&')
+    const bool clear = (fabs(l[0]) > two_eps) & (fabs(l[1]) > two_eps) & (fabs(l[2]) > two_eps) &
+                       (fabs(q[0]) > two_eps) & (fabs(q[1]) > two_eps) & (fabs(q[2]) > two_eps);
+    if (!clear) return false;
+    if (f > 0.0) {
+        if (!(f > 1e-3)) return false;
+        const double hf = 0.5 / f, w = eps * hf;
+        double n2[3], act[3];
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            n2[k] = copysign(q[k] + fabs(q[k]), l[k]);            // 2 m_k sigma_k (the exact clamp of box_key_outside)
+            act[k] = q[k] > 0.0 ? 1.0 : 0.0;
         }
         #pragma unroll
-        for (int i = 0; i < 3; ++i) g[i] = (key_to_dist(k[i]) - dmin) * ieps;
-    } else {
-        box_grad_analytic(b, px, py, pz, g);
+        for (int i = 0; i < 3; ++i) {
+            const double r0 = b.r[i], r1 = b.r[3 + i], r2 = b.r[6 + i];               // column i of inv_R
+            const double u = fma(n2[0], r0, fma(n2[1], r1, n2[2] * r2)) * hf;         // a / f
+            const double v = fma(act[0] * r0, r0, fma(act[1] * r1, r1, act[2] * r2 * r2));
+            const double c = fma(-u, u, v);
+            g[i] = fma(c * w, fma(-2.0 * u, w, 1.0), u);
+        }
+        return true;
     }
+    // inside: f = max_k q_k; the arg-max must be stable under the perturbation
+    int j = 0;
+    if (q[1] > q[j]) j = 1;
+    if (q[2] > (j == 1 ? q[1] : q[0])) j = 2;
+    const double qj = j == 0 ? q[0] : (j == 1 ? q[1] : q[2]);
+    double second = -1e300;
+    #pragma unroll
+    for (int k = 0; k < 3; ++k) if (k != j && q[k] > second) second = q[k];
+    if (!(qj - second > 4 * eps)) return false;
+    const double lj = j == 0 ? l[0] : (j == 1 ? l[1] : l[2]);
+    const double sg = lj < 0.0 ? -1.0 : 1.0;
+    #pragma unroll
+    for (int i = 0; i < 3; ++i) g[i] = sg * (j == 0 ? b.r[i] : (j == 1 ? b.r[3 + i] : b.r[6 + i]));
+    return true;
+}
+__device__ __forceinline__ bool box_gradient_fd_series(const BoxRow<float> &, float, float, float, float, float[3]) { return false; }
+
+// gradient!(sdf, p, out) on the argmin box (sdf.jl:34-41, 116-119).
+// grad_mode 0 = forward difference (series where valid, else direct), 1 = analytic, 2 = forward difference, always direct
+template <typename real>
+__device__ __forceinline__ void box_gradient(const BoxRow<real> &b, int grad_mode, real px, real py, real pz, real dmin, real g[3]) {
+    if (grad_mode == 1) { box_grad_analytic(b, px, py, pz, g); return; }
+    if (grad_mode == 0 && box_gradient_fd_series(b, px, py, pz, dmin, g)) return;
+    box_gradient_fd_direct(b, px, py, pz, dmin, g);
 }
 
 // Euler-rate coefficients of rpy_derivative! (algorithm.jl:56-63) for the link rotation R (row-major):
@@ -379,7 +443,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 }
                 if (JR > 0) {
                     switch (qcol) {       // uniform branch: one register copy, static indices
-                        #define KIN_CASE(k) case k: if (k < JR) jfr[k < JR ? k : 0] = f; break;
+                        #define KIN_CASE(k) case k: if (k < JR) { asm volatile(""); jfr[k < JR ? k : 0] = f; } break;
                         KIN_CASE(0) KIN_CASE(1) KIN_CASE(2) KIN_CASE(3) KIN_CASE(4) KIN_CASE(5) KIN_CASE(6) KIN_CASE(7)
                         #undef KIN_CASE
                         default: break;

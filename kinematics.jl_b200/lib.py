@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 F64, F32 = 0, 1
 SOA, AOS, TILED32 = 0, 1, 2
 FIXED, REVOLUTE, PRISMATIC = 0, 1, 2
-GRAD_FD, GRAD_ANALYTIC = 0, 1
+GRAD_FD, GRAD_ANALYTIC, GRAD_FD_DIRECT = 0, 1, 2
 SCRATCH_REFERENCE, SCRATCH_CLEAN = 0, 1
 POSE_IK_OBJECTIVE, POSE_CONSTRAINT = 0, 1
 

@@ -195,6 +195,64 @@ def test_fridge_union_points_vs_oracle():
     np.testing.assert_allclose(host(g_fd), gf_ref, rtol=0, atol=1e-7)
 
 
+def test_fd_series_matches_direct_fd_near_every_kink():
+    """KIN_GRAD_FD evaluates the FD quotient of sdf.jl:34-41 from its closed form away from kinks and
+    directly near them; KIN_GRAD_FD_DIRECT always perturbs the point as the reference does.  The two (and
+    the oracle) must agree to the FD's own rounding noise everywhere, in particular for points placed a few
+    eps from each kind of kink: faces (q_k = 0), the mid-planes (l_k = 0), edges/corners, the surface seen
+    from outside, and the medial surfaces inside the box."""
+    from kinematics_jl_b200.transform import rotz, rotation, translation
+    cy, sy = np.cos(-0.5), np.sin(-0.5)
+    pose = K.Transform(np.array([0.4, -0.2, 0.7]), rotz(0.3) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]))
+    half = np.array([0.3, 0.2, 0.5])
+    box = K.BoxSDF(pose, 2 * half)
+    rng = np.random.default_rng(5)
+    eps = 1e-7
+    offs = np.array([0.0, 0.3, 0.9, 1.1, 1.9, 2.1, 3.9, 4.1, 30.0, 1e4, 2e4]) * eps
+    offs = np.concatenate([offs, -offs])
+    local = [(rng.random((20000, 3)) - 0.5) * 2.4]                      # bulk: inside and outside
+    for k in range(3):
+        for o in offs:
+            base = (rng.random((40, 3)) - 0.5) * 2.0 * half * 1.6
+            a = base.copy(); a[:, k] = half[k] + o; local.append(a)      # near a face plane (inside the face or beyond its edges)
+            a = base.copy(); a[:, k] = -half[k] - o; local.append(a)
+            a = base.copy(); a[:, k] = o; local.append(a)                # near a mid-plane: sign(l_k) flips
+            a = base.copy(); a[:, k] = half[k] + o; a[:, (k + 1) % 3] = half[(k + 1) % 3] + rng.choice(offs, 40)
+            local.append(a)                                              # near an edge
+    # inside, near the medial surfaces q_j == q_k
+    m = (rng.random((400, 3)) - 0.5) * 2 * half
+    for o in offs[:8]:
+        a = m.copy(); a[:, 0] = half[0] - (half[1] - np.abs(a[:, 1])) + o; local.append(a)
+    local = np.concatenate(local)
+    pts = local @ rotation(pose).T + translation(pose)
+    g_fd = host(box.gradient(dev(pts)))
+    g_dir = host(box.gradient(dev(pts), grad_mode=K.GRAD_FD_DIRECT))
+    so = R.BoxSDF(pose.mat, 2 * half)
+    g_ref = np.zeros_like(pts)
+    for i, p in enumerate(pts):
+        so(p)                                   # the reference differences against the cached value (sdf.jl:116-119)
+        g_ref[i] = so.gradient(p)
+    # the direct path restates the reference's arithmetic: rounding-level agreement with the oracle
+    np.testing.assert_allclose(g_dir, g_ref, rtol=0, atol=5e-8)
+    # the series path agrees with both to the FD's rounding noise (~ulp(f)/eps)
+    np.testing.assert_allclose(g_fd, g_dir, rtol=0, atol=5e-8)
+    np.testing.assert_allclose(g_fd, g_ref, rtol=0, atol=5e-8)
+    far = np.abs(g_fd - g_dir).max()
+    assert far < 5e-8, far
+
+
+def test_fd_series_matches_direct_fd_on_a_large_fused_batch():
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(True)
+    K.set_joint_angles(m, joints, dev(scenes.random_configs(jo, 1 << 20, True, seed=11)))
+    out = {}
+    for mode in (K.GRAD_FD, K.GRAD_FD_DIRECT):
+        v, g = K.compute_coll_dists_and_grads(sscc, joints, sdf, truncation_dist=0.25, grad_mode=mode)
+        out[mode] = (host(v), host(g))
+    assert np.array_equal(out[K.GRAD_FD][0], out[K.GRAD_FD_DIRECT][0])            # distances do not depend on the mode
+    diff = np.abs(out[K.GRAD_FD][1] - out[K.GRAD_FD_DIRECT][1])
+    assert diff.max() < 1e-7, diff.max()
+
+
 # ------------------------------------------------------------------------------------------------
 # collision (test_collision.jl + the 16-sphere / fridge scene)
 # ------------------------------------------------------------------------------------------------

@@ -198,7 +198,12 @@ __device__ __forceinline__ bool box_gradient_fd_series(const BoxRow<double> &b, 
     if (!clear) return false;
     if (f > 0.0) {
         if (!(f > 1e-3)) return false;
-        const double hf = 0.5 / f, w = eps * hf;
+        // 1 / f to ~1e-14 relative (single-precision seed + one Newton step; f > 1e-3 is well inside the float range):
+        // the quotient only has to match the reference's FD to its rounding noise, a full IEEE division costs 4x more
+        float seed;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"((float)f));      // one MUFU.RCP
+        const double r0 = (double)seed;
+        const double hf = 0.5 * fma(r0, fma(-f, r0, 1.0), r0), w = eps * hf;
         double n2[3], act[3];
         #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -686,7 +691,8 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     }
                     if (!want_grads) continue;
                     if (truncated) {            // collision.jl:84-86
-                        for (int j = 0; j < ND; ++j, Gp += es) *Gp = real(0);
+                        for (int j = 0; j < ND; ++j) Gp[(size_t)j * es] = real(0);
+                        Gp += (size_t)ND * es;
                         continue;
                     }
                     const real *cs = &SCR(so_cent + 3 * s);
@@ -709,9 +715,10 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                         } else if (stale) {     // column left over from an earlier sphere (collision.jl:76,90)
                             cx = st[0]; cy = st[BS]; cz = st[2 * BS];
                         } else { cx = cy = cz = real(0); }
-                        *Gp = fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz));   // transpose(grad) * jac
-                        Gp += es; jf += 6 * BS; st += 3 * BS;
+                        Gp[(size_t)j * es] = fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz));   // transpose(grad) * jac
+                        jf += 6 * BS; st += 3 * BS;
                     }
+                    Gp += (size_t)ND * es;      // (a pointer bumped inside the loop is live across its early exit: two extra moves per column)
                 }
             }
         }

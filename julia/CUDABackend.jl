@@ -21,7 +21,7 @@ const libkin = get(ENV, "KIN_B200_LIB", "libkin_b200.so")
 
 const KIN_F64, KIN_F32 = Cint(0), Cint(1)
 const KIN_LAYOUT_SOA, KIN_LAYOUT_AOS, KIN_LAYOUT_TILED32 = Cint(0), Cint(1), Cint(2)
-const KIN_GRAD_FD, KIN_GRAD_ANALYTIC = Cint(0), Cint(1)
+const KIN_GRAD_FD, KIN_GRAD_ANALYTIC, KIN_GRAD_FD_DIRECT = Cint(0), Cint(1), Cint(2)
 const KIN_SCRATCH_REFERENCE, KIN_SCRATCH_CLEAN = Cint(0), Cint(1)
 
 # include/kin_b200.h: KinModelDesc

@@ -14,6 +14,7 @@
 
 #include "../../include/kin_b200.h"
 #include "kin_kernels.cuh"
+#include "kin_kernels_ws.cuh"
 #include "kin_model.hpp"
 
 namespace {
@@ -57,7 +58,7 @@ struct HostStage {          // resources of kin_eval_host, created on first use
 
 struct KinModel {
     kin::HostModel hm;
-    int device = 0, n_sm = 0;
+    int device = 0, n_sm = 0, dev_smem = 0;
     cudaMemPool_t pool = nullptr;   // stream-ordered workspace pool that keeps its memory between calls
     std::mutex mu;
     std::map<std::vector<int>, DeviceProgram *> cache;
@@ -146,6 +147,20 @@ const int kBS[kNumBS] = {128, 96, 64, 32};
      {KIN_K(real, aos, 64, false), KIN_K(real, aos, 64, true)}, {KIN_K(real, aos, 32, false), KIN_K(real, aos, 32, true)}}
 const KernelFn kKernels[2][3][kNumBS][2][2] = {{KIN_BS_ROW(double, 0), KIN_BS_ROW(double, 1), KIN_BS_ROW(double, 2)},
                                                {KIN_BS_ROW(float, 0), KIN_BS_ROW(float, 1), KIN_BS_ROW(float, 2)}};
+
+// Warp-specialised fused kernel (kin_kernels_ws.cuh): FP64, SoA / tiled, collision, <= 8 columns, a chain without
+// save slots, ring fits in shared memory, and a batch large enough to fill one 384-thread CTA per SM a few times.
+const KernelFn kWsKernels[2] = {kin::kin_eval_ws_kernel<0>, kin::kin_eval_ws_kernel<2>};
+constexpr long long kWsMinBatch = 1 << 16;
+
+bool ws_eligible(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
+    const kin::ProgHeader &h = dp->prog.h;
+    if (std::getenv("KIN_DISABLE_WS")) return false;          // tuning / test aid: force kin_eval_kernel
+    if (c->precision != KIN_F64 || (c->layout != KIN_LAYOUT_SOA && c->layout != KIN_LAYOUT_TILED32)) return false;
+    if (!c->vals_out || h.n_sph <= 0 || h.n_dof > kin::JF_REGS || h.so_jf != h.so_save) return false;
+    if (c->n < kWsMinBatch && !std::getenv("KIN_FORCE_WS")) return false;
+    return kin::ws_smem_bytes(h) <= (size_t)m->dev_smem;
+}
 
 int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
     const kin::ProgHeader &h = dp->prog.h;
@@ -262,6 +277,24 @@ int launch(KinModel *m, const KinCall *c, DeviceProgram *dp, cudaStream_t stream
     a.with_rot = c->with_rot ? 1 : 0; a.rpy_jac = c->rpy_jac ? 1 : 0; a.keep_irrelevant = c->keep_irrelevant ? 1 : 0;
     a.grad_mode = c->grad_mode; a.scratch_ref = c->scratch_mode == KIN_SCRATCH_REFERENCE;
     a.truncation_dist = c->truncation_dist; a.vals_offset = c->vals_offset;
+    if (ws_eligible(m, c, dp)) {
+        const KernelFn k = kWsKernels[li == KIN_LAYOUT_TILED32 ? 1 : 0];
+        const size_t smem = kin::ws_smem_bytes(dp->prog.h);
+        CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long tiles = (c->n + kin::WS_TILE - 1) / kin::WS_TILE;
+        const long long grid = tiles < m->n_sm ? tiles : m->n_sm;
+        if (grid < 1) return KIN_OK;
+        // hand-over ring: stream-ordered scratch from the model's pool (concurrent launches get their own)
+        void *ring = nullptr;
+        CUDA_TRY(cudaMallocFromPoolAsync(&ring, kin::ws_ring_bytes(dp->prog.h, (int)grid), m->pool, stream));
+        a.ws_ring = ring;
+        k<<<(unsigned)grid, kin::WS_THREADS, smem, stream>>>(a);
+        cudaError_t le = cudaGetLastError();
+        cudaFreeAsync(ring, stream);
+        if (le != cudaSuccess) return fail_cuda(le, "launching kin_eval_ws_kernel");
+        g_launches.fetch_add(1);
+        return KIN_OK;
+    }
     const int block = dp->block[pi][li];
     const long long tiles = (c->n + block - 1) / block;
     long long grid = (long long)dp->occ[pi][li] * m->n_sm;
@@ -296,6 +329,7 @@ int kin_model_create(const KinModelDesc *d, KinModel **out) {
     if (rc != KIN_OK) { delete m; return rc; }
     cudaError_t e = cudaGetDevice(&m->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, m->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
     if (e == cudaSuccess) {
         // workspaces (kin_pose_residual, kin_sdf_points) come from a private pool whose release threshold is
         // "never": the default pool hands memory back at every synchronisation and re-mapping hundreds of MB
@@ -391,6 +425,16 @@ int kin_query_launch(KinModel *m, const KinCall *c, int32_t *regs, int32_t *smem
     rc = get_program(m, c, &dp);
     if (rc != KIN_OK) return rc;
     const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
+    if (ws_eligible(m, c, dp)) {
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, kWsKernels[li == KIN_LAYOUT_TILED32 ? 1 : 0]));
+        const long long tiles = (c->n + kin::WS_TILE - 1) / kin::WS_TILE;
+        if (regs) *regs = fa.numRegs;            // launch value; setmaxnreg moves it to 104 (producer) / 200 (consumers)
+        if (smem_bytes) *smem_bytes = (int32_t)kin::ws_smem_bytes(dp->prog.h);
+        if (block) *block = kin::WS_THREADS;
+        if (grid) *grid = (int32_t)(tiles < m->n_sm ? tiles : m->n_sm);
+        return KIN_OK;
+    }
     const int b = dp->block[pi][li];
     long long tiles = (c->n + b - 1) / b, g = (long long)dp->occ[pi][li] * m->n_sm;
     if (g > tiles) g = tiles;

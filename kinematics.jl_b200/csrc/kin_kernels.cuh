@@ -36,6 +36,7 @@ struct KernelArgs {
     int with_rot, rpy_jac, keep_irrelevant;
     int grad_mode, scratch_ref;  // scratch_ref = 1: reproduce the reference's shared Jacobian scratch
     double truncation_dist, vals_offset;
+    void *ws_ring;               // kin_eval_ws_kernel only: global hand-over ring (kin_kernels_ws.cuh)
 };
 
 template <typename real> struct Tf { real r[9]; real p[3]; };   // rotation row-major

@@ -168,7 +168,7 @@ def untile32(x, N):
 def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac_links=None, with_rot=True,
              rpy_jac=False, keep_irrelevant=False, J_into=None, collision=False, with_grads=True,
              truncation_dist=np.inf, grad_mode=_lib.GRAD_FD, scratch_mode=_lib.SCRATCH_REFERENCE,
-             want_argmin=False, vals_offset=0.0, stream=None):
+             want_argmin=False, vals_offset=0.0, stream=None, launch_info=False):
     """One ``kin_eval``.  Outputs are allocated in the layout of the call (default: the layout of Q) and
     returned as batch-first VIEWS: T (N, n_fk, 3, 4), J (N, n_jac, rows, cols), vals (N, S),
     grads (N, n_dof, S), argmin (N, S)."""
@@ -246,4 +246,8 @@ def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac
     _lib.check(_lib.lib().kin_eval(dm.h, C.byref(c)))
     for key, store, perm_soa, perm_aos in pending:
         out[key] = view(store, perm_soa, perm_aos)
+    if launch_info:                          # which kernel configuration this call maps to (kin_query_launch)
+        regs, smem, block, grid = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().kin_query_launch(dm.h, C.byref(c), C.byref(regs), C.byref(smem), C.byref(block), C.byref(grid)))
+        out["launch"] = {"regs": regs.value, "smem_bytes": smem.value, "block": block.value, "grid": grid.value}
     return out

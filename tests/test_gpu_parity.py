@@ -195,6 +195,52 @@ def test_fridge_union_points_vs_oracle():
     np.testing.assert_allclose(host(g_fd), gf_ref, rtol=0, atol=1e-7)
 
 
+@pytest.mark.parametrize("layout", [L.SOA, L.TILED32])
+@pytest.mark.parametrize("n", [1, 300, 70001])
+def test_warp_specialised_kernel_is_bitwise_identical(layout, n, monkeypatch):
+    """Large FP64 SoA / tiled collision launches take the warp-specialised kernel (kin_kernels_ws.cuh: producer
+    warps walk the chain, consumer warps do the sphere work).  It runs the same arithmetic in the same order as
+    kin_eval_kernel, so every output must be bitwise identical -- for ragged batches, with and without
+    truncation, in both scratch modes and all gradient modes."""
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
+    q = scenes.random_configs(jo, n, False, seed=17, zeros_every=97)
+    from kinematics_jl_b200.device import current_q, evaluate
+    K.set_joint_angles(m, joints, dev(q))
+    K.compute_coll_dists(sscc, joints, sdf)                         # uploads sphere / box tables
+    dm = device_model(m)
+    Q, ql, N = current_q(m)
+    assert N == n and dm.n_dof == 8
+    fk = [l.id for l in m.links[:25]]
+    jac = [K.find_link(m, "gripper_link").id, K.find_link(m, "wrist_flex_link").id]
+
+    def run(**kw):
+        out = evaluate(dm, Q, ql, N, layout=layout, fk_links=fk, jac_links=jac, with_rot=True, rpy_jac=True,
+                       collision=True, want_argmin=True, launch_info=True, **kw)
+        torch.cuda.synchronize()
+        return {k: out[k].contiguous().clone() for k in ("T", "J", "vals", "grads", "argmin")}, out["launch"]["block"]
+
+    cases = [dict(truncation_dist=np.inf, grad_mode=K.GRAD_FD, scratch_mode=K.SCRATCH_REFERENCE),
+             dict(truncation_dist=0.08, grad_mode=K.GRAD_FD_DIRECT, scratch_mode=K.SCRATCH_REFERENCE, vals_offset=0.03),
+             dict(truncation_dist=0.3, grad_mode=K.GRAD_ANALYTIC, scratch_mode=K.SCRATCH_CLEAN)]
+    for kw in cases:
+        monkeypatch.delenv("KIN_DISABLE_WS", raising=False)
+        monkeypatch.setenv("KIN_FORCE_WS", "1")
+        n0 = L.lib().kin_launch_count()
+        ws, block = run(**kw)
+        assert L.lib().kin_launch_count() == n0 + 1 and block == 384          # one warp-specialised launch
+        monkeypatch.setenv("KIN_DISABLE_WS", "1")
+        classic, block = run(**kw)
+        assert block in (32, 64, 96, 128)
+        for k in ws:
+            assert torch.equal(ws[k], classic[k]), (k, kw)
+    # and against the oracle once
+    v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, q[:2000], np.inf, R.GRAD_FD, R.SCRATCH_REFERENCE)
+    monkeypatch.delenv("KIN_DISABLE_WS", raising=False)
+    ws, _ = run(**cases[0])
+    np.testing.assert_allclose(host(ws["vals"])[:2000], v_ref, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(host(ws["grads"])[:2000], g_ref.transpose(0, 2, 1), rtol=0, atol=1e-7)
+
+
 def test_fd_series_matches_direct_fd_near_every_kink():
     """KIN_GRAD_FD evaluates the FD quotient of sdf.jl:34-41 from its closed form away from kinks and
     directly near them; KIN_GRAD_FD_DIRECT always perturbs the point as the reference does.  The two (and

@@ -16,7 +16,7 @@
 // 12 resident warps (3 per sub-partition: one producer + two consumers) instead of 8; the producer's 5k
 // instructions per configuration and the consumers' 11k balance at one producer per two consumers.
 //
-// The ring lives in GLOBAL memory (one region per CTA, 4 stages x 96 KB, reused every few microseconds and
+// The ring lives in GLOBAL memory (one region per CTA, 2 stages x 96 KB -- measured: 4 stages 17.1 ms, 3: 16.7, 2: 16.3 per 2^24 -- reused every few microseconds and
 // therefore L2-resident): shared memory cannot hold both the consumers' per-configuration state (80 slots x 256
 // threads = 160 KB) and a hand-over buffer deep enough to keep them busy -- a first version with a two-stage
 // ring in shared memory left each consumer idle while its only stage was being refilled and ended 3 % slower
@@ -33,7 +33,13 @@ namespace kin {
 
 constexpr int WS_TILE = 128;                     // configurations per tile = threads per warpgroup
 constexpr int WS_THREADS = 3 * WS_TILE;
-constexpr int WS_STAGES = 4;                     // ring depth (tiles)
+#ifndef KIN_WS_STAGES
+#define KIN_WS_STAGES 2
+#endif
+#ifndef KIN_WS_SLEEP_NS
+#define KIN_WS_SLEEP_NS 200
+#endif
+constexpr int WS_STAGES = KIN_WS_STAGES;         // ring depth (tiles)
 constexpr int WS_FRAME_SLOTS = 6 * JF_REGS;      // ring slots [0, 48): joint frames, [48, 48 + 3 S): sphere centres
 // consumer-private shared slots: [0, 3 S) centres, then the shared Jacobian scratch of collision.jl:76 (3 x 8),
 // then (dmin, argmin) of the current sphere group
@@ -71,7 +77,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
 }
 // a waiting warp sleeps between polls so that it does not take issue slots from the warps it is waiting for
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+    while (!mbar_try_wait(bar, parity)) __nanosleep(KIN_WS_SLEEP_NS);
 }
 
 // The ring is re-used every few microseconds while 4 KB of results per configuration stream through the same L2:

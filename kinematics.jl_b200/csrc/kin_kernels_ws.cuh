@@ -316,18 +316,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
             const long long n = min((blockIdx.x + k * gridDim.x) * BS + t, (long long)A.n - 1);
             const real *rg = ring + (size_t)st * ring_slots * BS + t;
             mbar_wait(&bars[st], (unsigned)((k / WS_STAGES) & 1));       // full
-            // copy out: frames -> registers, centres -> private shared memory; then the stage is free again
+            // copy out: centres -> private shared memory (asynchronous global -> shared copies: no registers, all in
+            // flight together with the frame loads), frames -> registers; then the stage is free again.
+            // cp.async.ca may allocate in L1; producer and consumer share this SM's L1 and synchronise at CTA scope,
+            // so a later refill of the stage is seen.
+            {
+                const real *src = rg + WS_FRAME_SLOTS * BS;
+                for (int i = 0; i < 3 * S; ++i) cp_async_elem(cent0 + i * BS, src + i * BS);
+                cp_async_commit();
+            }
             JFrame<real> jfr[JR];
             FOR_COLUMNS(j) {
                 const real *jf = rg + 6 * BS * j;
                 jfr[j].o[0] = ring_ld(jf, pol); jfr[j].o[1] = ring_ld(jf + BS, pol); jfr[j].o[2] = ring_ld(jf + 2 * BS, pol);
                 jfr[j].a[0] = ring_ld(jf + 3 * BS, pol); jfr[j].a[1] = ring_ld(jf + 4 * BS, pol); jfr[j].a[2] = ring_ld(jf + 5 * BS, pol);
             }
-            {
-                const real *src = rg + WS_FRAME_SLOTS * BS;
-                #pragma unroll 12
-                for (int i = 0; i < 3 * S; ++i) cent0[i * BS] = ring_ld(src + i * BS, pol);
-            }
+            cp_async_wait<0>();
             mbar_arrive(&bars[WS_STAGES + st]);        // empty: the producer may refill this stage
             if (stale)
                 for (int i = 0; i < 3 * ND; ++i) stale0[i * BS] = real(0);   // jac = zeros(3, n_dof), collision.jl:76

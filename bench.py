@@ -35,9 +35,10 @@ N_LINKS, N_DOF, N_SPH = 25, 8, 16
 BYTES_FKJ = 8 * N_DOF + 8 * 12 * N_LINKS + 8 * 6 * N_DOF                   # 2848
 BYTES_FUSED = BYTES_FKJ + 8 * N_SPH + 8 * N_SPH * N_DOF                     # 4000
 # DRAM bytes per configuration measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one
-# `--set full` capture of a 4 194 304-configuration launch, profiles/r01_final_{fkj,fused}_ncu_summary.txt)
-NCU_DRAM_BYTES_PER_CONFIG_FKJ = (268483072 + 11620233000) / 4194304          # 2834.5
-NCU_DRAM_BYTES_PER_CONFIG_FUSED = (269890816 + 16454000000) / 4194304        # 3987.3
+# `--set full` capture of a 4 194 304-configuration launch, profiles/r01b_fkj_ncu_summary.txt and
+# profiles/r01c_fused_ws_ncu_summary.txt)
+NCU_DRAM_BYTES_PER_CONFIG_FKJ = (268579072 + 11617420000) / 4194304          # 2833.8
+NCU_DRAM_BYTES_PER_CONFIG_FUSED = (271707392 + 16592617000) / 4194304        # 4020.8 (warp-specialised kernel)
 METRIC = "fetch_fk_jacobian_configs_per_s"
 UNIT = "configs/s"
 
@@ -262,7 +263,7 @@ def main():
     info = launch_info(call)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_CONFIG_FKJ * N, "traffic_source": "ncu dram__bytes_read+write per configuration "
-                "(profiles/r01_final_fkj_ncu_summary.txt, 2^22-configuration launch) x configurations per launch",
+                "(profiles/r01b_fkj_ncu_summary.txt, 2^22-configuration launch) x configurations per launch",
                 "peak_source": peak_src, "kernel": "kin_eval_kernel<double,SoA>",
                 "algorithmic_bytes_per_config": BYTES_FKJ, "launch_ms": kern_ms, "launch": info}
 
@@ -280,6 +281,7 @@ def main():
                  "roofline": {"bound": "hbm-or-fp64 (see DESIGN.md)", "achieved": ach_f, "peak": peak, "unit": "GB/s",
                               "frac": ach_f / peak, "algorithmic_bytes_per_config": BYTES_FUSED,
                               "traffic": NCU_DRAM_BYTES_PER_CONFIG_FUSED * N,
+                              "kernel": "kin_eval_ws_kernel<SoA> (block 384) when launch.block == 384, else kin_eval_kernel",
                               "launch": launch_info(callf)}}
         del V, G
 

@@ -85,12 +85,22 @@ __device__ __forceinline__ void tf_mul_const(const Tf<real> &a, const real *__re
 
 // One row of the box table in registers.
 template <typename real> struct BoxRow { real r[9], t[3], h[3]; };
-template <typename real>
-__device__ __forceinline__ void load_box(const real *__restrict__ b, BoxRow<real> &o) {
+__device__ __forceinline__ void load_box(const float *__restrict__ b, BoxRow<float> &o) {
     #pragma unroll
     for (int i = 0; i < 9; ++i) o.r[i] = b[i];
     #pragma unroll
     for (int i = 0; i < 3; ++i) { o.t[i] = b[9 + i]; o.h[i] = b[12 + i]; }
+}
+// FP64 rows are 16-byte aligned (even BOX_REALS, even ro_box, 16-byte aligned table): 8 x 128-bit loads
+__device__ __forceinline__ void load_box(const double *__restrict__ b, BoxRow<double> &o) {
+    const double2 *b2 = reinterpret_cast<const double2 *>(b);
+    double v[16];
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) { const double2 x = b2[i]; v[2 * i] = x.x; v[2 * i + 1] = x.y; }
+    #pragma unroll
+    for (int i = 0; i < 9; ++i) o.r[i] = v[i];
+    #pragma unroll
+    for (int i = 0; i < 3; ++i) { o.t[i] = v[9 + i]; o.h[i] = v[12 + i]; }
 }
 
 // BoxSDF call (sdf.jl:67-74) in "key" form.  With q = |inv_pose * p| - w/2 and s = |max(q,0)|^2 the

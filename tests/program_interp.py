@@ -9,7 +9,7 @@ import numpy as np
 from kinematics_jl_b200 import lib as L
 from kinematics_jl_b200.device import make_desc
 
-NODE_INTS, NODE_REALS, ATT_INTS, ATT_REALS, SPH_REALS, BOX_REALS = 12, 16, 4, 12, 4, 17
+NODE_INTS, NODE_REALS, ATT_INTS, ATT_REALS, SPH_REALS, BOX_REALS = 12, 16, 4, 12, 4, 18
 HEADER_FIELDS = ["n_nodes", "n_att", "n_sph", "n_box", "n_joints", "with_base", "n_dof", "n_fk", "n_jac",
                  "io_node", "io_att", "io_sph_order", "io_sph_mask", "io_col_type", "n_int",
                  "ro_node", "ro_att", "ro_sph", "ro_box", "n_real",

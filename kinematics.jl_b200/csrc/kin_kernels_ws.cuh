@@ -6,10 +6,10 @@
 // the chain walk (phase 1: algorithm.jl:1-54,83-114) ~80 registers, the sphere / box / chain-rule work (phase 2:
 // collision.jl:67-94, sdf.jl:34-41,108-119) ~195 because it holds the eight joint frames in registers.  Here one
 // CTA of 384 threads per SM is split into three warpgroups with `setmaxnreg`:
-//     warpgroup 0  PRODUCER   104 registers: walks the chain of one configuration per thread, writes link
+//     warpgroup 0  PRODUCER   88 registers: walks the chain of one configuration per thread, writes link
 //                  transforms and Jacobians to global memory and hands (joint frames, sphere centres) over
 //                  through a ring of WS_STAGES tiles;
-//     warpgroup 1, 2  CONSUMERS  200 registers: take the frames into registers and the centres into their private
+//     warpgroup 1, 2  CONSUMERS  208 registers (88 + 2 x 208 = 3 x 168): take the frames into registers and the centres into their private
 //                  shared memory, release the ring stage at once, and do phase 2 exactly as kin_eval_kernel does
 //                  (same helpers, same order => bitwise-identical results:
 //                  test_warp_specialised_kernel_is_bitwise_identical).
@@ -41,8 +41,8 @@ constexpr int WS_THREADS = 3 * WS_TILE;
 #endif
 constexpr int WS_STAGES = KIN_WS_STAGES;         // ring depth (tiles)
 constexpr int WS_FRAME_SLOTS = 6 * JF_REGS;      // ring slots [0, 48): joint frames, [48, 48 + 3 S): sphere centres
-// consumer-private shared slots: [0, 3 S) centres, then the shared Jacobian scratch of collision.jl:76 (3 x 8),
-// then (dmin, argmin) of the current sphere group
+// consumer-private shared slots: the shared Jacobian scratch of collision.jl:76 (3 x 8), (dmin, argmin) of the
+// current sphere group, then the 3 S centre coordinates
 __host__ __device__ inline int ws_ring_slots(int n_sph) { return WS_FRAME_SLOTS + 3 * n_sph; }
 __host__ __device__ inline int ws_priv_slots(int n_sph) { return 3 * n_sph + 3 * JF_REGS + 2 * SPH_GROUP; }
 // bytes of global scratch one launch needs (n_cta regions)
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
 
     if (wg == 0) {
         // =========================== PRODUCER: phase 1 ===========================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         auto prefetch_q = [&](long long k_, int buf) {
             const long long n_ = min((blockIdx.x + k_ * gridDim.x) * BS + t, (long long)A.n - 1);
             const real *qn = reinterpret_cast<const real *>(A.q) + rec_base(n_, ND);
@@ -300,16 +300,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
         }
     } else {
         // =========================== CONSUMERS: phase 2 ===========================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         constexpr int JR = JF_REGS;
         const int cw = wg - 1;                         // consumer 0 / 1 takes the even / odd tiles of this CTA
         real *pv = priv + (size_t)cw * priv_slots * BS + t;             // pv[slot * BS]: this thread's private state
         const bool want_grads = A.grads_out != nullptr;
         const bool stale = want_grads && A.scratch_ref;
         const real trunc = (real)A.truncation_dist, voff = (real)A.vals_offset;
-        real *cent0 = pv;
-        real *stale0 = pv + (3 * S) * BS;
-        real *hand = pv + (3 * S + 3 * JF_REGS) * BS;
+        // fixed-size areas first: their slot offsets are compile-time constants (one base register + immediates;
+        // with the S-dependent centres in front the compiler re-derived these addresses from the kernel parameters
+        // in front of every access of the column loop)
+        real *stale0 = pv;
+        real *hand = pv + (3 * JF_REGS) * BS;
+        real *cent0 = pv + (3 * JF_REGS + 2 * SPH_GROUP) * BS;
         #define FOR_COLUMNS(j) _Pragma("unroll") for (int j = 0; j < JR; ++j) if (j >= ND) break; else
         for (long long k = cw; k < my_tiles; k += 2) {
             const int st = (int)(k % WS_STAGES);

@@ -38,7 +38,7 @@ BYTES_FUSED = BYTES_FKJ + 8 * N_SPH + 8 * N_SPH * N_DOF                     # 40
 # `--set full` capture of a 4 194 304-configuration launch, profiles/r01b_fkj_ncu_summary.txt and
 # profiles/r01c_fused_ws_ncu_summary.txt)
 NCU_DRAM_BYTES_PER_CONFIG_FKJ = (268579072 + 11617420000) / 4194304          # 2833.8
-NCU_DRAM_BYTES_PER_CONFIG_FUSED = (271707392 + 16592617000) / 4194304        # 4020.8 (warp-specialised kernel)
+NCU_DRAM_BYTES_PER_CONFIG_FUSED = (272353792 + 16609201000) / 4194304        # 4024.9 (warp-specialised kernel)
 METRIC = "fetch_fk_jacobian_configs_per_s"
 UNIT = "configs/s"
 

@@ -241,6 +241,59 @@ def test_warp_specialised_kernel_is_bitwise_identical(layout, n, monkeypatch):
     np.testing.assert_allclose(host(ws["grads"])[:2000], g_ref.transpose(0, 2, 1), rtol=0, atol=1e-7)
 
 
+def test_warp_specialised_kernel_argument_combinations_and_streams(monkeypatch):
+    """The warp-specialised kernel with outputs switched off one by one (collision only, distances only, no
+    argmin, translation-only geometric Jacobian), bitwise against kin_eval_kernel; then two launches in flight on
+    two streams at once (each takes its own hand-over ring from the model's pool) against the serial result."""
+    from kinematics_jl_b200.device import current_q, evaluate
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
+    n = 40000
+    q = scenes.random_configs(jo, n, False, seed=23)
+    K.set_joint_angles(m, joints, dev(q))
+    K.compute_coll_dists(sscc, joints, sdf)
+    dm = device_model(m)
+    Q, ql, N = current_q(m)
+    fk = [K.find_link(m, "gripper_link").id, K.find_link(m, "head_camera_link").id]
+    jac = [K.find_link(m, "elbow_flex_link").id]
+    combos = [dict(collision=True),                                                        # collision only
+              dict(collision=True, with_grads=False, want_argmin=True),                    # distances + argmin
+              dict(collision=True, fk_links=fk),                                           # no Jacobian
+              dict(collision=True, jac_links=jac, with_rot=False),                         # 3 x n_dof Jacobian
+              dict(collision=True, fk_links=fk, jac_links=jac, with_rot=True, rpy_jac=False, truncation_dist=0.1)]
+
+    def run(kw, stream=None):
+        out = evaluate(dm, Q, ql, N, layout=L.SOA, launch_info=True, stream=stream, **kw)
+        return out
+
+    for kw in combos:
+        monkeypatch.delenv("KIN_DISABLE_WS", raising=False)
+        monkeypatch.setenv("KIN_FORCE_WS", "1")
+        ws = run(kw)
+        assert ws["launch"]["block"] == 384
+        monkeypatch.setenv("KIN_DISABLE_WS", "1")
+        classic = run(kw)
+        assert classic["launch"]["block"] != 384
+        torch.cuda.synchronize()
+        for k in ws:
+            if k != "launch":
+                assert torch.equal(ws[k].contiguous(), classic[k].contiguous()), (k, kw)
+    # concurrent launches on two streams
+    monkeypatch.delenv("KIN_DISABLE_WS", raising=False)
+    kw = combos[-1]
+    serial = run(kw)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for rep in range(4):
+        for st in (s1, s2):
+            with torch.cuda.stream(st):
+                outs.append(run(kw, stream=st.cuda_stream))
+    torch.cuda.synchronize()
+    for o in outs:
+        for k in ("T", "J", "vals", "grads"):
+            assert torch.equal(o[k].contiguous(), serial[k].contiguous()), k
+
+
 def test_fd_series_matches_direct_fd_near_every_kink():
     """KIN_GRAD_FD evaluates the FD quotient of sdf.jl:34-41 from its closed form away from kinks and
     directly near them; KIN_GRAD_FD_DIRECT always perturbs the point as the reference does.  The two (and

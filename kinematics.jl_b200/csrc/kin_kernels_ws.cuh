@@ -6,23 +6,25 @@
 // the chain walk (phase 1: algorithm.jl:1-54,83-114) ~80 registers, the sphere / box / chain-rule work (phase 2:
 // collision.jl:67-94, sdf.jl:34-41,108-119) ~195 because it holds the eight joint frames in registers.  Here one
 // CTA of 384 threads per SM is split into three warpgroups with `setmaxnreg`:
-//     warpgroup 0  PRODUCER   88 registers: walks the chain of one configuration per thread, writes link
-//                  transforms and Jacobians to global memory and hands (joint frames, sphere centres) over
-//                  through a ring of WS_STAGES tiles;
-//     warpgroup 1, 2  CONSUMERS  208 registers (88 + 2 x 208 = 3 x 168): take the frames into registers and the centres into their private
-//                  shared memory, release the ring stage at once, and do phase 2 exactly as kin_eval_kernel does
-//                  (same helpers, same order => bitwise-identical results:
-//                  test_warp_specialised_kernel_is_bitwise_identical).
-// 12 resident warps (3 per sub-partition: one producer + two consumers) instead of 8; the producer's 5k
-// instructions per configuration and the consumers' 11k balance at one producer per two consumers.
+//     warpgroup 0     PRODUCER   88 registers: walks the chain of one configuration per thread, writes link
+//                     transforms and Jacobians to global memory and hands (joint frames, sphere centres) over
+//                     through a ring of WS_STAGES tiles;
+//     warpgroup 1, 2  CONSUMERS  208 registers each (88 + 2 x 208 = 3 x 168): copy the frames into registers and
+//                     the centres into their private shared memory (cp.async), release the ring stage at once,
+//                     and do phase 2 exactly as kin_eval_kernel does (same helpers, same order => bitwise-identical
+//                     results: test_warp_specialised_kernel_is_bitwise_identical).
+// 12 resident warps (3 per sub-partition: one producer + two consumers) instead of 8; the producer's ~5.7k
+// instructions per configuration and the consumers' ~12k balance at one producer per two consumers (the producer
+// waits for a free stage ~8 % of its time, the consumers for a full one < 1 %).
 //
-// The ring lives in GLOBAL memory (one region per CTA, 2 stages x 96 KB -- measured: 4 stages 17.1 ms, 3: 16.7, 2: 16.3 per 2^24 -- reused every few microseconds and
-// therefore L2-resident): shared memory cannot hold both the consumers' per-configuration state (80 slots x 256
-// threads = 160 KB) and a hand-over buffer deep enough to keep them busy -- a first version with a two-stage
-// ring in shared memory left each consumer idle while its only stage was being refilled and ended 3 % slower
-// than kin_eval_kernel.  Producer and consumers run on the same SM; mbarrier full[stage] (128 producer
-// arrivals, release) / empty[stage] (128 consumer arrivals) order the hand-over, every thread only ever touches
-// its own column of a stage, and the consumers read the ring with ld.global.cg.
+// The ring lives in GLOBAL memory: one region per CTA, WS_STAGES x 96 KB, reused every few microseconds and
+// therefore L2-resident (measured per 2^24 configurations: 4 stages 17.1 ms, 3: 16.7, 2: 16.3 -- the smaller
+// footprint stays in L2, DRAM traffic is back to the algorithmic 4 KB per configuration).  Shared memory cannot
+// hold both the consumers' per-configuration state (80 slots x 256 threads = 160 KB) and a hand-over buffer deep
+// enough to keep them busy: a first version with a two-stage ring in shared memory left each consumer idle while
+// its only stage was being refilled and ended 3 % slower than kin_eval_kernel.  Producer and consumers run on the
+// same SM; mbarrier full[stage] (128 producer arrivals) / empty[stage] (128 consumer arrivals) order the
+// hand-over at CTA scope, and every thread only ever touches its own column of a stage.
 //
 // Eligible: FP64, SoA or tiled layout, collision requested, n_dof <= 8, a chain without save slots, and the
 // consumers' state fits in shared memory (S <= ~16 spheres); kin_b200.cu falls back to kin_eval_kernel otherwise.
@@ -81,14 +83,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 }
 
 // The ring is re-used every few microseconds while 4 KB of results per configuration stream through the same L2:
-// ring accesses carry an evict_last policy and the result stores are streaming (st.global.cs), otherwise LRU
-// writes every ring line back to HBM before it is read (+35 % DRAM traffic, measured).
+// ring loads carry an evict_last policy and bypass L1, and the result stores are streaming (st.global.cs); with
+// plain accesses and a 4-stage ring every ring line was written back to HBM before it was read (+35 % DRAM
+// traffic, measured).  Ring stores are plain C++ stores: `asm volatile` stores serialise the producer's schedule.
 __device__ __forceinline__ uint64_t l2_evict_last_policy() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ void ring_st(double *p, double v, uint64_t) { *p = v; }   // plain store: freely scheduled
+__device__ __forceinline__ void ring_st(double *p, double v, uint64_t) { *p = v; }
 __device__ __forceinline__ double ring_ld(const double *p, uint64_t pol) {
     double v;
     asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");

@@ -157,7 +157,9 @@ bool ws_eligible(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
     const kin::ProgHeader &h = dp->prog.h;
     if (std::getenv("KIN_DISABLE_WS")) return false;          // tuning / test aid: force kin_eval_kernel
     if (c->precision != KIN_F64 || (c->layout != KIN_LAYOUT_SOA && c->layout != KIN_LAYOUT_TILED32)) return false;
-    if (!c->vals_out || h.n_sph <= 0 || h.n_dof > kin::JF_REGS || h.so_jf != h.so_save) return false;
+    // <= 8 control joints (+ the planar base); no save slots (so_jf - so_save = 12 x save slots): a chain
+    if (!c->vals_out || h.n_sph <= 0 || h.n_joints > kin::JF_REGS || h.n_dof > kin::WS_MAX_COLS) return false;
+    if (h.so_jf != h.so_save) return false;
     if (c->n < kWsMinBatch && !std::getenv("KIN_FORCE_WS")) return false;
     return kin::ws_smem_bytes(h) <= (size_t)m->dev_smem;
 }

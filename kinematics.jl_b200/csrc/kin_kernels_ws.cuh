@@ -26,7 +26,8 @@
 // same SM; mbarrier full[stage] (128 producer arrivals) / empty[stage] (128 consumer arrivals) order the
 // hand-over at CTA scope, and every thread only ever touches its own column of a stage.
 //
-// Eligible: FP64, SoA or tiled layout, collision requested, n_dof <= 8, a chain without save slots, and the
+// Eligible: FP64, SoA or tiled layout, collision requested, <= 8 control joints (+ planar base), a chain without
+// save slots, and the
 // consumers' state fits in shared memory (S <= ~16 spheres); kin_b200.cu falls back to kin_eval_kernel otherwise.
 #pragma once
 #include "kin_kernels.cuh"
@@ -42,11 +43,15 @@ constexpr int WS_THREADS = 3 * WS_TILE;
 #define KIN_WS_SLEEP_NS 200
 #endif
 constexpr int WS_STAGES = KIN_WS_STAGES;         // ring depth (tiles)
-constexpr int WS_FRAME_SLOTS = 6 * JF_REGS;      // ring slots [0, 48): joint frames, [48, 48 + 3 S): sphere centres
-// consumer-private shared slots: the shared Jacobian scratch of collision.jl:76 (3 x 8), (dmin, argmin) of the
+// Columns: up to JF_REGS control joints, whose frames the consumers hold in registers, plus the three columns of
+// the planar base (prismatic x, prismatic y, revolute z: algorithm.jl:98-105), whose frames are the constants
+// e_x, e_y and (e_z through (x, y, 0)) -- the consumers keep just (x, y).
+constexpr int WS_MAX_COLS = JF_REGS + 3;
+constexpr int WS_FRAME_SLOTS = 6 * WS_MAX_COLS;  // ring slots [0, 66): joint frames, [66, 66 + 3 S): sphere centres
+// consumer-private shared slots: the shared Jacobian scratch of collision.jl:76 (3 x 11), (dmin, argmin) of the
 // current sphere group, then the 3 S centre coordinates
 __host__ __device__ inline int ws_ring_slots(int n_sph) { return WS_FRAME_SLOTS + 3 * n_sph; }
-__host__ __device__ inline int ws_priv_slots(int n_sph) { return 3 * n_sph + 3 * JF_REGS + 2 * SPH_GROUP; }
+__host__ __device__ inline int ws_priv_slots(int n_sph) { return 3 * n_sph + 3 * WS_MAX_COLS + 2 * SPH_GROUP; }
 // bytes of global scratch one launch needs (n_cta regions)
 __host__ __device__ inline size_t ws_ring_bytes(const ProgHeader &h, int n_cta) {
     return sizeof(double) * (size_t)n_cta * WS_STAGES * ws_ring_slots(h.n_sph) * WS_TILE;
@@ -56,7 +61,7 @@ __host__ __device__ inline size_t ws_smem_bytes(const ProgHeader &h) {
     size_t b = sizeof(int32_t) * (size_t)h.n_int + sizeof(double) * (size_t)h.n_real;
     b = (b + 15) & ~size_t(15);
     b += 64;                                                            // mbarriers
-    b += sizeof(double) * 2 * JF_REGS * WS_TILE;                        // q double buffer
+    b += sizeof(double) * 2 * WS_MAX_COLS * WS_TILE;                    // q double buffer
     b += sizeof(double) * 2 * (size_t)ws_priv_slots(h.n_sph) * WS_TILE; // two consumer warpgroups
     return b;
 }
@@ -112,8 +117,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
     size_t off = (sizeof(int32_t) * (size_t)h.n_int + sizeof(real) * (size_t)h.n_real + 15) & ~size_t(15);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + off);      // full[WS_STAGES], empty[WS_STAGES]
     off += 64;
-    real *qs = reinterpret_cast<real *>(smem_raw + off);                // [2][JF_REGS][BS]
-    off += sizeof(real) * 2 * JF_REGS * BS;
+    real *qs = reinterpret_cast<real *>(smem_raw + off);                // [2][WS_MAX_COLS][BS]
+    off += sizeof(real) * 2 * WS_MAX_COLS * BS;
     real *priv = reinterpret_cast<real *>(smem_raw + off);              // [2 consumers][priv_slots][BS]
     const int ring_slots = ws_ring_slots(h.n_sph), priv_slots = ws_priv_slots(h.n_sph);
     // this CTA's region of the global ring: [WS_STAGES][ring_slots][BS]
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
         auto prefetch_q = [&](long long k_, int buf) {
             const long long n_ = min((blockIdx.x + k_ * gridDim.x) * BS + t, (long long)A.n - 1);
             const real *qn = reinterpret_cast<const real *>(A.q) + rec_base(n_, ND);
-            real *dst = qs + (size_t)buf * JF_REGS * BS + t;
+            real *dst = qs + (size_t)buf * WS_MAX_COLS * BS + t;
             for (int c = 0; c < ND; ++c) cp_async_elem(dst + c * BS, qn + c * es);
             cp_async_commit();
         };
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
             const long long n = min((blockIdx.x + k * gridDim.x) * BS + t, (long long)A.n - 1);
             if (k + 1 < my_tiles) { prefetch_q(k + 1, qb ^ 1); cp_async_wait<1>(); }
             else cp_async_wait<0>();
-            const real *qv = qs + (size_t)qb * JF_REGS * BS + t;        // qv[c * BS]
+            const real *qv = qs + (size_t)qb * WS_MAX_COLS * BS + t;    // qv[c * BS]
             real *rg = ring + (size_t)st * ring_slots * BS + t;         // rg[slot * BS], global
             mbar_wait(&bars[WS_STAGES + st], (unsigned)(((k / WS_STAGES) & 1) ^ 1));   // the stage has been copied out
             real *Tn = reinterpret_cast<real *>(A.T_out) + rec_base(n, 12 * n_fk);
@@ -314,9 +319,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
         // with the S-dependent centres in front the compiler re-derived these addresses from the kernel parameters
         // in front of every access of the column loop)
         real *stale0 = pv;
-        real *hand = pv + (3 * JF_REGS) * BS;
-        real *cent0 = pv + (3 * JF_REGS + 2 * SPH_GROUP) * BS;
-        #define FOR_COLUMNS(j) _Pragma("unroll") for (int j = 0; j < JR; ++j) if (j >= ND) break; else
+        real *hand = pv + (3 * WS_MAX_COLS) * BS;
+        real *cent0 = pv + (3 * WS_MAX_COLS + 2 * SPH_GROUP) * BS;
+        const bool with_base = ND > DC;
+        // the control-joint columns (frames in registers, static indices); the base columns follow separately
+        #define FOR_COLUMNS(j) _Pragma("unroll") for (int j = 0; j < JR; ++j) if (j >= DC) break; else
         for (long long k = cw; k < my_tiles; k += 2) {
             const int st = (int)(k % WS_STAGES);
             const long long n = min((blockIdx.x + k * gridDim.x) * BS + t, (long long)A.n - 1);
@@ -337,6 +344,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                 jfr[j].o[0] = ring_ld(jf, pol); jfr[j].o[1] = ring_ld(jf + BS, pol); jfr[j].o[2] = ring_ld(jf + 2 * BS, pol);
                 jfr[j].a[0] = ring_ld(jf + 3 * BS, pol); jfr[j].a[1] = ring_ld(jf + 4 * BS, pol); jfr[j].a[2] = ring_ld(jf + 5 * BS, pol);
             }
+            real bx = real(0), by = real(0);           // origin of the base's revolute column: (x, y, 0)
+            if (with_base) { bx = ring_ld(rg + 6 * BS * (DC + 2), pol); by = ring_ld(rg + 6 * BS * (DC + 2) + BS, pol); }
             cp_async_wait<0>();
             mbar_arrive(&bars[WS_STAGES + st]);        // empty: the producer may refill this stage
             if (stale)
@@ -418,6 +427,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                         } else { cx = cy = cz = real(0); }
                         __stcs(&Gp[(size_t)j * es], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));   // transpose(grad) * jac
                         sp += 3 * BS;
+                    }
+                    if (with_base) {              // base block, algorithm.jl:98-105: same jac_col, constant frames
+                        #pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const int j = DC + k;
+                            JFrame<real> f;
+                            f.o[0] = bx; f.o[1] = by; f.o[2] = real(0);
+                            f.a[0] = k == 0 ? real(1) : real(0); f.a[1] = k == 1 ? real(1) : real(0); f.a[2] = k == 2 ? real(1) : real(0);
+                            real cx, cy, cz;
+                            if ((mask >> j) & 1u) {
+                                jac_col(f, k == 2, px, py, pz, cx, cy, cz);
+                                if (stale) { sp[0] = cx; sp[BS] = cy; sp[2 * BS] = cz; }
+                            } else if (stale) {
+                                cx = sp[0]; cy = sp[BS]; cz = sp[2 * BS];
+                            } else { cx = cy = cz = real(0); }
+                            __stcs(&Gp[(size_t)j * es], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));
+                            sp += 3 * BS;
+                        }
                     }
                     Gp += (size_t)ND * es;
                 }

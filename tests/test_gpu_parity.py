@@ -195,21 +195,22 @@ def test_fridge_union_points_vs_oracle():
     np.testing.assert_allclose(host(g_fd), gf_ref, rtol=0, atol=1e-7)
 
 
+@pytest.mark.parametrize("with_base", [False, True])
 @pytest.mark.parametrize("layout", [L.SOA, L.TILED32])
 @pytest.mark.parametrize("n", [1, 300, 70001])
-def test_warp_specialised_kernel_is_bitwise_identical(layout, n, monkeypatch):
+def test_warp_specialised_kernel_is_bitwise_identical(layout, n, with_base, monkeypatch):
     """Large FP64 SoA / tiled collision launches take the warp-specialised kernel (kin_kernels_ws.cuh: producer
     warps walk the chain, consumer warps do the sphere work).  It runs the same arithmetic in the same order as
     kin_eval_kernel, so every output must be bitwise identical -- for ragged batches, with and without
     truncation, in both scratch modes and all gradient modes."""
-    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
-    q = scenes.random_configs(jo, n, False, seed=17, zeros_every=97)
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(with_base)
+    q = scenes.random_configs(jo, n, with_base, seed=17, zeros_every=97)
     from kinematics_jl_b200.device import current_q, evaluate
     K.set_joint_angles(m, joints, dev(q))
     K.compute_coll_dists(sscc, joints, sdf)                         # uploads sphere / box tables
     dm = device_model(m)
     Q, ql, N = current_q(m)
-    assert N == n and dm.n_dof == 8
+    assert N == n and dm.n_dof == (11 if with_base else 8)
     fk = [l.id for l in m.links[:25]]
     jac = [K.find_link(m, "gripper_link").id, K.find_link(m, "wrist_flex_link").id]
 

@@ -150,7 +150,9 @@ const KernelFn kKernels[2][3][kNumBS][2][2] = {{KIN_BS_ROW(double, 0), KIN_BS_RO
 
 // Warp-specialised fused kernel (kin_kernels_ws.cuh): FP64, SoA / tiled, collision, <= 8 columns, a chain without
 // save slots, ring fits in shared memory, and a batch large enough to fill one 384-thread CTA per SM a few times.
-const KernelFn kWsKernels[2] = {kin::kin_eval_ws_kernel<0>, kin::kin_eval_ws_kernel<2>};
+// [layout: SoA, tiled][planar base]
+const KernelFn kWsKernels[2][2] = {{kin::kin_eval_ws_kernel<0, false>, kin::kin_eval_ws_kernel<0, true>},
+                                   {kin::kin_eval_ws_kernel<2, false>, kin::kin_eval_ws_kernel<2, true>}};
 constexpr long long kWsMinBatch = 1 << 16;
 
 bool ws_eligible(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
@@ -280,9 +282,15 @@ int launch(KinModel *m, const KinCall *c, DeviceProgram *dp, cudaStream_t stream
     a.grad_mode = c->grad_mode; a.scratch_ref = c->scratch_mode == KIN_SCRATCH_REFERENCE;
     a.truncation_dist = c->truncation_dist; a.vals_offset = c->vals_offset;
     if (ws_eligible(m, c, dp)) {
-        const KernelFn k = kWsKernels[li == KIN_LAYOUT_TILED32 ? 1 : 0];
+        const int wi = li == KIN_LAYOUT_TILED32 ? 1 : 0;
+        const int bi = dp->prog.h.n_dof > dp->prog.h.n_joints ? 1 : 0;
+        const KernelFn k = kWsKernels[wi][bi];
         const size_t smem = kin::ws_smem_bytes(dp->prog.h);
-        CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static std::atomic<int> ws_smem_limit[2][2] = {{{0}, {0}}, {{0}, {0}}};   // opt-in shared-memory limit set so far
+        if (ws_smem_limit[wi][bi].load() < (int)smem) {
+            CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, m->dev_smem));
+            ws_smem_limit[wi][bi].store(m->dev_smem);
+        }
         const long long tiles = (c->n + kin::WS_TILE - 1) / kin::WS_TILE;
         const long long grid = tiles < m->n_sm ? tiles : m->n_sm;
         if (grid < 1) return KIN_OK;
@@ -429,7 +437,7 @@ int kin_query_launch(KinModel *m, const KinCall *c, int32_t *regs, int32_t *smem
     const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
     if (ws_eligible(m, c, dp)) {
         cudaFuncAttributes fa;
-        CUDA_TRY(cudaFuncGetAttributes(&fa, kWsKernels[li == KIN_LAYOUT_TILED32 ? 1 : 0]));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, kWsKernels[li == KIN_LAYOUT_TILED32 ? 1 : 0][dp->prog.h.n_dof > dp->prog.h.n_joints ? 1 : 0]));
         const long long tiles = (c->n + kin::WS_TILE - 1) / kin::WS_TILE;
         if (regs) *regs = fa.numRegs;            // launch value; setmaxnreg moves it to 104 (producer) / 200 (consumers)
         if (smem_bytes) *smem_bytes = (int32_t)kin::ws_smem_bytes(dp->prog.h);

@@ -47,22 +47,24 @@ constexpr int WS_STAGES = KIN_WS_STAGES;         // ring depth (tiles)
 // the planar base (prismatic x, prismatic y, revolute z: algorithm.jl:98-105), whose frames are the constants
 // e_x, e_y and (e_z through (x, y, 0)) -- the consumers keep just (x, y).
 constexpr int WS_MAX_COLS = JF_REGS + 3;
-constexpr int WS_FRAME_SLOTS = 6 * WS_MAX_COLS;  // ring slots [0, 66): joint frames, [66, 66 + 3 S): sphere centres
-// consumer-private shared slots: the shared Jacobian scratch of collision.jl:76 (3 x 11), (dmin, argmin) of the
+__host__ __device__ constexpr int ws_cols(bool base) { return base ? WS_MAX_COLS : JF_REGS; }   // column capacity of the layouts
+__host__ __device__ inline bool ws_has_base(const ProgHeader &h) { return h.n_dof > h.n_joints; }
+// ring slots [0, 6 cols): joint frames, then 3 S sphere-centre coordinates
+__host__ __device__ inline int ws_ring_slots(int n_sph, bool base) { return 6 * ws_cols(base) + 3 * n_sph; }
+// consumer-private shared slots: the shared Jacobian scratch of collision.jl:76 (3 x cols), (dmin, argmin) of the
 // current sphere group, then the 3 S centre coordinates
-__host__ __device__ inline int ws_ring_slots(int n_sph) { return WS_FRAME_SLOTS + 3 * n_sph; }
-__host__ __device__ inline int ws_priv_slots(int n_sph) { return 3 * n_sph + 3 * WS_MAX_COLS + 2 * SPH_GROUP; }
+__host__ __device__ inline int ws_priv_slots(int n_sph, bool base) { return 3 * n_sph + 3 * ws_cols(base) + 2 * SPH_GROUP; }
 // bytes of global scratch one launch needs (n_cta regions)
 __host__ __device__ inline size_t ws_ring_bytes(const ProgHeader &h, int n_cta) {
-    return sizeof(double) * (size_t)n_cta * WS_STAGES * ws_ring_slots(h.n_sph) * WS_TILE;
+    return sizeof(double) * (size_t)n_cta * WS_STAGES * ws_ring_slots(h.n_sph, ws_has_base(h)) * WS_TILE;
 }
 // bytes of dynamic shared memory: tables, 2 x WS_STAGES mbarriers, producer q double buffer, consumer state
 __host__ __device__ inline size_t ws_smem_bytes(const ProgHeader &h) {
     size_t b = sizeof(int32_t) * (size_t)h.n_int + sizeof(double) * (size_t)h.n_real;
     b = (b + 15) & ~size_t(15);
     b += 64;                                                            // mbarriers
-    b += sizeof(double) * 2 * WS_MAX_COLS * WS_TILE;                    // q double buffer
-    b += sizeof(double) * 2 * (size_t)ws_priv_slots(h.n_sph) * WS_TILE; // two consumer warpgroups
+    b += sizeof(double) * 2 * ws_cols(ws_has_base(h)) * WS_TILE;        // q double buffer
+    b += sizeof(double) * 2 * (size_t)ws_priv_slots(h.n_sph, ws_has_base(h)) * WS_TILE; // two consumer warpgroups
     return b;
 }
 
@@ -103,7 +105,9 @@ __device__ __forceinline__ double ring_ld(const double *p, uint64_t pol) {
     return v;
 }
 
-template <int LAY>
+// BASE: the model has the planar base (instantiated separately so that the base block is not in the hot loop of
+// the fixed-base kernel: instruction fetch is one of its limiters)
+template <int LAY, bool BASE>
 __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid_constant__ KernelArgs A) {
     typedef double real;
     constexpr bool TILED = LAY == 2;
@@ -117,10 +121,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
     size_t off = (sizeof(int32_t) * (size_t)h.n_int + sizeof(real) * (size_t)h.n_real + 15) & ~size_t(15);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + off);      // full[WS_STAGES], empty[WS_STAGES]
     off += 64;
-    real *qs = reinterpret_cast<real *>(smem_raw + off);                // [2][WS_MAX_COLS][BS]
-    off += sizeof(real) * 2 * WS_MAX_COLS * BS;
+    constexpr int COLS = ws_cols(BASE), FRAME_SLOTS = 6 * COLS;
+    real *qs = reinterpret_cast<real *>(smem_raw + off);                // [2][COLS][BS]
+    off += sizeof(real) * 2 * COLS * BS;
     real *priv = reinterpret_cast<real *>(smem_raw + off);              // [2 consumers][priv_slots][BS]
-    const int ring_slots = ws_ring_slots(h.n_sph), priv_slots = ws_priv_slots(h.n_sph);
+    const int ring_slots = ws_ring_slots(h.n_sph, BASE), priv_slots = ws_priv_slots(h.n_sph, BASE);
     // this CTA's region of the global ring: [WS_STAGES][ring_slots][BS]
     real *ring = reinterpret_cast<real *>(A.ws_ring) + (size_t)blockIdx.x * WS_STAGES * ring_slots * BS;
 
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
         auto prefetch_q = [&](long long k_, int buf) {
             const long long n_ = min((blockIdx.x + k_ * gridDim.x) * BS + t, (long long)A.n - 1);
             const real *qn = reinterpret_cast<const real *>(A.q) + rec_base(n_, ND);
-            real *dst = qs + (size_t)buf * WS_MAX_COLS * BS + t;
+            real *dst = qs + (size_t)buf * COLS * BS + t;
             for (int c = 0; c < ND; ++c) cp_async_elem(dst + c * BS, qn + c * es);
             cp_async_commit();
         };
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
             const long long n = min((blockIdx.x + k * gridDim.x) * BS + t, (long long)A.n - 1);
             if (k + 1 < my_tiles) { prefetch_q(k + 1, qb ^ 1); cp_async_wait<1>(); }
             else cp_async_wait<0>();
-            const real *qv = qs + (size_t)qb * WS_MAX_COLS * BS + t;    // qv[c * BS]
+            const real *qv = qs + (size_t)qb * COLS * BS + t;           // qv[c * BS]
             real *rg = ring + (size_t)st * ring_slots * BS + t;         // rg[slot * BS], global
             mbar_wait(&bars[WS_STAGES + st], (unsigned)(((k / WS_STAGES) & 1) ^ 1));   // the stage has been copied out
             real *Tn = reinterpret_cast<real *>(A.T_out) + rec_base(n, 12 * n_fk);
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                     const int s = ti[io_sph_order + k2];
                     const real *sr = tr + ro_sph + s * SPH_REALS;
                     const real c0 = sr[0], c1 = sr[1], c2 = sr[2];
-                    real *cs = rg + (WS_FRAME_SLOTS + 3 * s) * BS;
+                    real *cs = rg + (FRAME_SLOTS + 3 * s) * BS;
                     #pragma unroll
                     for (int i = 0; i < 3; ++i)
                         ring_st(cs + i * BS, fma_(T.r[i * 3 + 0], c0, fma_(T.r[i * 3 + 1], c1, fma_(T.r[i * 3 + 2], c2, T.p[i]))), pol);
@@ -319,9 +324,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
         // with the S-dependent centres in front the compiler re-derived these addresses from the kernel parameters
         // in front of every access of the column loop)
         real *stale0 = pv;
-        real *hand = pv + (3 * WS_MAX_COLS) * BS;
-        real *cent0 = pv + (3 * WS_MAX_COLS + 2 * SPH_GROUP) * BS;
-        const bool with_base = ND > DC;
+        real *hand = pv + (3 * COLS) * BS;
+        real *cent0 = pv + (3 * COLS + 2 * SPH_GROUP) * BS;
+        constexpr bool with_base = BASE;
         // the control-joint columns (frames in registers, static indices); the base columns follow separately
         #define FOR_COLUMNS(j) _Pragma("unroll") for (int j = 0; j < JR; ++j) if (j >= DC) break; else
         for (long long k = cw; k < my_tiles; k += 2) {
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
             // cp.async.ca may allocate in L1; producer and consumer share this SM's L1 and synchronise at CTA scope,
             // so a later refill of the stage is seen.
             {
-                const real *src = rg + WS_FRAME_SLOTS * BS;
+                const real *src = rg + FRAME_SLOTS * BS;
                 for (int i = 0; i < 3 * S; ++i) cp_async_elem(cent0 + i * BS, src + i * BS);
                 cp_async_commit();
             }

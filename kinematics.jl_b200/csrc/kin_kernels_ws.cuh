@@ -85,8 +85,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
     return ok != 0;
 }
 // a waiting warp sleeps between polls so that it does not take issue slots from the warps it is waiting for
+// A hand-over that never completes would hang the GPU; after ~2^24 polls (seconds, against microseconds per tile) the
+// kernel traps instead, which surfaces as a CUDA error on the stream.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(KIN_WS_SLEEP_NS);
+    unsigned polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(KIN_WS_SLEEP_NS);
+        if (++polls > (1u << 24)) __trap();
+    }
 }
 
 // The ring is re-used every few microseconds while 4 KB of results per configuration stream through the same L2:

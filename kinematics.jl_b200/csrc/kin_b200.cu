@@ -150,9 +150,17 @@ const KernelFn kKernels[2][3][kNumBS][2][2] = {{KIN_BS_ROW(double, 0), KIN_BS_RO
 
 // Warp-specialised fused kernel (kin_kernels_ws.cuh): FP64, SoA / tiled, collision, <= 8 columns, a chain without
 // save slots, ring fits in shared memory, and a batch large enough to fill one 384-thread CTA per SM a few times.
-// [layout: SoA, tiled][planar base]
-const KernelFn kWsKernels[2][2] = {{kin::kin_eval_ws_kernel<0, false>, kin::kin_eval_ws_kernel<0, true>},
-                                   {kin::kin_eval_ws_kernel<2, false>, kin::kin_eval_ws_kernel<2, true>}};
+// [layout: SoA, tiled][planar base][collision-only call: the producer also does the box search]
+#define KIN_WS(lay, base) {kin::kin_eval_ws_kernel<lay, base, false>, kin::kin_eval_ws_kernel<lay, base, true>}
+const KernelFn kWsKernels[2][2][2] = {{KIN_WS(0, false), KIN_WS(0, true)}, {KIN_WS(2, false), KIN_WS(2, true)}};
+
+// collision-only variant: no link transforms / Jacobians requested, no truncation (with a finite truncation
+// distance most spheres skip the gradient stage, the consumers are idle already and the box search would make the
+// producer the bottleneck: trajectory stack of config 5 0.19 -> 0.23 ms), and its larger consumer state still fits
+bool ws_pre(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
+    return !c->T_out && !c->J_out && std::isinf(c->truncation_dist) && c->truncation_dist > 0 && !std::getenv("KIN_DISABLE_WS_PRE") &&
+           kin::ws_smem_bytes(dp->prog.h, true) <= (size_t)m->dev_smem;
+}
 constexpr long long kWsMinBatch = 1 << 16;
 
 bool ws_eligible(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
@@ -163,7 +171,7 @@ bool ws_eligible(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
     if (!c->vals_out || h.n_sph <= 0 || h.n_joints > kin::JF_REGS || h.n_dof > kin::WS_MAX_COLS) return false;
     if (h.so_jf != h.so_save) return false;
     if (c->n < kWsMinBatch && !std::getenv("KIN_FORCE_WS")) return false;
-    return kin::ws_smem_bytes(h) <= (size_t)m->dev_smem;
+    return kin::ws_smem_bytes(h, false) <= (size_t)m->dev_smem;
 }
 
 int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
@@ -283,20 +291,20 @@ int launch(KinModel *m, const KinCall *c, DeviceProgram *dp, cudaStream_t stream
     a.truncation_dist = c->truncation_dist; a.vals_offset = c->vals_offset;
     if (ws_eligible(m, c, dp)) {
         const int wi = li == KIN_LAYOUT_TILED32 ? 1 : 0;
-        const int bi = dp->prog.h.n_dof > dp->prog.h.n_joints ? 1 : 0;
-        const KernelFn k = kWsKernels[wi][bi];
-        const size_t smem = kin::ws_smem_bytes(dp->prog.h);
-        static std::atomic<int> ws_smem_limit[2][2] = {{{0}, {0}}, {{0}, {0}}};   // opt-in shared-memory limit set so far
-        if (ws_smem_limit[wi][bi].load() < (int)smem) {
+        const int bi = dp->prog.h.n_dof > dp->prog.h.n_joints ? 1 : 0, pi_ = ws_pre(m, c, dp) ? 1 : 0;
+        const KernelFn k = kWsKernels[wi][bi][pi_];
+        const size_t smem = kin::ws_smem_bytes(dp->prog.h, pi_ != 0);
+        static std::atomic<int> ws_smem_limit[2][2][2];                 // opt-in shared-memory limit set so far (zero-initialised)
+        if (ws_smem_limit[wi][bi][pi_].load() < (int)smem) {
             CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, m->dev_smem));
-            ws_smem_limit[wi][bi].store(m->dev_smem);
+            ws_smem_limit[wi][bi][pi_].store(m->dev_smem);
         }
         const long long tiles = (c->n + kin::WS_TILE - 1) / kin::WS_TILE;
         const long long grid = tiles < m->n_sm ? tiles : m->n_sm;
         if (grid < 1) return KIN_OK;
         // hand-over ring: stream-ordered scratch from the model's pool (concurrent launches get their own)
         void *ring = nullptr;
-        CUDA_TRY(cudaMallocFromPoolAsync(&ring, kin::ws_ring_bytes(dp->prog.h, (int)grid), m->pool, stream));
+        CUDA_TRY(cudaMallocFromPoolAsync(&ring, kin::ws_ring_bytes(dp->prog.h, (int)grid, pi_ != 0), m->pool, stream));
         a.ws_ring = ring;
         k<<<(unsigned)grid, kin::WS_THREADS, smem, stream>>>(a);
         cudaError_t le = cudaGetLastError();
@@ -437,10 +445,11 @@ int kin_query_launch(KinModel *m, const KinCall *c, int32_t *regs, int32_t *smem
     const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
     if (ws_eligible(m, c, dp)) {
         cudaFuncAttributes fa;
-        CUDA_TRY(cudaFuncGetAttributes(&fa, kWsKernels[li == KIN_LAYOUT_TILED32 ? 1 : 0][dp->prog.h.n_dof > dp->prog.h.n_joints ? 1 : 0]));
+        const bool pre = ws_pre(m, c, dp);
+        CUDA_TRY(cudaFuncGetAttributes(&fa, kWsKernels[li == KIN_LAYOUT_TILED32 ? 1 : 0][dp->prog.h.n_dof > dp->prog.h.n_joints ? 1 : 0][pre ? 1 : 0]));
         const long long tiles = (c->n + kin::WS_TILE - 1) / kin::WS_TILE;
         if (regs) *regs = fa.numRegs;            // launch value; setmaxnreg moves it to 104 (producer) / 200 (consumers)
-        if (smem_bytes) *smem_bytes = (int32_t)kin::ws_smem_bytes(dp->prog.h);
+        if (smem_bytes) *smem_bytes = (int32_t)kin::ws_smem_bytes(dp->prog.h, pre);
         if (block) *block = kin::WS_THREADS;
         if (grid) *grid = (int32_t)(tiles < m->n_sm ? tiles : m->n_sm);
         return KIN_OK;

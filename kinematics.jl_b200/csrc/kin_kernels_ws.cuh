@@ -50,21 +50,25 @@ constexpr int WS_MAX_COLS = JF_REGS + 3;
 __host__ __device__ constexpr int ws_cols(bool base) { return base ? WS_MAX_COLS : JF_REGS; }   // column capacity of the layouts
 __host__ __device__ inline bool ws_has_base(const ProgHeader &h) { return h.n_dof > h.n_joints; }
 // ring slots [0, 6 cols): joint frames, then 3 S sphere-centre coordinates
-__host__ __device__ inline int ws_ring_slots(int n_sph, bool base) { return 6 * ws_cols(base) + 3 * n_sph; }
-// consumer-private shared slots: the shared Jacobian scratch of collision.jl:76 (3 x cols), (dmin, argmin) of the
-// current sphere group, then the 3 S centre coordinates
-__host__ __device__ inline int ws_priv_slots(int n_sph, bool base) { return 3 * n_sph + 3 * ws_cols(base) + 2 * SPH_GROUP; }
+// PRE (collision-only calls: no link transforms / Jacobians requested): the producer, which then has little to do,
+// also runs the box search (phase 2a) of every sphere and hands (distance, argmin) over; the consumers keep phase 2b.
+// ring slots [0, 6 cols): joint frames, then 3 S sphere-centre coordinates [, then S distances and S argmins]
+__host__ __device__ inline int ws_ring_slots(int n_sph, bool base, bool pre) { return 6 * ws_cols(base) + 3 * n_sph + (pre ? 2 * n_sph : 0); }
+// consumer-private shared slots (doubles): the shared Jacobian scratch of collision.jl:76 (3 x cols); (dmin, argmin)
+// of the current sphere group [PRE: S distances + S int32 argmins from the producer]; the 3 S centre coordinates
+__host__ __device__ inline int ws_hand_slots(int n_sph, bool pre) { return pre ? n_sph + (n_sph + 1) / 2 : 2 * SPH_GROUP; }
+__host__ __device__ inline int ws_priv_slots(int n_sph, bool base, bool pre) { return 3 * n_sph + 3 * ws_cols(base) + ws_hand_slots(n_sph, pre); }
 // bytes of global scratch one launch needs (n_cta regions)
-__host__ __device__ inline size_t ws_ring_bytes(const ProgHeader &h, int n_cta) {
-    return sizeof(double) * (size_t)n_cta * WS_STAGES * ws_ring_slots(h.n_sph, ws_has_base(h)) * WS_TILE;
+__host__ __device__ inline size_t ws_ring_bytes(const ProgHeader &h, int n_cta, bool pre) {
+    return sizeof(double) * (size_t)n_cta * WS_STAGES * ws_ring_slots(h.n_sph, ws_has_base(h), pre) * WS_TILE;
 }
 // bytes of dynamic shared memory: tables, 2 x WS_STAGES mbarriers, producer q double buffer, consumer state
-__host__ __device__ inline size_t ws_smem_bytes(const ProgHeader &h) {
+__host__ __device__ inline size_t ws_smem_bytes(const ProgHeader &h, bool pre) {
     size_t b = sizeof(int32_t) * (size_t)h.n_int + sizeof(double) * (size_t)h.n_real;
     b = (b + 15) & ~size_t(15);
     b += 64;                                                            // mbarriers
     b += sizeof(double) * 2 * ws_cols(ws_has_base(h)) * WS_TILE;        // q double buffer
-    b += sizeof(double) * 2 * (size_t)ws_priv_slots(h.n_sph, ws_has_base(h)) * WS_TILE; // two consumer warpgroups
+    b += sizeof(double) * 2 * (size_t)ws_priv_slots(h.n_sph, ws_has_base(h), pre) * WS_TILE; // two consumer warpgroups
     return b;
 }
 
@@ -113,7 +117,7 @@ __device__ __forceinline__ double ring_ld(const double *p, uint64_t pol) {
 
 // BASE: the model has the planar base (instantiated separately so that the base block is not in the hot loop of
 // the fixed-base kernel: instruction fetch is one of its limiters)
-template <int LAY, bool BASE>
+template <int LAY, bool BASE, bool PRE>
 __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid_constant__ KernelArgs A) {
     typedef double real;
     constexpr bool TILED = LAY == 2;
@@ -131,7 +135,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
     real *qs = reinterpret_cast<real *>(smem_raw + off);                // [2][COLS][BS]
     off += sizeof(real) * 2 * COLS * BS;
     real *priv = reinterpret_cast<real *>(smem_raw + off);              // [2 consumers][priv_slots][BS]
-    const int ring_slots = ws_ring_slots(h.n_sph, BASE), priv_slots = ws_priv_slots(h.n_sph, BASE);
+    const int ring_slots = ws_ring_slots(h.n_sph, BASE, PRE), priv_slots = ws_priv_slots(h.n_sph, BASE, PRE);
+    const int ring_pre = FRAME_SLOTS + 3 * h.n_sph;                    // PRE: first distance slot; argmins follow
     // this CTA's region of the global ring: [WS_STAGES][ring_slots][BS]
     real *ring = reinterpret_cast<real *>(A.ws_ring) + (size_t)blockIdx.x * WS_STAGES * ring_slots * BS;
 
@@ -166,7 +171,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
 
     if (wg == 0) {
         // =========================== PRODUCER: phase 1 ===========================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        if (PRE) asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");      // 120 + 2 x 192 = 3 x 168
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");           //  88 + 2 x 208 = 3 x 168
         auto prefetch_q = [&](long long k_, int buf) {
             const long long n_ = min((blockIdx.x + k_ * gridDim.x) * BS + t, (long long)A.n - 1);
             const real *qn = reinterpret_cast<const real *>(A.q) + rec_base(n_, ND);
@@ -251,8 +257,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                         #undef GIVENS
                     }
                 }
-                // ---- requested links hanging from this node ----
-                for (int a = ni[5]; a < ni[6]; ++a) {
+                // ---- requested links hanging from this node (none in a collision-only call) ----
+                if (!PRE) for (int a = ni[5]; a < ni[6]; ++a) {
                     const int32_t *ai = ti + io_att + a * ATT_INTS;
                     const real *ar = tr + ro_att + a * ATT_REALS;
                     Tf<real> Tl;
@@ -315,11 +321,51 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                         ring_st(cs + i * BS, fma_(T.r[i * 3 + 0], c0, fma_(T.r[i * 3 + 1], c1, fma_(T.r[i * 3 + 2], c2, T.p[i]))), pol);
                 }
             }
+            if (PRE) {
+                // ---- phase 2a of every sphere (the consumers' code, so bitwise the same distances / argmins); the
+                //      centres are this thread's own stores of a moment ago, read back through L2 ----
+                for (int s0 = 0; s0 < S; s0 += SPH_GROUP) {
+                    real px[SPH_GROUP], py[SPH_GROUP], pz[SPH_GROUP], kmin[SPH_GROUP];
+                    int kidx[SPH_GROUP];
+                    #pragma unroll
+                    for (int g = 0; g < SPH_GROUP; ++g) {
+                        const real *cs = rg + (FRAME_SLOTS + 3 * min(s0 + g, S - 1)) * BS;
+                        px[g] = ring_ld(cs, pol); py[g] = ring_ld(cs + BS, pol); pz[g] = ring_ld(cs + 2 * BS, pol);
+                        kmin[g] = CUDART_INF; kidx[g] = 0;
+                    }
+                    for (int b = 0; b < n_box; ++b) {
+                        BoxRow<real> row;
+                        load_box(tr + ro_box + b * BOX_REALS, row);
+                        real key[SPH_GROUP], qx[SPH_GROUP], qy[SPH_GROUP], qz[SPH_GROUP];
+                        bool any_inside = false;
+                        #pragma unroll
+                        for (int g = 0; g < SPH_GROUP; ++g) {
+                            key[g] = box_key_outside(row, px[g], py[g], pz[g], qx[g], qy[g], qz[g]);
+                            any_inside |= !(key[g] > real(0));
+                        }
+                        if (any_inside) {
+                            #pragma unroll
+                            for (int g = 0; g < SPH_GROUP; ++g)
+                                if (!(key[g] > real(0))) key[g] = box_inside_key(qx[g], qy[g], qz[g]);
+                        }
+                        #pragma unroll
+                        for (int g = 0; g < SPH_GROUP; ++g)
+                            if (key[g] < kmin[g]) { kmin[g] = key[g]; kidx[g] = b; }
+                    }
+                    #pragma unroll
+                    for (int g = 0; g < SPH_GROUP; ++g)
+                        if (s0 + g < S) {
+                            ring_st(rg + (ring_pre + s0 + g) * BS, key_to_dist(kmin[g]), pol);
+                            ring_st(rg + (ring_pre + S + s0 + g) * BS, (real)kidx[g], pol);
+                        }
+                }
+            }
             mbar_arrive(&bars[st]);                   // full: frames + centres of this tile are in the ring
         }
     } else {
         // =========================== CONSUMERS: phase 2 ===========================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        if (PRE) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         constexpr int JR = JF_REGS;
         const int cw = wg - 1;                         // consumer 0 / 1 takes the even / odd tiles of this CTA
         real *pv = priv + (size_t)cw * priv_slots * BS + t;             // pv[slot * BS]: this thread's private state
@@ -330,8 +376,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
         // with the S-dependent centres in front the compiler re-derived these addresses from the kernel parameters
         // in front of every access of the column loop)
         real *stale0 = pv;
-        real *hand = pv + (3 * COLS) * BS;
-        real *cent0 = pv + (3 * COLS + 2 * SPH_GROUP) * BS;
+        real *hand = pv + (3 * COLS) * BS;                                // !PRE: (dmin, argmin) of the current group
+        real *pre_d = hand;                                               //  PRE: S distances, then S int32 argmins
+        int *pre_k = reinterpret_cast<int *>(pv + (3 * COLS + S) * BS - t) + t;   // int column of this thread: pre_k[s * BS]
+        real *cent0 = pv + (3 * COLS + ws_hand_slots(S, PRE)) * BS;
         constexpr bool with_base = BASE;
         // the control-joint columns (frames in registers, static indices); the base columns follow separately
         #define FOR_COLUMNS(j) _Pragma("unroll") for (int j = 0; j < JR; ++j) if (j >= DC) break; else
@@ -347,7 +395,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
             {
                 const real *src = rg + FRAME_SLOTS * BS;
                 for (int i = 0; i < 3 * S; ++i) cp_async_elem(cent0 + i * BS, src + i * BS);
+                if (PRE) for (int i = 0; i < S; ++i) cp_async_elem(pre_d + i * BS, rg + (ring_pre + i) * BS);
                 cp_async_commit();
+                if (PRE) for (int i = 0; i < S; ++i) pre_k[i * BS] = (int)ring_ld(rg + (ring_pre + S + i) * BS, pol);
             }
             JFrame<real> jfr[JR];
             FOR_COLUMNS(j) {
@@ -366,8 +416,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
             int32_t *Ap = A.argmin_out ? A.argmin_out + rec_base(n, S) : nullptr;
 
             for (int s0 = 0; s0 < S; s0 += SPH_GROUP) {
-                // ---- 2a: distances of SPH_GROUP spheres; one box-table row feeds all of them ----
-                {
+                // ---- 2a: distances of SPH_GROUP spheres; one box-table row feeds all of them (PRE: done by the producer) ----
+                if (!PRE) {
                     real px[SPH_GROUP], py[SPH_GROUP], pz[SPH_GROUP], kmin[SPH_GROUP];
                     int kidx[SPH_GROUP];
                     #pragma unroll
@@ -405,8 +455,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                 #pragma unroll 1
                 for (int g = 0; g < SPH_GROUP && s0 + g < S; ++g) {
                     const int s = s0 + g;
-                    const real dmin = hand[g * BS];
-                    const int kmin = reinterpret_cast<const int *>(&hand[(SPH_GROUP + g) * BS])[0];
+                    const real dmin = PRE ? pre_d[s * BS] : hand[g * BS];
+                    const int kmin = PRE ? pre_k[s * BS] : reinterpret_cast<const int *>(&hand[(SPH_GROUP + g) * BS])[0];
                     const real dist0 = dmin - tr[ro_sph + s * SPH_REALS + 3];
                     const bool truncated = dist0 > trunc;
                     __stcs(Vp, (truncated ? trunc : dist0) - voff);

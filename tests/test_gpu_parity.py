@@ -256,7 +256,9 @@ def test_warp_specialised_kernel_argument_combinations_and_streams(monkeypatch):
     Q, ql, N = current_q(m)
     fk = [K.find_link(m, "gripper_link").id, K.find_link(m, "head_camera_link").id]
     jac = [K.find_link(m, "elbow_flex_link").id]
-    combos = [dict(collision=True),                                                        # collision only
+    combos = [dict(collision=True),                                                        # collision only: producer does the box search
+              dict(collision=True, grad_mode=K.GRAD_ANALYTIC, scratch_mode=K.SCRATCH_CLEAN, want_argmin=True),
+              dict(collision=True, truncation_dist=0.05, vals_offset=0.02),                # collision only, truncated
               dict(collision=True, with_grads=False, want_argmin=True),                    # distances + argmin
               dict(collision=True, fk_links=fk),                                           # no Jacobian
               dict(collision=True, jac_links=jac, with_rot=False),                         # 3 x n_dof Jacobian

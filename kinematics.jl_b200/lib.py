@@ -23,7 +23,7 @@ _ip = C.POINTER(C.c_int32)
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static"]
 SOURCES = ["kin_b200.cu", "kin_model.cpp"]
-HEADERS = ["kin_kernels.cuh", "kin_program.h", "kin_model.hpp"]
+HEADERS = ["kin_kernels.cuh", "kin_kernels_ws.cuh", "kin_program.h", "kin_model.hpp"]
 
 
 class KinError(RuntimeError):

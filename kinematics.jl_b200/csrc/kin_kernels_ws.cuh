@@ -367,6 +367,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
         if (PRE) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         constexpr int JR = JF_REGS;
+        // the output stride in a register the compiler cannot trace back to the kernel parameters (it otherwise
+        // re-loads it from the constant bank in front of the stores of the column loop: LDC, 2.6 % of the stalls)
+        size_t es_c = es;
+        if (!TILED) asm volatile("" : "+l"(es_c));
         const int cw = wg - 1;                         // consumer 0 / 1 takes the even / odd tiles of this CTA
         real *pv = priv + (size_t)cw * priv_slots * BS + t;             // pv[slot * BS]: this thread's private state
         const bool want_grads = A.grads_out != nullptr;
@@ -460,12 +464,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                     const real dist0 = dmin - tr[ro_sph + s * SPH_REALS + 3];
                     const bool truncated = dist0 > trunc;
                     __stcs(Vp, (truncated ? trunc : dist0) - voff);
-                    Vp += es;
-                    if (Ap) { __stcs(Ap, kmin + 1); Ap += es; }
+                    Vp += es_c;
+                    if (Ap) { __stcs(Ap, kmin + 1); Ap += es_c; }
                     if (!want_grads) continue;
                     if (truncated) {            // collision.jl:84-86
-                        for (int j = 0; j < ND; ++j) __stcs(&Gp[(size_t)j * es], real(0));
-                        Gp += (size_t)ND * es;
+                        for (int j = 0; j < ND; ++j) __stcs(&Gp[(size_t)j * es_c], real(0));
+                        Gp += (size_t)ND * es_c;
                         continue;
                     }
                     const real *cs = cent0 + 3 * s * BS;
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                         } else if (stale) {     // column left over from an earlier sphere (collision.jl:76,90)
                             cx = sp[0]; cy = sp[BS]; cz = sp[2 * BS];
                         } else { cx = cy = cz = real(0); }
-                        __stcs(&Gp[(size_t)j * es], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));   // transpose(grad) * jac
+                        __stcs(&Gp[(size_t)j * es_c], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));   // transpose(grad) * jac
                         sp += 3 * BS;
                     }
                     if (with_base) {              // base block, algorithm.jl:98-105: same jac_col, constant frames
@@ -503,11 +507,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                             } else if (stale) {
                                 cx = sp[0]; cy = sp[BS]; cz = sp[2 * BS];
                             } else { cx = cy = cz = real(0); }
-                            __stcs(&Gp[(size_t)j * es], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));
+                            __stcs(&Gp[(size_t)j * es_c], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));
                             sp += 3 * BS;
                         }
                     }
-                    Gp += (size_t)ND * es;
+                    Gp += (size_t)ND * es_c;
                 }
             }
         }

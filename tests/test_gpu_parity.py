@@ -297,6 +297,55 @@ def test_warp_specialised_kernel_argument_combinations_and_streams(monkeypatch):
             assert torch.equal(o[k].contiguous(), serial[k].contiguous()), k
 
 
+@pytest.mark.parametrize("with_base", [False, True])
+def test_warp_specialised_kernel_on_a_second_model_vs_oracle(with_base, monkeypatch):
+    """A different chain (the PR2 right arm of data/ground_truth.json: fixed joints between the controlled ones, so
+    attachments carry non-trivial constant transforms), 10 spheres on 3 links in an order that is NOT the chain
+    order, a union of 3 rotated boxes: warp-specialised kernel against the oracle and bitwise against
+    kin_eval_kernel."""
+    from kinematics_jl_b200.device import current_q, evaluate
+    from kinematics_jl_b200.transform import rotz
+    g = json.load(open(os.path.join(DATA, "ground_truth.json")))
+    path = os.path.join(GOLDEN, "pr2_right_arm_mini.urdf")
+    m, mo = K.parse_urdf(path, with_base=with_base), R.parse_urdf(path, with_base=with_base)
+    joints = [K.find_joint(m, n) for n in g["joint_names"]]
+    jo = [R.find_joint(mo, n) for n in g["joint_names"]]
+    sscc, so = K.SweptSphereCollisionChecker(m), R.SweptSphereCollisionChecker(mo)
+    rng = np.random.default_rng(4)
+    for name, k, rad in (("r_wrist_roll_link", 4, 0.05), ("r_shoulder_lift_link", 3, 0.09), ("r_forearm_link", 3, 0.06)):
+        cents = [list(np.array([0.08 * i, 0.0, 0.0]) + rng.normal(0, 0.01, 3)) for i in range(k)]
+        K.add_coll_links(sscc, K.find_link(m, name), cents, rad)
+        R.add_coll_links(so, R.find_link(mo, name), cents, [rad] * k)
+    poses, widths = [], []
+    for c, yaw, w in (([0.7, -0.3, 0.9], 0.4, [0.3, 0.2, 0.5]), ([0.4, -0.9, 0.6], -0.8, [0.2, 0.6, 0.2]), ([0.9, 0.2, 1.3], 1.1, [0.4, 0.4, 0.1])):
+        poses.append(K.Transform(np.array(c), rotz(yaw)))
+        widths.append(w)
+    sdf = K.UnionSDF([K.BoxSDF(p, w) for p, w in zip(poses, widths)])
+    sdf_o = R.RefSDF([p.mat for p in poses], widths)
+    n = 20000
+    q = scenes.random_configs(jo, n, with_base, seed=9, zeros_every=211)
+    K.set_joint_angles(m, joints, dev(q))
+    K.compute_coll_dists(sscc, joints, sdf)
+    dm = device_model(m)
+    Q, ql, N = current_q(m)
+    kw = dict(layout=L.SOA, fk_links=[l.id for l in m.links[:11]], jac_links=[K.find_link(m, "r_wrist_roll_link").id],
+              with_rot=True, rpy_jac=True, collision=True, want_argmin=True, truncation_dist=0.4, launch_info=True)
+    monkeypatch.setenv("KIN_FORCE_WS", "1")
+    ws = evaluate(dm, Q, ql, N, **kw)
+    assert ws["launch"]["block"] == 384
+    monkeypatch.setenv("KIN_DISABLE_WS", "1")
+    classic = evaluate(dm, Q, ql, N, **kw)
+    assert classic["launch"]["block"] != 384
+    for k in ("T", "J", "vals", "grads", "argmin"):
+        assert torch.equal(ws[k].contiguous(), classic[k].contiguous()), k
+    v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, q, 0.4, R.GRAD_FD, R.SCRATCH_REFERENCE)
+    np.testing.assert_allclose(host(ws["vals"]), v_ref, rtol=RTOL, atol=ATOL)
+    assert np.array_equal(ws["argmin"].cpu().numpy(), am_ref)
+    np.testing.assert_allclose(host(ws["grads"]), g_ref.transpose(0, 2, 1), rtol=0, atol=1e-7)
+    T_ref = R.batch_fk(mo, jo, q, mo.links[:11])[:, :, :3, :]
+    np.testing.assert_allclose(host(ws["T"]), T_ref, rtol=RTOL, atol=ATOL)
+
+
 def test_fd_series_matches_direct_fd_near_every_kink():
     """KIN_GRAD_FD evaluates the FD quotient of sdf.jl:34-41 from its closed form away from kinks and
     directly near them; KIN_GRAD_FD_DIRECT always perturbs the point as the reference does.  The two (and

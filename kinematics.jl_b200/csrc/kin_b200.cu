@@ -161,7 +161,7 @@ bool ws_pre(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
     return !c->T_out && !c->J_out && std::isinf(c->truncation_dist) && c->truncation_dist > 0 && !std::getenv("KIN_DISABLE_WS_PRE") &&
            kin::ws_smem_bytes(dp->prog.h, true) <= (size_t)m->dev_smem;
 }
-constexpr long long kWsMinBatch = 1 << 16;
+constexpr long long kWsMinBatch = 80 * 1024;   // measured crossover (profiles/crossover_ws.py): 64 Ki -3 %, 128 Ki +11 %
 
 bool ws_eligible(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
     const kin::ProgHeader &h = dp->prog.h;

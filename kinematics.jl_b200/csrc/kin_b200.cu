@@ -59,6 +59,7 @@ struct HostStage {          // resources of kin_eval_host, created on first use
 struct KinModel {
     kin::HostModel hm;
     int device = 0, n_sm = 0, dev_smem = 0;
+    std::atomic<int> ws_smem_limit[2][2][2] = {};   // opt-in shared-memory limit set on this model's device, per WS kernel
     cudaMemPool_t pool = nullptr;   // stream-ordered workspace pool that keeps its memory between calls
     std::mutex mu;
     std::map<std::vector<int>, DeviceProgram *> cache;
@@ -294,10 +295,9 @@ int launch(KinModel *m, const KinCall *c, DeviceProgram *dp, cudaStream_t stream
         const int bi = dp->prog.h.n_dof > dp->prog.h.n_joints ? 1 : 0, pi_ = ws_pre(m, c, dp) ? 1 : 0;
         const KernelFn k = kWsKernels[wi][bi][pi_];
         const size_t smem = kin::ws_smem_bytes(dp->prog.h, pi_ != 0);
-        static std::atomic<int> ws_smem_limit[2][2][2];                 // opt-in shared-memory limit set so far (zero-initialised)
-        if (ws_smem_limit[wi][bi][pi_].load() < (int)smem) {
+        if (m->ws_smem_limit[wi][bi][pi_].load() < (int)smem) {         // function attributes are per device
             CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, m->dev_smem));
-            ws_smem_limit[wi][bi][pi_].store(m->dev_smem);
+            m->ws_smem_limit[wi][bi][pi_].store(m->dev_smem);
         }
         const long long tiles = (c->n + kin::WS_TILE - 1) / kin::WS_TILE;
         const long long grid = tiles < m->n_sm ? tiles : m->n_sm;

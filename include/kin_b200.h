@@ -40,6 +40,9 @@
  *   - a KinModel is immutable after creation except through kin_model_set_boxes /
  *     kin_model_set_spheres (which must not race with launches that use the model); concurrent
  *     kin_eval calls on different streams are allowed.  One model per device.
+ *   - large FP64 SoA / tiled collision launches run the warp-specialised kernel (csrc/kin_kernels_ws.cuh),
+ *     which takes ~28 MB of temporary device scratch per launch from a model-private stream-ordered pool
+ *     (allocated and freed on `stream`); results are bitwise identical to the single-kernel path.
  */
 #ifndef KIN_B200_H
 #define KIN_B200_H

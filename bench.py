@@ -342,6 +342,35 @@ def main():
         variants["fused_aos_layout"] = {"value": world * Na / (ms_ * 1e-3), "unit": UNIT, "ms_per_step": ms_, "configs": Na,
                                         "hbm_frac": BYTES_FUSED * Na / (ms_ * 1e-3) / 1e9 / peak, "launch": launch_info(ca)}
         del Qa, Ta, Ja, Va, Ga
+        # the fused step on the Fetch WITH the planar base (11 columns: SURVEY 8d variant), SoA
+        mb, jb, sb = scenes.product_fetch(True)
+        Nb = min(N, 1 << 22)
+        K.set_joint_angles(mb, jb, torch.zeros((1, N_DOF + 3), dtype=torch.float64, device=dev))
+        K.compute_coll_dists(sb, jb, sdf)
+        dmb = device_model(mb)
+        gb = torch.Generator(device=dev).manual_seed(1000 + rank)
+        lob = torch.cat([lo, torch.tensor([-1.0, -1.0, -np.pi], device=dev, dtype=torch.float64)])
+        hib = torch.cat([hi, torch.tensor([1.0, 1.0, np.pi], device=dev, dtype=torch.float64)])
+        Qb = lob[:, None] + (hib - lob)[:, None] * torch.rand((N_DOF + 3, Nb), generator=gb, device=dev, dtype=torch.float64)
+        Tb = torch.empty((N_LINKS * 12, Nb), dtype=torch.float64, device=dev)
+        Jb = torch.empty((6 * (N_DOF + 3), Nb), dtype=torch.float64, device=dev)
+        Vb = torch.empty((N_SPH, Nb), dtype=torch.float64, device=dev)
+        Gb = torch.empty((N_SPH * (N_DOF + 3), Nb), dtype=torch.float64, device=dev)
+        cb = make_call(Nb, Qb.data_ptr(), Tb.data_ptr(), Jb.data_ptr(), Vb.data_ptr(), Gb.data_ptr())
+        jac_b = np.array([K.find_link(mb, "gripper_link").id], dtype=np.int32)
+        cb.jac_links = jac_b.ctypes.data_as(ip)
+        dm_main, dm = dm, dmb                      # timed() / launch_info() use `dm`
+        try:
+            tms_, per_, _ = timed(cb, max(3, args.steps // 2), W)
+            ms_ = float(np.mean(per_))
+            bytes_b = 8 * (N_DOF + 3) + 8 * 12 * N_LINKS + 8 * 6 * (N_DOF + 3) + 8 * N_SPH + 8 * N_SPH * (N_DOF + 3)
+            variants["fused_with_planar_base(11 columns)"] = {
+                "value": world * Nb / (ms_ * 1e-3), "unit": UNIT, "ms_per_step": ms_, "configs": Nb,
+                "algorithmic_bytes_per_config": bytes_b, "hbm_frac": bytes_b * Nb / (ms_ * 1e-3) / 1e9 / peak,
+                "launch": launch_info(cb)}
+        finally:
+            dm = dm_main
+        del Qb, Tb, Jb, Vb, Gb
 
     # ---- configs 4 and 5 of BASELINE.json (caller-side rows of SURVEY 8f), through the host mirror ----
     callers = {}

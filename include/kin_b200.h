@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define KIN_B200_ABI_VERSION 1
+#define KIN_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define KIN_API __attribute__((visibility("default")))
@@ -168,6 +168,13 @@ typedef struct {
 
 KIN_API const char *kin_last_error(void);
 KIN_API int kin_abi_version(void);
+/* Hex digest of the sources the library was compiled from (csrc/ and this header, baked in with -DKIN_BUILD_ID by
+ * kinematics.jl_b200/lib.py: build).  The Python host refuses a library whose id differs from the sources beside
+ * it, so a stale prebuilt binary cannot be loaded silently. */
+KIN_API const char *kin_build_id(void);
+/* 1 when the library was compiled with -DKIN_DEBUG (bounds checks on every table / scratch index inside the
+ * kernels -- the analogue of the reference's @debugassert, Kinematics.jl:25-30; a violation traps). */
+KIN_API int kin_debug_build(void);
 
 /* load_urdf.jl:20-80 / mechanism.jl:147-181 -> device tables on the CURRENT cuda device */
 KIN_API int kin_model_create(const KinModelDesc *desc, KinModel **out);

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -41,6 +42,7 @@ struct DeviceProgram {
     int32_t *d_int = nullptr;
     double *d_r64 = nullptr;
     float *d_r32 = nullptr;
+    ~DeviceProgram() { cudaFree(d_int); cudaFree(d_r64); cudaFree(d_r32); }
     // launch configuration per (precision, layout)
     int block[2][3] = {{0, 0, 0}, {0, 0, 0}}, occ[2][3] = {{0, 0, 0}, {0, 0, 0}}, regs[2][3] = {{0, 0, 0}, {0, 0, 0}};
     int bs_index[2][3] = {{0, 0, 0}, {0, 0, 0}};
@@ -61,31 +63,37 @@ struct KinModel {
     int device = 0, n_sm = 0, dev_smem = 0;
     std::atomic<int> ws_smem_limit[2][2][2] = {};   // opt-in shared-memory limit set on this model's device, per WS kernel
     cudaMemPool_t pool = nullptr;   // stream-ordered workspace pool that keeps its memory between calls
-    std::mutex mu;
-    std::map<std::vector<int>, DeviceProgram *> cache;
+    std::mutex mu;            // guards hm and the program cache (held only while a program is looked up / compiled)
+    std::mutex stage_mu;      // one host-staged call at a time per model (kin_eval_host)
+    // programs are reference-counted: a launch keeps its program alive even if kin_model_set_spheres /
+    // kin_model_set_boxes on another thread drops the cache entry meanwhile
+    std::map<std::vector<int>, std::shared_ptr<DeviceProgram>> cache;
     HostStage stage;
 };
 
 namespace {
 
-void free_program(DeviceProgram *p) {
-    if (!p) return;
-    cudaFree(p->d_int); cudaFree(p->d_r64); cudaFree(p->d_r32);
-    delete p;
-}
+void clear_cache(KinModel *m) { m->cache.clear(); }
 
-void clear_cache(KinModel *m) {
-    for (auto &kv : m->cache) free_program(kv.second);
-    m->cache.clear();
-}
+// Every entry point that touches the device runs on the model's device, whatever the caller's current device is
+// (the pool, the function attributes and the program tables belong to it), and restores the caller's device.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 int load_spheres(kin::HostModel &hm, int32_t n, const int32_t *link, const double *center, const double *radius) {
     if (n < 0 || n > KIN_MAX_SPHERES) return fail(KIN_ERR_LIMIT, "n_spheres exceeds KIN_MAX_SPHERES");
     if (n > 0 && (!link || !center || !radius)) return fail(KIN_ERR_INVALID_ARGUMENT, "null sphere table");
+    for (int s = 0; s < n; ++s)          // validate before touching the model: a failed call leaves it unchanged
+        if (link[s] < 1 || link[s] > hm.n_links) return fail(KIN_ERR_INVALID_ARGUMENT, "sphere_link id out of range");
     hm.n_sph = n;
     hm.sph_link.assign(n, 0); hm.sph_c.assign(3 * (size_t)n, 0.0); hm.sph_r.assign(n, 0.0);
     for (int s = 0; s < n; ++s) {
-        if (link[s] < 1 || link[s] > hm.n_links) return fail(KIN_ERR_INVALID_ARGUMENT, "sphere_link id out of range");
         hm.sph_link[s] = link[s] - 1;
         for (int k = 0; k < 3; ++k) hm.sph_c[3 * s + k] = center[3 * s + k];
         hm.sph_r[s] = radius[s];
@@ -205,7 +213,7 @@ int configure(KinModel *m, DeviceProgram *dp, int pi, int li) {
     return KIN_OK;
 }
 
-int get_program(KinModel *m, const KinCall *c, DeviceProgram **out) {
+int get_program(KinModel *m, const KinCall *c, std::shared_ptr<DeviceProgram> &out) {
     const bool want_coll = c->vals_out != nullptr;
     const bool want_stale = want_coll && c->grads_out && c->scratch_mode == KIN_SCRATCH_REFERENCE;
     const int n_fk = c->T_out ? c->n_fk_links : 0, n_jac = c->J_out ? c->n_jac_links : 0;
@@ -227,12 +235,10 @@ int get_program(KinModel *m, const KinCall *c, DeviceProgram **out) {
             if (c->jac_links[i] < 1 || c->jac_links[i] > m->hm.n_links) return fail(KIN_ERR_INVALID_ARGUMENT, "jacobian link id out of range");
             jac[i] = c->jac_links[i] - 1;
         }
-        DeviceProgram *dp = new DeviceProgram();
+        std::shared_ptr<DeviceProgram> dp = std::make_shared<DeviceProgram>();
         std::string err;
-        if (!kin::compile_program(m->hm, fk, jac, want_coll, want_stale, kin::JF_REGS, dp->prog, err)) {
-            delete dp;
+        if (!kin::compile_program(m->hm, fk, jac, want_coll, want_stale, kin::JF_REGS, dp->prog, err))
             return fail(KIN_ERR_INVALID_ARGUMENT, err);
-        }
         const kin::Program &p = dp->prog;
         std::vector<float> r32(p.reals.begin(), p.reals.end());
         cudaError_t e;
@@ -242,18 +248,17 @@ int get_program(KinModel *m, const KinCall *c, DeviceProgram **out) {
             (e = cudaMemcpy(dp->d_int, p.ints.data(), sizeof(int32_t) * p.ints.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
             (e = cudaMemcpy(dp->d_r64, p.reals.data(), sizeof(double) * p.reals.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
             (e = cudaMemcpy(dp->d_r32, r32.data(), sizeof(float) * r32.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
-            free_program(dp);
             return fail_cuda(e, "uploading the kinematic program");
         }
         it = m->cache.emplace(key, dp).first;
     }
-    DeviceProgram *dp = it->second;
+    std::shared_ptr<DeviceProgram> dp = it->second;
     const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
     if (dp->block[pi][li] == 0) {
-        int rc = configure(m, dp, pi, li);
+        int rc = configure(m, dp.get(), pi, li);
         if (rc != KIN_OK) return rc;
     }
-    *out = dp;
+    out = dp;
     return KIN_OK;
 }
 
@@ -332,6 +337,19 @@ extern "C" {
 
 const char *kin_last_error(void) { return g_err.c_str(); }
 int kin_abi_version(void) { return KIN_B200_ABI_VERSION; }
+#ifndef KIN_BUILD_ID
+#define KIN_BUILD_ID "unknown"
+#endif
+// the id sits behind a marker so that lib.py can read it from the file without loading the library
+extern "C" __attribute__((visibility("default"), used)) const char kin_build_id_marker[] = "KIN_BUILD_ID=" KIN_BUILD_ID;
+const char *kin_build_id(void) { return kin_build_id_marker + 13; }
+int kin_debug_build(void) {
+#ifdef KIN_DEBUG
+    return 1;
+#else
+    return 0;
+#endif
+}
 int64_t kin_launch_count(void) { return g_launches.load(); }
 
 int kin_model_create(const KinModelDesc *d, KinModel **out) {
@@ -395,6 +413,7 @@ int kin_program_dump(const KinModelDesc *d, const int32_t *fk_links, int32_t n_f
 
 int kin_model_destroy(KinModel *m) {
     if (!m) return KIN_OK;
+    DeviceGuard guard(m->device);
     clear_cache(m);
     for (int i = 0; i < HostStage::kStreams; ++i) {
         if (m->stage.stream[i]) cudaStreamDestroy(m->stage.stream[i]);
@@ -407,18 +426,34 @@ int kin_model_destroy(KinModel *m) {
 
 int kin_model_set_spheres(KinModel *m, int32_t n, const int32_t *link, const double *center, const double *radius) {
     if (!m) return fail(KIN_ERR_INVALID_ARGUMENT, "null model");
+    DeviceGuard guard(m->device);
     std::lock_guard<std::mutex> lock(m->mu);
     int rc = load_spheres(m->hm, n, link, center, radius);
-    clear_cache(m);
+    if (rc == KIN_OK) clear_cache(m);
     return rc;
 }
 
 int kin_model_set_boxes(KinModel *m, int32_t n, const double *pose, const double *width) {
     if (!m) return fail(KIN_ERR_INVALID_ARGUMENT, "null model");
+    DeviceGuard guard(m->device);
     std::lock_guard<std::mutex> lock(m->mu);
+    const int old_n = m->hm.n_box;
     int rc = load_boxes(m->hm, n, pose, width);
-    clear_cache(m);
-    return rc;
+    if (rc != KIN_OK) return rc;
+    if (n != old_n) { clear_cache(m); return KIN_OK; }
+    // Same number of boxes (the obstacle moved, sdf.jl:14-32): the compiled programs stay valid, only the box rows
+    // of their real sections are rewritten in place -- no recompilation, no cudaMalloc / cudaFree.
+    for (auto &kv : m->cache) {
+        DeviceProgram *dp = kv.second.get();
+        const kin::ProgHeader &h = dp->prog.h;
+        if (h.n_box != n || n == 0) continue;
+        double *rows = &dp->prog.reals[h.ro_box];
+        kin::emit_box_rows(m->hm, rows);
+        std::vector<float> r32(rows, rows + (size_t)n * kin::BOX_REALS);
+        CUDA_TRY(cudaMemcpy(dp->d_r64 + h.ro_box, rows, sizeof(double) * r32.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dp->d_r32 + h.ro_box, r32.data(), sizeof(float) * r32.size(), cudaMemcpyHostToDevice));
+    }
+    return KIN_OK;
 }
 
 int kin_model_n_dof(const KinModel *m) { return m ? m->hm.n_dof() : 0; }
@@ -430,25 +465,28 @@ int kin_eval(KinModel *m, const KinCall *c) {
     if (rc != KIN_OK) return rc;
     if (c->n == 0) return KIN_OK;
     if (!c->T_out && !c->J_out && !c->vals_out) return KIN_OK;
-    DeviceProgram *dp = nullptr;
-    rc = get_program(m, c, &dp);
+    DeviceGuard guard(m->device);
+    std::shared_ptr<DeviceProgram> dp;
+    rc = get_program(m, c, dp);
     if (rc != KIN_OK) return rc;
-    return launch(m, c, dp, (cudaStream_t)c->stream);
+    return launch(m, c, dp.get(), (cudaStream_t)c->stream);
 }
 
 int kin_query_launch(KinModel *m, const KinCall *c, int32_t *regs, int32_t *smem_bytes, int32_t *block, int32_t *grid) {
     int rc = validate_call(m, c);
     if (rc != KIN_OK) return rc;
-    DeviceProgram *dp = nullptr;
-    rc = get_program(m, c, &dp);
+    DeviceGuard guard(m->device);
+    std::shared_ptr<DeviceProgram> dp_;
+    rc = get_program(m, c, dp_);
     if (rc != KIN_OK) return rc;
+    DeviceProgram *dp = dp_.get();
     const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
     if (ws_eligible(m, c, dp)) {
         cudaFuncAttributes fa;
         const bool pre = ws_pre(m, c, dp);
         CUDA_TRY(cudaFuncGetAttributes(&fa, kWsKernels[li == KIN_LAYOUT_TILED32 ? 1 : 0][dp->prog.h.n_dof > dp->prog.h.n_joints ? 1 : 0][pre ? 1 : 0]));
         const long long tiles = (c->n + kin::WS_TILE - 1) / kin::WS_TILE;
-        if (regs) *regs = fa.numRegs;            // launch value; setmaxnreg moves it to 104 (producer) / 200 (consumers)
+        if (regs) *regs = fa.numRegs;            // launch value; setmaxnreg moves it to 88 (producer) / 208 (consumers), 120 / 192 in the collision-only variant
         if (smem_bytes) *smem_bytes = (int32_t)kin::ws_smem_bytes(dp->prog.h, pre);
         if (block) *block = kin::WS_THREADS;
         if (grid) *grid = (int32_t)(tiles < m->n_sm ? tiles : m->n_sm);
@@ -471,9 +509,11 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
     if (rc != KIN_OK) return rc;
     if (c->n == 0) return KIN_OK;
     if (!c->T_out && !c->J_out && !c->vals_out) return KIN_OK;
-    DeviceProgram *dp = nullptr;
-    rc = get_program(m, c, &dp);
+    DeviceGuard guard(m->device);
+    std::shared_ptr<DeviceProgram> dp_;
+    rc = get_program(m, c, dp_);
     if (rc != KIN_OK) return rc;
+    DeviceProgram *dp = dp_.get();
     const size_t es = c->precision == KIN_F32 ? 4 : 8;
     const int ND = m->hm.n_dof(), S = m->hm.n_sph;
     const int rows = c->with_rot ? 6 : 3;
@@ -484,11 +524,14 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
     const size_t per_cfg = es * (cq + cT + cJ + cV + cG) + 4 * cA;
     long long chunk = 1 << 16;
     if (chunk > c->n) chunk = c->n;
+    // tiled storage holds whole tiles of 32 configurations: size the staging carves for the padded chunk (the
+    // kernel addresses, and the copies move, roundup(count, 32) records; host buffers are padded likewise)
+    if (c->layout == KIN_LAYOUT_TILED32) chunk = (chunk + 31) / 32 * 32;
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t need = align(es * cq * chunk) + align(es * cT * chunk) + align(es * cJ * chunk) +
                         align(es * cV * chunk) + align(es * cG * chunk) + align(4 * cA * chunk);
     (void)per_cfg;
-    std::lock_guard<std::mutex> lock(m->mu);   // one host-staged call at a time per model
+    std::lock_guard<std::mutex> lock(m->stage_mu);   // one host-staged call at a time per model (m->mu stays free)
     HostStage &st = m->stage;
     if (st.bytes < need) {
         for (int i = 0; i < HostStage::kStreams; ++i) {
@@ -576,7 +619,12 @@ int kin_sdf_points(int32_t n_boxes, const double *box_pose, const double *box_wi
                              cudaMemcpyHostToDevice, stream));
     const int block = 256;
     long long grid = (n + block - 1) / block;
-    if (grid > 148 * 8) grid = 148 * 8;
+    {
+        int dev = 0, n_sm = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (grid > (long long)n_sm * 8) grid = (long long)n_sm * 8;
+    }
     const bool aos = layout == KIN_LAYOUT_AOS;
     if (precision == KIN_F64) {
         if (aos) kin::sdf_points_kernel<double, true><<<(unsigned)grid, block, bytes, stream>>>((const double *)d_tab, n_boxes, (const double *)pts, n, grad_mode, (double *)vals_out, (double *)grads_out, argmin_out);
@@ -599,6 +647,7 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
     if (mode != KIN_POSE_IK_OBJECTIVE && mode != KIN_POSE_CONSTRAINT) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown pose mode");
     if (layout != KIN_LAYOUT_SOA && layout != KIN_LAYOUT_AOS) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_pose_residual supports the SoA and AoS layouts");
     if (n == 0) return KIN_OK;
+    DeviceGuard guard(m->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t es = precision == KIN_F32 ? 4 : 8;
     const int nd = m->hm.n_dof(), rows = with_rot ? 6 : 3;
@@ -615,7 +664,7 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
     if (rc != KIN_OK) { cudaFreeAsync(ws, stream); return rc; }
     const int block = 256;
     long long grid = (n + block - 1) / block;
-    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid > (long long)m->n_sm * 16) grid = (long long)m->n_sm * 16;
     const bool aos = layout == KIN_LAYOUT_AOS;
     if (precision == KIN_F64) {
         auto T = (const double *)ws, J = (const double *)((unsigned char *)ws + tb);
@@ -626,7 +675,10 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
         if (aos) kin::pose_residual_kernel<float, true><<<(unsigned)grid, block, 0, stream>>>(T, J, (const float *)target, target_per_config, n, nd, with_rot, mode, (float *)val_out, (float *)jac_out);
         else kin::pose_residual_kernel<float, false><<<(unsigned)grid, block, 0, stream>>>(T, J, (const float *)target, target_per_config, n, nd, with_rot, mode, (float *)val_out, (float *)jac_out);
     }
-    CUDA_TRY(cudaGetLastError());
+    {
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) { cudaFreeAsync(ws, stream); return fail_cuda(le, "launching pose_residual_kernel"); }
+    }
     g_launches.fetch_add(1);
     CUDA_TRY(cudaFreeAsync(ws, stream));
     return KIN_OK;

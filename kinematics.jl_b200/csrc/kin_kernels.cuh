@@ -23,6 +23,24 @@
 #define KIN_LM_MAX_DOF 16
 #endif
 
+// Debug build (-DKIN_DEBUG, kinematics.jl_b200/lib.py: build(debug=True) -> libkin_b200_debug.so): every table
+// index and scratch-slot index the kernels derive from the program tables is range-checked; a violation prints
+// the condition and traps.  This is the analogue of the reference's @debugassert (Kinematics.jl:25-30, cache.jl:24,35,
+// stack.jl:15,21, algorithm.jl:9-10,43).  compiles to nothing in the release build.
+#ifdef KIN_DEBUG
+#include <cstdio>
+#define KIN_DASSERT(cond)                                                                                   \
+    do {                                                                                                    \
+        if (!(cond)) {                                                                                      \
+            printf("KIN_DEBUG assertion failed: %s (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                                      \
+            __trap();                                                                                       \
+        }                                                                                                   \
+    } while (0)
+#else
+#define KIN_DASSERT(cond) ((void)0)
+#endif
+
 namespace kin {
 
 struct KernelArgs {
@@ -434,6 +452,8 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 T.p[0] = T.p[1] = T.p[2] = real(0);
             } else {
                 const int psrc = ni[0], flags = ni[2], qcol = ni[3];
+                KIN_DASSERT(qcol >= 0 && qcol < ND);
+                KIN_DASSERT(psrc < 0 || so_save + 12 * (psrc + 1) <= h.so_jf);
                 if (psrc >= 0) {
                     const real *sv = &SCR(so_save + 12 * psrc);
                     #pragma unroll
@@ -506,6 +526,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                 }
             }
             if (ni[4] >= 0) {
+                KIN_DASSERT(so_save + 12 * (ni[4] + 1) <= h.so_jf);
                 real *sv = &SCR(so_save + 12 * ni[4]);
                 #pragma unroll
                 for (int i = 0; i < 9; ++i) sv[i * BS] = T.r[i];
@@ -517,6 +538,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
             for (int a = ni[5]; a < ni[6]; ++a) {
                 const int32_t *ai = ti + io_att + a * ATT_INTS;
                 const real *ar = tr + ro_att + a * ATT_REALS;
+                KIN_DASSERT(a >= 0 && a < h.n_att && ai[0] < n_fk && ai[2] < h.n_jac);
                 Tf<real> Tl;
                 tf_mul_const(T, ar, ai[1] & AF_R_IDENTITY, Tl);
                 if (ai[0] >= 0 && A.T_out) {       // get_transform, as 3x4 column-major
@@ -593,6 +615,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
             if (COLL) {
                 for (int k = ni[7]; k < ni[8]; ++k) {
                     const int s = ti[io_sph_order + k];
+                    KIN_DASSERT(k >= 0 && k < S && s >= 0 && s < S);
                     const real *sr = tr + ro_sph + s * SPH_REALS;
                     const real c0 = sr[0], c1 = sr[1], c2 = sr[2];
                     real *cs = &SCR(so_cent + 3 * s);
@@ -660,6 +683,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     const int s = s0 + g;
                     const real dmin = hand[g * BS];
                     const int kmin = reinterpret_cast<const int *>(&hand[(SPH_GROUP + g) * BS])[0];
+                    KIN_DASSERT(kmin >= 0 && kmin < n_box);
                     const real dist0 = dmin - tr[ro_sph + s * SPH_REALS + 3];
                     const bool truncated = dist0 > trunc;
                     *Vp = (truncated ? trunc : dist0) - voff;

@@ -88,14 +88,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
         "}" : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// a waiting warp sleeps between polls so that it does not take issue slots from the warps it is waiting for
-// A hand-over that never completes would hang the GPU; after ~2^24 polls (seconds, against microseconds per tile) the
-// kernel traps instead, which surfaces as a CUDA error on the stream.
+// a waiting warp sleeps between polls so that it does not take issue slots from the warps it is waiting for.
+// A hand-over that never completes would hang the GPU.  The debug build (-DKIN_DEBUG) traps after 2^24 polls
+// (seconds, against microseconds per tile); the release build only after 2^28 (about a minute of sleeping -- far
+// beyond any slowdown a debugger or sanitizer causes), because a trap is a sticky error for the whole context.
+#ifdef KIN_DEBUG
+#define KIN_WS_MAX_POLLS (1u << 24)
+#else
+#define KIN_WS_MAX_POLLS (1u << 28)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     unsigned polls = 0;
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(KIN_WS_SLEEP_NS);
-        if (++polls > (1u << 24)) __trap();
+        if (++polls > KIN_WS_MAX_POLLS) __trap();
     }
 }
 
@@ -203,6 +209,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                     T.p[0] = T.p[1] = T.p[2] = real(0);
                 } else {
                     const int flags = ni[2], qcol = ni[3];
+                    KIN_DASSERT(qcol >= 0 && qcol < ND && 6 * (qcol + 1) <= FRAME_SLOTS && ni[0] < 0);
                     // A = T_parent * joint.pose : the joint frame (algorithm.jl:47-48); the chain has no branching here
                     Tf<real> Aj;
                     tf_mul_const(T, nr, flags & NF_OFF_R_IDENTITY, Aj);
@@ -313,6 +320,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                 // ---- collision-sphere centres on this node (collision.jl:54 / :80) ----
                 for (int k2 = ni[7]; k2 < ni[8]; ++k2) {
                     const int s = ti[io_sph_order + k2];
+                    KIN_DASSERT(s >= 0 && s < S && FRAME_SLOTS + 3 * (s + 1) <= ring_slots);
                     const real *sr = tr + ro_sph + s * SPH_REALS;
                     const real c0 = sr[0], c1 = sr[1], c2 = sr[2];
                     real *cs = rg + (FRAME_SLOTS + 3 * s) * BS;
@@ -461,6 +469,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                     const int s = s0 + g;
                     const real dmin = PRE ? pre_d[s * BS] : hand[g * BS];
                     const int kmin = PRE ? pre_k[s * BS] : reinterpret_cast<const int *>(&hand[(SPH_GROUP + g) * BS])[0];
+                    KIN_DASSERT(kmin >= 0 && kmin < n_box && st >= 0 && st < WS_STAGES);
                     const real dist0 = dmin - tr[ro_sph + s * SPH_REALS + 3];
                     const bool truncated = dist0 > trunc;
                     __stcs(Vp, (truncated ? trunc : dist0) - voff);

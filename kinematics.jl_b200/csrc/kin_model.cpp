@@ -109,6 +109,16 @@ bool HostModel::finalize(std::string &err) {
     return true;
 }
 
+void emit_box_rows(const HostModel &m, double *dst) {
+    for (int b = 0; b < m.n_box; ++b) {
+        double *br = dst + (size_t)b * BOX_REALS;
+        std::memset(br, 0, sizeof(double) * BOX_REALS);
+        std::memcpy(br, m.box_inv[b].r, sizeof(double) * 9);
+        std::memcpy(br + 9, m.box_inv[b].p, sizeof(double) * 3);
+        std::memcpy(br + 12, &m.box_half[3 * b], sizeof(double) * 3);
+    }
+}
+
 namespace {
 struct Node {
     int link;            // -1 for the virtual root
@@ -310,12 +320,7 @@ bool compile_program(const HostModel &m, const std::vector<int> &fk_links, const
     for (int l = 0; l < L; ++l)
         if (m.qidx[l] >= 0) I[h.io_col_type + m.qidx[l]] = m.jtype[l];
     if (m.with_base) { I[h.io_col_type + m.n_joints] = 2; I[h.io_col_type + m.n_joints + 1] = 2; I[h.io_col_type + m.n_joints + 2] = 1; }
-    for (int b = 0; b < h.n_box; ++b) {
-        double *br = &R[h.ro_box + (size_t)b * BOX_REALS];
-        std::memcpy(br, m.box_inv[b].r, sizeof(double) * 9);
-        std::memcpy(br + 9, m.box_inv[b].p, sizeof(double) * 3);
-        std::memcpy(br + 12, &m.box_half[3 * b], sizeof(double) * 3);
-    }
+    if (h.n_box > 0) emit_box_rows(m, &R[h.ro_box]);
 
     // ---- per-thread scratch map ----
     // so_q doubles as the per-group (dmin, argmin) hand-over of the collision phase: 2 * SPH_GROUP slots

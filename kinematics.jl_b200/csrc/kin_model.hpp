@@ -44,6 +44,9 @@ struct Program {
     std::vector<double> reals;
 };
 
+// the box table of a program: n_box rows of BOX_REALS doubles (inverse pose, half extents, padding)
+void emit_box_rows(const HostModel &m, double *dst);
+
 // fk_links / jac_links are 0-based link indices in output order.
 bool compile_program(const HostModel &m, const std::vector<int> &fk_links, const std::vector<int> &jac_links,
                      bool want_coll, bool want_stale, int jf_regs, Program &out, std::string &err);

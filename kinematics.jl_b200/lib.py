@@ -3,11 +3,13 @@ library is missing or there is no CUDA device, every operator raises."""
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libkin_b200.so")
+SO_PATH_DEBUG = os.path.join(HERE, "libkin_b200_debug.so")
 CSRC = os.path.join(HERE, "csrc")
 
 F64, F32 = 0, 1
@@ -23,7 +25,6 @@ _ip = C.POINTER(C.c_int32)
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static"]
 SOURCES = ["kin_b200.cu", "kin_model.cpp"]
-HEADERS = ["kin_kernels.cuh", "kin_kernels_ws.cuh", "kin_program.h", "kin_model.hpp"]
 
 
 class KinError(RuntimeError):
@@ -48,46 +49,100 @@ class KinCall(C.Structure):
                 ("vals_offset", C.c_double), ("stream", C.c_void_p)]
 
 
-EXPORTS = ["kin_last_error", "kin_abi_version", "kin_model_create", "kin_model_destroy", "kin_model_set_spheres",
+EXPORTS = ["kin_last_error", "kin_abi_version", "kin_build_id", "kin_debug_build", "kin_model_create", "kin_model_destroy", "kin_model_set_spheres",
            "kin_model_set_boxes", "kin_model_n_dof", "kin_model_n_spheres", "kin_model_n_boxes", "kin_eval",
            "kin_eval_host", "kin_fk_links", "kin_fk_jacobian", "kin_collision", "kin_launch_count",
            "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual", "kin_lm_step", "kin_lm_accept"]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(SO_PATH):
-        return True
-    t = os.path.getmtime(SO_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(os.path.dirname(HERE), "include", "kin_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+def source_files():
+    """Every file the library is compiled from (the build id is their digest)."""
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cpp", ".cuh", ".h", ".hpp"))] + \
+           [os.path.join(os.path.dirname(HERE), "include", "kin_b200.h")]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> kinematics.jl_b200/libkin_b200.so (in-tree)."""
-    if force or needs_build():
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + \
-              [os.path.join(CSRC, s) for s in SOURCES]
-        out = subprocess.run(cmd, capture_output=True, text=True)
-        if out.returncode != 0:
-            raise KinError("nvcc failed:\n" + out.stdout + out.stderr)
+def source_id() -> str:
+    """sha256 (first 16 hex digits) over the names and contents of csrc/* and include/kin_b200.h."""
+    h = hashlib.sha256()
+    for f in source_files():
+        h.update(os.path.basename(f).encode() + b"\0")
+        h.update(open(f, "rb").read())
+        h.update(b"\0")
+    return h.hexdigest()[:16]
+
+
+def so_path(debug: bool = False) -> str:
+    return SO_PATH_DEBUG if debug else SO_PATH
+
+
+_ID_MARKER = b"KIN_BUILD_ID="
+
+
+def so_build_id(path: str):
+    """Build id of a built library, or None when it is missing / predates the build id.  Read from the file
+    (the id is stored behind a marker string) rather than through dlopen, which would pin the old mapping."""
+    if not os.path.exists(path):
+        return None
+    data = open(path, "rb").read()
+    i = data.find(_ID_MARKER)
+    if i < 0:
+        return None
+    j = data.find(b"\0", i)
+    return data[i + len(_ID_MARKER):j].decode(errors="replace")
+
+
+def needs_build(debug: bool = False) -> bool:
+    return so_build_id(so_path(debug)) != source_id()
+
+
+def _nvcc_cmd(debug: bool, verbose: bool):
+    return ["nvcc"] + NVCC_FLAGS + (["-DKIN_DEBUG"] if debug else []) + ['-DKIN_BUILD_ID="%s"' % source_id()] + \
+           (["-Xptxas", "-v"] if verbose else []) + ["-o", so_path(debug)] + [os.path.join(CSRC, s) for s in SOURCES]
+
+
+def build(force: bool = False, verbose: bool = False, debug: bool = False, both: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> kinematics.jl_b200/libkin_b200.so (in-tree).
+    ``debug=True`` builds libkin_b200_debug.so with -DKIN_DEBUG (bounds-checked table / scratch indices);
+    ``both=True`` builds the two libraries side by side (two nvcc processes)."""
+    variants = [False, True] if both else [debug]
+    procs = []
+    for dbg in variants:
+        if force or needs_build(dbg):
+            procs.append((dbg, subprocess.Popen(_nvcc_cmd(dbg, verbose), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for dbg, pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise KinError("nvcc failed (%s build):\n" % ("debug" if dbg else "release") + out + err)
         if verbose:
-            print(out.stderr)
-    return SO_PATH
+            print(err)
+    return so_path(debug)
 
 
 _LIB = None
 
 
 def lib():
-    """Load libkin_b200.so; raises KinError when it has not been built (no fallback path exists)."""
+    """Load libkin_b200.so (libkin_b200_debug.so when KIN_DEBUG=1 is set); raises KinError when it has not been
+    built or was built from other sources than the ones beside it (no fallback path exists)."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(SO_PATH):
-            raise KinError("libkin_b200.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
-                           "there is no CPU fallback" % SO_PATH)
-        L = C.CDLL(SO_PATH)
+        debug = os.environ.get("KIN_DEBUG", "") not in ("", "0")
+        path = so_path(debug)
+        if not os.path.exists(path):
+            raise KinError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "there is no CPU fallback" % path)
+        L = C.CDLL(path)
+        try:
+            L.kin_build_id.restype = C.c_char_p
+            built = L.kin_build_id().decode()
+        except AttributeError:
+            built = "none"
+        if built != source_id() and not os.environ.get("KIN_ALLOW_STALE_SO"):
+            raise KinError("%s was built from other sources (build id %s, sources on disk %s): rebuild with "
+                           "`python -c 'import __graft_entry__ as g; g.build()'`" % (path, built, source_id()))
         L.kin_last_error.restype = C.c_char_p
         L.kin_abi_version.restype = C.c_int
+        L.kin_debug_build.restype = C.c_int
         L.kin_model_create.argtypes = [C.POINTER(KinModelDesc), C.POINTER(C.c_void_p)]
         L.kin_model_destroy.argtypes = [C.c_void_p]
         L.kin_model_set_spheres.argtypes = [C.c_void_p, C.c_int32, _ip, _dp, _dp]

@@ -5,15 +5,9 @@ import os
 
 import numpy as np
 
-import kinematics_jl_b200 as K
 from oracle import ref_model as R
 from conftest import DATA, FETCH_JOINT_NAMES
-
-FRIDGE_STATE = [2.0, 1.2, 0.0, 0.0]       # door angle, base x, y, theta (fridge_demo.jl:28)
-
-
-def sphere_fixture():
-    return json.load(open(os.path.join(DATA, "fetch_spheres.json")))["links"]
+from scene_fetch import FRIDGE_STATE, product_fetch, sphere_fixture  # noqa: F401  (the product-side builders)
 
 
 def random_configs(joints_ref, N, with_base, seed=0, zeros_every=0):
@@ -28,16 +22,6 @@ def random_configs(joints_ref, N, with_base, seed=0, zeros_every=0):
     if zeros_every:
         q[::zeros_every] = 0.0              # exercises the a == 0.0 short-cut (mechanism.jl:95,101)
     return np.ascontiguousarray(q)
-
-
-def product_fetch(with_base=False, sphere_links=None):
-    m = K.parse_urdf(os.path.join(DATA, "fetch.urdf"), with_base=with_base)
-    joints = [K.find_joint(m, n) for n in FETCH_JOINT_NAMES]
-    sscc = K.SweptSphereCollisionChecker(m)
-    for s in sphere_fixture():
-        if sphere_links is None or s["link"] in sphere_links:
-            K.add_coll_links(sscc, K.find_link(m, s["link"]), s["centers"], s["radius"])
-    return m, joints, sscc
 
 
 def oracle_fetch(with_base=False, sphere_links=None):

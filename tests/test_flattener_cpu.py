@@ -23,7 +23,8 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L.EXPORTS)
     for name in declared:
         assert hasattr(L.lib(), name), name
-    assert L.lib().kin_abi_version() == 1
+    assert L.lib().kin_abi_version() == 2
+    assert L.lib().kin_build_id().decode() == L.source_id()        # the loaded binary is the one built from these sources
 
 
 def test_no_device_is_a_loud_error():

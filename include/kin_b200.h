@@ -230,6 +230,16 @@ typedef enum { KIN_POSE_IK_OBJECTIVE = 0, KIN_POSE_CONSTRAINT = 1 } KinPoseMode;
 KIN_API int kin_pose_residual(KinModel *model, int32_t precision, int32_t layout, const void *q, int64_t n,
                               int32_t link_id, const void *target, int32_t target_per_config, int32_t with_rot,
                               int32_t mode, void *val_out, void *jac_out, void *stream);
+/* The whole (link, target, with_rot) loop of one PoseConstraint (planning.jl:124-137) in one call: n_links
+ * links (HOST ids / flags), target = 6 values per link, per configuration (6 * n_links components in `layout`) or
+ * shared (6 * n_links contiguous values).  With n_cons = sum(with_rots[l] ? 6 : 3):
+ *   KIN_POSE_CONSTRAINT    val_out (n_cons per configuration) = the stacked pose differences, jac_out ((n_dof, n_cons)
+ *                          column-major per configuration) = the rows j_start:j_end of the reference's jac_mat
+ *   KIN_POSE_IK_OBJECTIVE  val_out[N] = sum over links of sum(e.^2), jac_out (n_dof) = its gradient
+ * Two kernel launches in total (kin_eval for the n_links transforms + Euler-rate Jacobians, then the residuals). */
+KIN_API int kin_pose_residual_multi(KinModel *model, int32_t precision, int32_t layout, const void *q, int64_t n,
+                                    int32_t n_links, const int32_t *link_ids, const int32_t *with_rots, const void *target,
+                                    int32_t target_per_config, int32_t mode, void *val_out, void *jac_out, void *stream);
 
 /* Batched Levenberg-Marquardt iteration of the IK driver built on kin_pose_residual / kin_eval (config 4;
  * the reference drives the same evaluations with NLopt SLSQP, inverse_kinematics.jl:1-30, which is third
@@ -252,6 +262,11 @@ KIN_API int kin_lm_accept(int64_t n, int32_t n_dof, int32_t dim, const double *q
 KIN_API int64_t kin_launch_count(void);
 KIN_API int kin_query_launch(KinModel *model, const KinCall *call, int32_t *regs, int32_t *smem_bytes,
                      int32_t *block, int32_t *grid);
+
+/* FP64 peak of the current device, measured: 8 independent DFMA chains per thread, 8 x 256 threads per SM.  Returns
+ * TFLOP/s (2 flops per DFMA), DFMA per clock per SM at the device's nominal maximum SM clock, and that clock.  This is
+ * the denominator of the "FP64 pipe" fractions in DESIGN.md / profiles (SURVEY 6 asks for it). */
+KIN_API int kin_probe_fp64(double *tflops_out, double *dfma_per_clk_per_sm_out, double *sm_mhz_out);
 
 /* Host-only (no device needed): compile the kinematic program a call with these requests would run
  * and copy its tables out; the CPU test-suite interprets them against the oracle.  header_out

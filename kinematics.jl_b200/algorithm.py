@@ -71,6 +71,10 @@ def get_jacobian_(m: Mechanism, link: Link, joints, with_rot: bool, mat_out, rpy
         mat_out[...] = store[0, 0].cpu().numpy().T
         return
     assert mat_out.shape == (N, rows, dm.n_dof)
+    if not mat_out.is_cuda:
+        raise ValueError("get_jacobian_: a batched mat_out must be a CUDA tensor")
+    if mat_out.dtype != Q.dtype:             # the kernel writes elements of q's type into the caller's buffer
+        Q, ql, N = current_q(m, mat_out.dtype)
     if mat_out.permute(0, 2, 1).is_contiguous():
         layout, store = _lib.AOS, mat_out.permute(0, 2, 1).unsqueeze(1)
     elif mat_out.permute(2, 1, 0).is_contiguous():

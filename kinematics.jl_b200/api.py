@@ -13,9 +13,10 @@ from .sdf import BoxSDF, UnionSDF
 from .collision import (SweptSphereCollisionChecker, add_coll_links, compute_coll_dists,
                         compute_coll_dists_and_grads)
 
-from .inverse_kinematics import ik_objective, inverse_kinematics_batch
-from .planning import (ConfigurationConstraint, IneqConst, PoseConstraint, create_straight_trajectory, gather_stacked,
-                       nloptize, pose_constraint, shard_range, smoothness_objective)
+from .inverse_kinematics import ik_objective, inverse_kinematics, inverse_kinematics_batch
+from .planning import (ConfigurationConstraint, EqConst, IneqConst, Objective, PoseConstraint, construct_problem,
+                       create_straight_trajectory, gather_packed, gather_stacked, nloptize, plan_trajectory, pose_constraint, scipynize,
+                       shard_range, smoothness_objective)
 from .lib import POSE_CONSTRAINT, POSE_IK_OBJECTIVE
 
 __all__ = [n for n in dir() if not n.startswith("_")]

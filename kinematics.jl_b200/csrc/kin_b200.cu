@@ -639,26 +639,29 @@ int kin_sdf_points(int32_t n_boxes, const double *box_pose, const double *box_wi
     return KIN_OK;
 }
 
-int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void *q, int64_t n, int32_t link_id,
-                      const void *target, int32_t target_per_config, int32_t with_rot, int32_t mode, void *val_out,
-                      void *jac_out, void *stream_) {
+int kin_pose_residual_multi(KinModel *m, int32_t precision, int32_t layout, const void *q, int64_t n, int32_t n_links,
+                            const int32_t *link_ids, const int32_t *with_rots, const void *target, int32_t target_per_config,
+                            int32_t mode, void *val_out, void *jac_out, void *stream_) {
     if (!m) return fail(KIN_ERR_INVALID_ARGUMENT, "null model");
     if (n < 0 || (n > 0 && (!q || !target || !val_out || !jac_out))) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_links < 1 || n_links > 32 || !link_ids || !with_rots) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_pose_residual: 1..32 links");
     if (mode != KIN_POSE_IK_OBJECTIVE && mode != KIN_POSE_CONSTRAINT) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown pose mode");
     if (layout != KIN_LAYOUT_SOA && layout != KIN_LAYOUT_AOS) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_pose_residual supports the SoA and AoS layouts");
     if (n == 0) return KIN_OK;
     DeviceGuard guard(m->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t es = precision == KIN_F32 ? 4 : 8;
-    const int nd = m->hm.n_dof(), rows = with_rot ? 6 : 3;
+    unsigned rot_mask = 0;
+    for (int l = 0; l < n_links; ++l) rot_mask |= (with_rots[l] ? 1u : 0u) << l;
+    const int nd = m->hm.n_dof(), rows = rot_mask ? 6 : 3;
     void *ws = nullptr;
-    const size_t tb = es * 12 * (size_t)n, jb = es * (size_t)rows * nd * (size_t)n;
+    const size_t tb = es * 12 * (size_t)n_links * (size_t)n, jb = es * (size_t)rows * nd * (size_t)n_links * (size_t)n;
     CUDA_TRY(cudaMallocFromPoolAsync(&ws, tb + jb, m->pool, stream));
     KinCall c;
     std::memset(&c, 0, sizeof c);
     c.precision = precision; c.layout = layout; c.n = n; c.q = q;
-    c.n_fk_links = 1; c.fk_links = &link_id; c.T_out = ws;
-    c.n_jac_links = 1; c.jac_links = &link_id; c.with_rot = with_rot; c.rpy_jac = 1; c.J_out = (unsigned char *)ws + tb;
+    c.n_fk_links = n_links; c.fk_links = link_ids; c.T_out = ws;
+    c.n_jac_links = n_links; c.jac_links = link_ids; c.with_rot = rot_mask ? 1 : 0; c.rpy_jac = 1; c.J_out = (unsigned char *)ws + tb;
     c.truncation_dist = INFINITY; c.stream = stream_;
     int rc = kin_eval(m, &c);
     if (rc != KIN_OK) { cudaFreeAsync(ws, stream); return rc; }
@@ -668,12 +671,12 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
     const bool aos = layout == KIN_LAYOUT_AOS;
     if (precision == KIN_F64) {
         auto T = (const double *)ws, J = (const double *)((unsigned char *)ws + tb);
-        if (aos) kin::pose_residual_kernel<double, true><<<(unsigned)grid, block, 0, stream>>>(T, J, (const double *)target, target_per_config, n, nd, with_rot, mode, (double *)val_out, (double *)jac_out);
-        else kin::pose_residual_kernel<double, false><<<(unsigned)grid, block, 0, stream>>>(T, J, (const double *)target, target_per_config, n, nd, with_rot, mode, (double *)val_out, (double *)jac_out);
+        if (aos) kin::pose_residual_kernel<double, true><<<(unsigned)grid, block, 0, stream>>>(T, J, (const double *)target, target_per_config, n, nd, n_links, rot_mask, mode, (double *)val_out, (double *)jac_out);
+        else kin::pose_residual_kernel<double, false><<<(unsigned)grid, block, 0, stream>>>(T, J, (const double *)target, target_per_config, n, nd, n_links, rot_mask, mode, (double *)val_out, (double *)jac_out);
     } else {
         auto T = (const float *)ws, J = (const float *)((unsigned char *)ws + tb);
-        if (aos) kin::pose_residual_kernel<float, true><<<(unsigned)grid, block, 0, stream>>>(T, J, (const float *)target, target_per_config, n, nd, with_rot, mode, (float *)val_out, (float *)jac_out);
-        else kin::pose_residual_kernel<float, false><<<(unsigned)grid, block, 0, stream>>>(T, J, (const float *)target, target_per_config, n, nd, with_rot, mode, (float *)val_out, (float *)jac_out);
+        if (aos) kin::pose_residual_kernel<float, true><<<(unsigned)grid, block, 0, stream>>>(T, J, (const float *)target, target_per_config, n, nd, n_links, rot_mask, mode, (float *)val_out, (float *)jac_out);
+        else kin::pose_residual_kernel<float, false><<<(unsigned)grid, block, 0, stream>>>(T, J, (const float *)target, target_per_config, n, nd, n_links, rot_mask, mode, (float *)val_out, (float *)jac_out);
     }
     {
         cudaError_t le = cudaGetLastError();
@@ -682,6 +685,13 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
     g_launches.fetch_add(1);
     CUDA_TRY(cudaFreeAsync(ws, stream));
     return KIN_OK;
+}
+
+int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void *q, int64_t n, int32_t link_id,
+                      const void *target, int32_t target_per_config, int32_t with_rot, int32_t mode, void *val_out,
+                      void *jac_out, void *stream_) {
+    return kin_pose_residual_multi(m, precision, layout, q, n, 1, &link_id, &with_rot, target, target_per_config, mode,
+                                   val_out, jac_out, stream_);
 }
 
 int kin_lm_step(int64_t n, int32_t n_dof, int32_t dim, const double *q, const double *e, const double *J,
@@ -703,6 +713,58 @@ int kin_lm_accept(int64_t n, int32_t n_dof, int32_t dim, const double *q_try, co
     kin::lm_accept_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, n_dof, dim, q_try, e_try, J_try, f_try, q, e, J, f, lambda);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1);
+    return KIN_OK;
+}
+
+// FP64 peak probe (the denominator of the "FP64 pipe" column of the rooflines): every thread runs 8 independent
+// DFMA chains, 8 CTAs of 256 threads per SM.
+}  // extern "C"
+namespace {
+__global__ void __launch_bounds__(256) probe_dfma_kernel(double *out, int iters) {
+    double a[8];
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1e-9 * (threadIdx.x + k);
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c);
+    }
+    double s = 0;
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+extern "C" {
+
+int kin_probe_fp64(double *tflops_out, double *dfma_per_clk_per_sm_out, double *sm_mhz_out) {
+    int dev = 0, n_sm = 0, khz = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    const int grid = n_sm * 8, block = 256, iters = 1 << 16;
+    double *buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, sizeof(double) * (size_t)grid * block));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {          // first repetition = warm-up
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        probe_dfma_kernel<<<grid, block>>>(buf, iters);
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    g_launches.fetch_add(4);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    const double dfma = 8.0 * iters * (double)grid * block;
+    if (tflops_out) *tflops_out = 2.0 * dfma / (best * 1e-3) / 1e12;
+    // per clock at the NOMINAL maximum SM clock (the achieved clock is sampled by the caller with nvidia-smi)
+    if (dfma_per_clk_per_sm_out) *dfma_per_clk_per_sm_out = dfma / (best * 1e-3) / ((double)khz * 1e3) / n_sm;
+    if (sm_mhz_out) *sm_mhz_out = khz / 1e3;
     return KIN_OK;
 }
 

@@ -796,52 +796,65 @@ sdf_points_kernel(const real *__restrict__ boxes, int n_box, const real *__restr
     }
 }
 
-// Pose residual / IK objective from the link transform T (12 per configuration) and its Euler-rate
-// Jacobian J (6 or 3 x n_dof), both produced by kin_eval_kernel in the same layout.
-//   mode 0  inverse_kinematics.jl:38-50   f = sum(e^2), grad = -2 J' e,   e = [p_t - p; rpy_t - rpy]
-//   mode 1  planning.jl:114-138           val = [p - p_t; rpy - rpy_t],   jac_T(n_dof, dim) = J'
+// Pose residuals / IK objective from the link transforms T (12 per link per configuration) and their Euler-rate
+// Jacobians J (rows_j x n_dof per link), both produced by kin_eval_kernel in the same layout, for ALL the
+// (link, target, with_rot) triples of a constraint in one launch (the loop of planning.jl:124-137).
+//   mode 0  inverse_kinematics.jl:38-50   f = sum(e^2), grad = -2 J' e,   e = [p_t - p; rpy_t - rpy]  (summed over links)
+//   mode 1  planning.jl:114-138           val = [p - p_t; rpy - rpy_t] per link, stacked;  jac_T(n_dof, n_cons) = J'
+// rot_mask bit l: link l constrains the rotation too (dim 6, else 3); rows_j = 6 when any bit is set, else 3.
+// target: 6 values per link ([x y z roll pitch yaw]), per configuration or shared.
 template <typename real, bool AOS>
 __global__ void __launch_bounds__(256)
 pose_residual_kernel(const real *__restrict__ T, const real *__restrict__ J, const real *__restrict__ target,
-                     int target_per_config, long long n_cfg, int nd, int with_rot, int mode,
+                     int target_per_config, long long n_cfg, int nd, int nl, unsigned rot_mask, int mode,
                      real *__restrict__ val_out, real *__restrict__ jac_out) {
-    const int rows = with_rot ? 6 : 3;
+    const int rows_j = rot_mask ? 6 : 3;
+    int n_cons = 0;
+    for (int l = 0; l < nl; ++l) n_cons += ((rot_mask >> l) & 1u) ? 6 : 3;
     for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n_cfg; n += (long long)gridDim.x * blockDim.x) {
         const size_t es = AOS ? size_t(1) : (size_t)n_cfg;
-        const real *Tn = T + (AOS ? n * 12 : n);
-        const real *Jn = J + (AOS ? n * (long long)(rows * nd) : n);
-        const real *tg = target_per_config ? target + (AOS ? n * 6 : n) : target;
         const size_t ts = target_per_config ? es : size_t(1);
-        real e[6];
-        #pragma unroll
-        for (int i = 0; i < 3; ++i) e[i] = Tn[(9 + i) * es] - tg[i * ts];          // p - p_t
-        if (with_rot) {   // rpy(T), transform.jl:45-48 (RotZYX): R[r][c] = T[c*3 + r]
-            const real r00 = Tn[0], r10 = Tn[es], r20 = Tn[2 * es], r01 = Tn[3 * es], r11 = Tn[4 * es],
-                       r21 = Tn[5 * es], r02 = Tn[6 * es], r12 = Tn[7 * es], r22 = Tn[8 * es];
-            const real yaw = atan2_(r10, r00);
-            real s1, c1;
-            sincos_(yaw, &s1, &c1);
-            const real pitch = atan2_(-r20, sqrt_(fma_(r21, r21, r22 * r22)));
-            const real roll = atan2_(fma_(r02, s1, -(r12 * c1)), fma_(r11, c1, -(r01 * s1)));
-            e[3] = roll - tg[3 * ts]; e[4] = pitch - tg[4 * ts]; e[5] = yaw - tg[5 * ts];
-        }
-        if (mode == 0) {
-            real f = 0;
-            for (int r = 0; r < rows; ++r) { e[r] = -e[r]; f = fma_(e[r], e[r], f); }   // e = target - now
-            val_out[n] = f;
-            real *g = jac_out + (AOS ? n * nd : n);
-            for (int j = 0; j < nd; ++j) {
-                real acc = 0;
-                for (int r = 0; r < rows; ++r) acc = fma_(Jn[(size_t)(j * rows + r) * es], e[r], acc);
-                g[j * es] = real(-2) * acc;
+        real f = 0;
+        real *g = jac_out + (AOS ? n * nd : n);                       // mode 0: gradient (n_dof)
+        real *v = val_out + (AOS ? n * n_cons : n);                   // mode 1: values (n_cons)
+        real *jt = jac_out + (AOS ? n * (long long)(n_cons * nd) : n);   // mode 1: (n_dof, n_cons) column-major
+        if (mode == 0)
+            for (int j = 0; j < nd; ++j) g[j * es] = real(0);
+        int c0 = 0;
+        for (int l = 0; l < nl; ++l) {
+            const bool with_rot = (rot_mask >> l) & 1u;
+            const int rows = with_rot ? 6 : 3;
+            const real *Tn = T + (AOS ? n * (long long)(12 * nl) : n) + (size_t)(12 * l) * es;
+            const real *Jn = J + (AOS ? n * (long long)(rows_j * nd * nl) : n) + (size_t)(l * rows_j * nd) * es;
+            const real *tg = target + (target_per_config ? (AOS ? n * (long long)(6 * nl) : n) : 0) + (size_t)(6 * l) * ts;
+            real e[6];
+            #pragma unroll
+            for (int i = 0; i < 3; ++i) e[i] = Tn[(9 + i) * es] - tg[i * ts];          // p - p_t
+            if (with_rot) {   // rpy(T), transform.jl:45-48 (RotZYX): R[r][c] = T[c*3 + r]
+                const real r00 = Tn[0], r10 = Tn[es], r20 = Tn[2 * es], r01 = Tn[3 * es], r11 = Tn[4 * es],
+                           r21 = Tn[5 * es], r02 = Tn[6 * es], r12 = Tn[7 * es], r22 = Tn[8 * es];
+                const real yaw = atan2_(r10, r00);
+                real s1, c1;
+                sincos_(yaw, &s1, &c1);
+                const real pitch = atan2_(-r20, sqrt_(fma_(r21, r21, r22 * r22)));
+                const real roll = atan2_(fma_(r02, s1, -(r12 * c1)), fma_(r11, c1, -(r01 * s1)));
+                e[3] = roll - tg[3 * ts]; e[4] = pitch - tg[4 * ts]; e[5] = yaw - tg[5 * ts];
             }
-        } else {
-            real *v = val_out + (AOS ? n * rows : n);
-            for (int r = 0; r < rows; ++r) v[r * es] = e[r];
-            real *jt = jac_out + (AOS ? n * (long long)(rows * nd) : n);
-            for (int r = 0; r < rows; ++r)
-                for (int j = 0; j < nd; ++j) jt[(size_t)(r * nd + j) * es] = Jn[(size_t)(j * rows + r) * es];
+            if (mode == 0) {
+                for (int r = 0; r < rows; ++r) { e[r] = -e[r]; f = fma_(e[r], e[r], f); }   // e = target - now
+                for (int j = 0; j < nd; ++j) {
+                    real acc = 0;
+                    for (int r = 0; r < rows; ++r) acc = fma_(Jn[(size_t)(j * rows_j + r) * es], e[r], acc);
+                    g[j * es] = fma_(real(-2), acc, g[j * es]);
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) v[(size_t)(c0 + r) * es] = e[r];
+                for (int r = 0; r < rows; ++r)
+                    for (int j = 0; j < nd; ++j) jt[(size_t)((c0 + r) * nd + j) * es] = Jn[(size_t)(j * rows_j + r) * es];
+            }
+            c0 += rows;
         }
+        if (mode == 0) val_out[n] = f;
     }
 }
 

@@ -165,10 +165,17 @@ def untile32(x, N):
     return x.permute(0, nd - 1, *range(1, nd - 1)).reshape((x.shape[0] * 32,) + tuple(x.shape[1:-1]))[:N]
 
 
+def _into(buf, shape, dtype, dev):
+    """Caller-provided output storage (SoA / AoS only): must be a contiguous tensor of exactly the storage shape."""
+    if tuple(buf.shape) != tuple(shape) or buf.dtype != dtype or buf.device != dev or not buf.is_contiguous():
+        raise ValueError("output storage must be a contiguous %s tensor of shape %s on %s" % (dtype, tuple(shape), dev))
+    return buf
+
+
 def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac_links=None, with_rot=True,
              rpy_jac=False, keep_irrelevant=False, J_into=None, collision=False, with_grads=True,
              truncation_dist=np.inf, grad_mode=_lib.GRAD_FD, scratch_mode=_lib.SCRATCH_REFERENCE,
-             want_argmin=False, vals_offset=0.0, stream=None, launch_info=False):
+             want_argmin=False, vals_offset=0.0, stream=None, launch_info=False, vals_into=None, grads_into=None):
     """One ``kin_eval``.  Outputs are allocated in the layout of the call (default: the layout of Q) and
     returned as batch-first VIEWS: T (N, n_fk, 3, 4), J (N, n_jac, rows, cols), vals (N, S),
     grads (N, n_dof, S), argmin (N, S)."""
@@ -222,6 +229,9 @@ def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac
         n, rows = len(ids), (6 if with_rot else 3)
         if J_into is not None:
             J = J_into                       # storage tensor in the call's layout (get_jacobian! semantics)
+            if J.dtype != dt or J.device != dev or J.numel() != n * nd * rows * N:
+                raise ValueError("get_jacobian!: mat_out must be a %s tensor on %s holding %d x %d x %d values per "
+                                 "configuration (got %s, %s, %d values)" % (dt, dev, n, rows, nd, J.dtype, J.device, J.numel()))
         else:
             J = alloc((n, nd, rows, N), (N, n, nd, rows))
         c.n_jac_links, c.jac_links, c.J_out = n, _iptr(ids), J.data_ptr()
@@ -232,11 +242,12 @@ def evaluate(dm: DeviceModel, Q, q_layout, N, *, layout=None, fk_links=None, jac
             raise _lib.KinError("collision requested but the device model has no spheres / no boxes "
                                 "(add_coll_links and pass an SDF first)")
         S = dm.n_spheres
-        V = alloc((S, N), (N, S))
+        V = alloc((S, N), (N, S)) if vals_into is None else _into(vals_into, (S, N) if layout == _lib.SOA else (N, S), dt, dev)
         c.vals_out = V.data_ptr()
         pending.append(("vals", V, (1, 0), (0, 1)))
         if with_grads:
-            G = alloc((S, nd, N), (N, S, nd))
+            G = alloc((S, nd, N), (N, S, nd)) if grads_into is None else \
+                _into(grads_into, (S, nd, N) if layout == _lib.SOA else (N, S, nd), dt, dev)
             c.grads_out = G.data_ptr()
             pending.append(("grads", G, (2, 1, 0), (0, 2, 1)))
         if want_argmin:

@@ -14,28 +14,36 @@ from .mechanism import Mechanism, set_joint_angles
 from .transform import Transform, rpy, translation
 
 
-def _targets_tensor(target, N, dtype, device):
-    """target: Transform (shared), or (N, 6) [x, y, z, roll, pitch, yaw] array / tensor.
-    -> (tensor, per_config flag)"""
+def _targets_tensor(targets, N, dtype, device):
+    """targets: one entry per link -- a Transform (shared by the batch), a 6-vector, or an (N, 6) array / tensor of
+    [x, y, z, roll, pitch, yaw].  -> (tensor (6 nl,) or (N, 6 nl), per_config flag)"""
     import torch
-    if isinstance(target, Transform):
-        t = np.concatenate([translation(target), rpy(target)])
-        return torch.tensor(t, dtype=dtype, device=device), 0
-    t = target if isinstance(target, torch.Tensor) else torch.as_tensor(np.asarray(target, dtype=np.float64))
-    t = t.to(device=device, dtype=dtype)
-    if t.dim() == 1:
-        return t.contiguous(), 0
-    assert t.shape == (N, 6), "targets must be (N, 6): x, y, z, roll, pitch, yaw"
-    return t, 1
+    cols, per = [], 0
+    for target in targets:
+        if isinstance(target, Transform):
+            t = torch.tensor(np.concatenate([translation(target), rpy(target)]), dtype=dtype, device=device)
+        else:
+            t = target if isinstance(target, torch.Tensor) else torch.as_tensor(np.asarray(target, dtype=np.float64))
+            t = t.to(device=device, dtype=dtype)
+        if t.dim() == 2:
+            assert t.shape == (N, 6), "targets must be (N, 6): x, y, z, roll, pitch, yaw"
+            per = 1
+        cols.append(t)
+    if per:
+        cols = [t if t.dim() == 2 else t[None, :].expand(N, 6) for t in cols]
+        return torch.cat(cols, dim=1).contiguous(), 1
+    return torch.cat(cols).contiguous(), 0
 
 
-def _pose_residual(m: Mechanism, link, joints, target, with_rot, mode):
+def _pose_residual(m: Mechanism, links, joints, targets, with_rots, mode):
+    """All (link, target, with_rot) triples in ONE kin_pose_residual_multi call (two kernel launches)."""
     import torch
     _check_joints(m, joints)
     dm = device_model(m)
     Q, layout, N = current_q(m)
-    nd, rows = dm.n_dof, (6 if with_rot else 3)
-    tg, per = _targets_tensor(target, N, Q.dtype, Q.device)
+    nl, nd = len(links), dm.n_dof
+    n_cons = sum(6 if w else 3 for w in with_rots)
+    tg, per = _targets_tensor(targets, N, Q.dtype, Q.device)
     if per:   # bring the targets to the layout of q
         tg = tg.t().contiguous().t() if layout == _lib.SOA else tg.contiguous()
     soa = layout == _lib.SOA
@@ -44,13 +52,17 @@ def _pose_residual(m: Mechanism, link, joints, target, with_rot, mode):
         jac = torch.empty((nd, N) if soa else (N, nd), dtype=Q.dtype, device=Q.device)
         jac_view = jac.t() if soa else jac
     else:
-        val = torch.empty((rows, N) if soa else (N, rows), dtype=Q.dtype, device=Q.device)
-        jac = torch.empty((rows, nd, N) if soa else (N, rows, nd), dtype=Q.dtype, device=Q.device)
-        jac_view = jac.permute(2, 1, 0) if soa else jac.permute(0, 2, 1)          # (N, n_dof, dim)
+        val = torch.empty((n_cons, N) if soa else (N, n_cons), dtype=Q.dtype, device=Q.device)
+        jac = torch.empty((n_cons, nd, N) if soa else (N, n_cons, nd), dtype=Q.dtype, device=Q.device)
+        jac_view = jac.permute(2, 1, 0) if soa else jac.permute(0, 2, 1)          # (N, n_dof, n_cons)
         val = val.t() if soa else val
-    _lib.check(_lib.lib().kin_pose_residual(
-        dm.h, _lib.F32 if Q.dtype == torch.float32 else _lib.F64, layout, Q.data_ptr(), N, link.id, tg.data_ptr(), per,
-        int(with_rot), mode, val.data_ptr(), jac.data_ptr(), torch.cuda.current_stream(Q.device).cuda_stream))
+    ids = np.ascontiguousarray([l.id for l in links], dtype=np.int32)
+    rots = np.ascontiguousarray([1 if w else 0 for w in with_rots], dtype=np.int32)
+    ip = C.POINTER(C.c_int32)
+    _lib.check(_lib.lib().kin_pose_residual_multi(
+        dm.h, _lib.F32 if Q.dtype == torch.float32 else _lib.F64, layout, Q.data_ptr(), N, nl, ids.ctypes.data_as(ip),
+        rots.ctypes.data_as(ip), tg.data_ptr(), per, mode, val.data_ptr(), jac.data_ptr(),
+        torch.cuda.current_stream(Q.device).cuda_stream))
     return val, jac_view
 
 
@@ -58,7 +70,7 @@ def ik_objective(m: Mechanism, link, joints, target_pose, with_rot=True):
     """``f_objective`` of inverse_kinematics.jl:38-50 at the configuration(s) of the last set_joint_angles:
     f = sum(pose_diff^2), grad = -2 J' pose_diff with the Euler-rate Jacobian.
     single -> (float, ndarray (n_dof,)); batch -> tensors (N,), (N, n_dof)."""
-    f, g = _pose_residual(m, link, joints, target_pose, with_rot, _lib.POSE_IK_OBJECTIVE)
+    f, g = _pose_residual(m, [link], joints, [target_pose], [with_rot], _lib.POSE_IK_OBJECTIVE)
     if m._single:
         return float(f[0]), g[0].double().cpu().numpy()
     return f, g
@@ -126,3 +138,39 @@ def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=T
             break
     set_joint_angles(m, joints, q)
     return q, f_pose
+
+
+def inverse_kinematics(m: Mechanism, link, joints, target_pose, sscc=None, sdf=None, use_bistage=True, ftol=1e-5,
+                       with_rot=True, margin=0.02):
+    """``inverse_kinematics!`` (inverse_kinematics.jl:1-30) for ONE target, driven by SLSQP as in the reference.
+    The reference calls NLopt's LD_SLSQP; NLopt is not installed here, scipy's SLSQP (the same Kraft routine, which
+    the reference itself uses as its SCIPY back-end in planning.jl:388-394) drives the same callbacks: the objective
+    ``f_objective`` (:38-50, ``ik_objective``), the joint-limit bounds (:52-63) and, with ``sscc`` / ``sdf``, the HARD
+    inequality constraint ``dists - margin >= 0`` of ``IneqConst(sscc, joints, sdf, 1, 0.02)`` (:14-19) after the
+    collision-free warm start (:8-13).  Every evaluation runs on the GPU (N = 1).  Returns (q, scipy result); the
+    mechanism is left at the solution like the reference leaves it."""
+    from scipy.optimize import minimize
+    from .planning import IneqConst, scipynize
+    nb = 3 if m.with_base else 0
+    lo = [j.lower_limit for j in joints] + [-np.inf] * nb
+    hi = [j.upper_limit for j in joints] + [np.inf] * nb
+    bounds = [(a if np.isfinite(a) else None, b if np.isfinite(b) else None) for a, b in zip(lo, hi)]
+
+    def fun(x):
+        set_joint_angles(m, joints, np.asarray(x, dtype=np.float64))
+        return ik_objective(m, link, joints, target_pose, with_rot)
+
+    def solve(x0, constraints):
+        return minimize(fun, x0, jac=True, method="SLSQP", bounds=bounds, constraints=constraints,
+                        options={"ftol": ftol, "maxiter": 200})
+
+    x0 = np.array([m.angles[j.id - 1] for j in joints] + (list(m.base_pose) if m.with_base else []))
+    if sscc is None or sdf is None:
+        res = solve(x0, ())
+    else:
+        if use_bistage:
+            x0 = solve(x0, ()).x
+        g, dg = scipynize(IneqConst(sscc, joints, sdf, 1, margin))
+        res = solve(x0, [{"type": "ineq", "fun": g, "jac": dg}])
+    set_joint_angles(m, joints, res.x)
+    return res.x, res

@@ -52,7 +52,7 @@ class KinCall(C.Structure):
 EXPORTS = ["kin_last_error", "kin_abi_version", "kin_build_id", "kin_debug_build", "kin_model_create", "kin_model_destroy", "kin_model_set_spheres",
            "kin_model_set_boxes", "kin_model_n_dof", "kin_model_n_spheres", "kin_model_n_boxes", "kin_eval",
            "kin_eval_host", "kin_fk_links", "kin_fk_jacobian", "kin_collision", "kin_launch_count",
-           "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual", "kin_lm_step", "kin_lm_accept"]
+           "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual", "kin_pose_residual_multi", "kin_lm_step", "kin_lm_accept", "kin_probe_fp64"]
 
 
 def source_files():
@@ -157,8 +157,11 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kin_pose_residual.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kin_pose_residual_multi.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, _ip, _ip,
+                                              C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kin_lm_step.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 8
         L.kin_lm_accept.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 10
+        L.kin_probe_fp64.argtypes = [_dp, _dp, _dp]
         L.kin_program_dump.argtypes = [C.POINTER(KinModelDesc), _ip, C.c_int32, _ip, C.c_int32, C.c_int32, C.c_int32,
                                        _ip, C.c_int32, _ip, C.c_int32, _dp, C.c_int32]
         _LIB = L

@@ -420,6 +420,49 @@ def ineq_const(sscc, joints, sdf, xi, n_wp, margin, grad_mode=GRAD_FD, scratch_m
     return val, blocks.reshape(n_wp, S, n_dof).transpose(0, 2, 1).copy()
 
 
+def objective_matrix(n_wp, weights):
+    """planning.jl:7-20: A = kron(A_sub, Diagonal(weights.^2)), A_sub = sum of the 3x3 acceleration blocks
+    [1 -2 1; -2 4 -2; 1 -2 1] placed at rows/cols i-1:i+1 for i in 2:n_wp-1 (dense here)."""
+    acc_block = np.array([[1.0, -2.0, 1.0], [-2.0, 4.0, -2.0], [1.0, -2.0, 1.0]])
+    A_sub = np.zeros((n_wp, n_wp))
+    for i in range(2, n_wp):                       # Julia 2:n_wp-1, 1-based
+        A_sub[i - 2:i + 1, i - 2:i + 1] += acc_block
+    return np.kron(A_sub, np.diag(np.asarray(weights, dtype=np.float64) ** 2))
+
+
+def objective(A, xi):
+    """planning.jl:22-28 -> (val, grad) = (xi' A xi, 2 A xi)."""
+    tmp = A @ xi
+    return float(xi @ tmp), 2.0 * tmp
+
+
+def eq_const(m, joints, xi, n_wp, cons_arr):
+    """planning.jl:162-176 with the partial constraints of :72-138.  cons_arr: list of
+    ("config", idx_wp, q_const) | ("pose", idx_wp, [links], [targets 4x4], [with_rots]); idx_wp is 1-based.
+    -> (val_vec[n_cons], jac_mat (n_dof n_wp, n_cons))."""
+    n_dof = len(joints) + m.n_dof_extra
+    X = np.asarray(xi, dtype=np.float64).reshape(n_wp, n_dof)      # xi_reshaped[:, idx_wp] of the reference
+    n_cons = sum(n_dof if c[0] == "config" else sum(6 if w else 3 for w in c[4]) for c in cons_arr)
+    val_vec, jac_mat = np.zeros(n_cons), np.zeros((n_dof * n_wp, n_cons))
+    i_end = 0
+    for c in cons_arr:
+        idx_wp = c[1]
+        q = X[idx_wp - 1]
+        j0 = (idx_wp - 1) * n_dof
+        if c[0] == "config":                        # planning.jl:83-88
+            i_start, i_end = i_end, i_end + n_dof
+            jac_mat[j0:j0 + n_dof, i_start:i_end] = -np.eye(n_dof)
+            val_vec[i_start:i_end] = np.asarray(c[2]) - q
+        else:                                       # planning.jl:114-138
+            for link, target, with_rot in zip(c[2], c[3], c[4]):
+                dim = 6 if with_rot else 3
+                i_start, i_end = i_end, i_end + dim
+                v, jt = pose_constraint(m, link, joints, q, target, with_rot)
+                val_vec[i_start:i_end] = v
+                jac_mat[j0:j0 + n_dof, i_start:i_end] = jt
+    return val_vec, jac_mat
+
+
 # --------------------------------------------------------------------------
 # batch drivers: q is (N, n_dof) C-contiguous
 # --------------------------------------------------------------------------

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from kinematics_jl_b200.planning import gather_stacked, shard_range
+from kinematics_jl_b200.planning import gather_packed, gather_stacked, shard_range
 
 
 def test_shard_ranges_tile_the_batch():
@@ -30,6 +30,13 @@ def _worker(rank, world, port, out):
     grads = torch.rand((P, n_wp, n_dof, n_coll), generator=g, dtype=torch.float64)
     v_all, g_all = gather_stacked(vals[a:b], grads[a:b])
     ok = torch.equal(v_all, vals) and torch.equal(g_all, grads)
+    # the packed form: one SoA slab [vals rows | grads rows] per rank, ONE collective, views of the gathered slab
+    Pl = b - a
+    slab = torch.cat([vals[a:b].permute(2, 0, 1).reshape(n_coll, Pl * n_wp),
+                      grads[a:b].permute(3, 2, 0, 1).reshape(n_coll * n_dof, Pl * n_wp)]).contiguous()
+    v_pk, g_pk = gather_packed(slab, n_wp, n_dof, n_coll)
+    ok = ok and v_pk.shape == (world, Pl, n_wp, n_coll) and g_pk.shape == (world, Pl, n_wp, n_dof, n_coll)
+    ok = ok and torch.equal(v_pk.reshape(P, n_wp, n_coll), vals) and torch.equal(g_pk.reshape(P, n_wp, n_dof, n_coll), grads)
     t = torch.tensor([1.0 + rank])                      # max-over-ranks reduction used by bench.py
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out[rank] = bool(ok) and float(t) == float(world)

@@ -163,3 +163,206 @@ def test_batched_collision_aware_ik():
     assert f(c0) < 90.0                      # the scenario does exercise the constraint
     assert f(c1) > 99.0
     assert f(r1 & c1) > 55.0
+
+
+# ------------------------------------------------------------------------------------------------
+# PoseConstraint with several (link, target, with_rot) triples in ONE library call; EqConst stacking
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("with_base", [False, True])
+def test_pose_constraint_multi_link_one_call_and_eq_const(with_base):
+    """planning.jl:124-137 loops over (link, target, with_rot); here it is one kin_pose_residual_multi call
+    (two kernel launches whatever the number of links); EqConst (planning.jl:140-176) places the rows."""
+    m, joints, _ = scenes.product_fetch(with_base)
+    mo, jo, _ = scenes.oracle_fetch(with_base)
+    names, rots = ["gripper_link", "elbow_flex_link", "wrist_roll_link"], [True, False, True]
+    links, links_o = [K.find_link(m, n) for n in names], [R.find_link(mo, n) for n in names]
+    Tts = [target_T([0.3, -0.4, 1.2], [0.2, -0.1, 0.4]), target_T([0.1, 0.2, 0.9], [0, 0, 0]), target_T([0.5, 0.1, 1.0], [-0.3, 0.2, 0.1])]
+    nd = 8 + (3 if with_base else 0)
+    n_cons = 6 + 3 + 6
+    q = scenes.random_configs(jo, 200, with_base, seed=91)
+    lib = K.load_library()
+    for Q in (dev(q), dev(q).t().contiguous().t()):                 # AoS and SoA
+        K.set_joint_angles(m, joints, Q)
+        K.pose_constraint(m, links, joints, [K.Transform(T) for T in Tts], rots)      # builds the program
+        n0 = lib.kin_launch_count()
+        v, jt = K.pose_constraint(m, links, joints, [K.Transform(T) for T in Tts], rots)
+        assert lib.kin_launch_count() - n0 == 2                       # kin_eval + residual kernel, not 2 per link
+        assert v.shape == (200, n_cons) and jt.shape == (200, nd, n_cons)
+        v, jt = v.cpu().numpy(), jt.cpu().numpy()
+        for n in range(0, 200, 11):
+            c0 = 0
+            for lo_, T, w in zip(links_o, Tts, rots):
+                vo, jto = R.pose_constraint(mo, lo_, jo, q[n], T, w)
+                dim = 6 if w else 3
+                np.testing.assert_allclose(v[n, c0:c0 + dim], vo, rtol=1e-12, atol=1e-12)
+                np.testing.assert_allclose(jt[n, :, c0:c0 + dim], jto, rtol=1e-11, atol=1e-11)
+                c0 += dim
+    # EqConst: start / goal configuration rows + a pose constraint at waypoint 4, reference-style flat xi
+    n_wp = 7
+    xi = scenes.random_configs(jo, n_wp, with_base, seed=92).reshape(-1)
+    qs, qg = xi[:nd] + 0.01, xi[-nd:] - 0.02
+    H = K.EqConst(n_wp, [K.ConfigurationConstraint(1, nd, qs), K.ConfigurationConstraint(n_wp, nd, qg),
+                         K.PoseConstraint(4, nd, links, [K.Transform(T) for T in Tts], rots, m, joints)])
+    val, jac = H(xi)
+    val_o, jac_o = R.eq_const(mo, jo, xi, n_wp, [("config", 1, qs), ("config", n_wp, qg), ("pose", 4, links_o, Tts, rots)])
+    assert jac.shape == (nd * n_wp, 2 * nd + n_cons)
+    np.testing.assert_allclose(val, val_o, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(jac, jac_o, rtol=1e-11, atol=1e-11)
+    assert np.array_equal(jac != 0, jac_o != 0)                       # same sparsity: rows of waypoint 4 only
+    h, dh = K.scipynize(H)
+    assert np.array_equal(h(xi), val) and np.array_equal(dh(xi), jac.T)
+    # batched problems: (P, n_wp, n_dof) tensor -> values + row blocks, expanded to the dense matrices
+    Xb = dev(scenes.random_configs(jo, 5 * n_wp, with_base, seed=93).reshape(5, n_wp, nd))
+    Hb = K.EqConst(n_wp, [K.ConfigurationConstraint(1, nd, dev(qs)), K.ConfigurationConstraint(n_wp, nd, dev(qg)),
+                          K.PoseConstraint(4, nd, links, [K.Transform(T) for T in Tts], rots, m, joints)])
+    vb, blocks = Hb(Xb)
+    dense = Hb.dense_batch(blocks)
+    for p in range(5):
+        vo, jo_ = R.eq_const(mo, jo, Xb[p].reshape(-1).cpu().numpy(), n_wp,
+                             [("config", 1, qs), ("config", n_wp, qg), ("pose", 4, links_o, Tts, rots)])
+        np.testing.assert_allclose(vb[p].cpu().numpy(), vo, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(dense[p].cpu().numpy(), jo_, rtol=1e-11, atol=1e-11)
+
+
+# ------------------------------------------------------------------------------------------------
+# config 5 at its real size: 4096 problems x 64 waypoints, margin 0.03, fridge SDF
+# ------------------------------------------------------------------------------------------------
+def test_ineq_const_config5_full_size():
+    """BASELINE.json configs[4]: the IneqConst stack (planning.jl:55-68, truncation = margin + 0.05) of 4096
+    straight-line problems x 64 waypoints in one batched call; 32 whole problems (2048 waypoints) sampled
+    across the batch are checked against the oracle, the rest through size-independent properties."""
+    m, joints, sscc = scenes.product_fetch(False)
+    mo, jo, so = scenes.oracle_fetch(False)
+    import scene_fetch
+    sdf, sdf_o = scene_fetch.product_fridge_sdf(), scenes.oracle_fridge_sdf()
+    P_, n_wp, margin, nd, S = 4096, 64, 0.03, 8, 16
+    qs = dev(scenes.random_configs(jo, P_, False, seed=101))
+    qg = dev(scenes.random_configs(jo, P_, False, seed=102))
+    X = K.create_straight_trajectory(qs, qg, n_wp)
+    G = K.IneqConst(sscc, joints, sdf, n_wp, margin)
+    V, B = G(X)
+    assert V.shape == (P_, n_wp, S) and B.shape == (P_, n_wp, nd, S)
+    # properties over all 262 144 waypoints: truncated entries are exactly (margin + 0.05) - margin with zero
+    # gradient blocks (collision.jl:84-86), nothing exceeds the truncation value, everything is finite
+    trunc_val = (margin + 0.05) - margin
+    assert bool(torch.isfinite(V).all()) and bool(torch.isfinite(B).all())
+    assert float(V.max()) <= trunc_val
+    is_tr = V == trunc_val
+    assert 0.05 < float(is_tr.double().mean()) < 0.999          # the scene exercises both branches
+    assert float(B.permute(0, 1, 3, 2)[is_tr].abs().max()) == 0.0
+    # waypoint 1 / n_wp of every problem are the start / goal configurations
+    K.set_joint_angles(m, joints, qs)
+    d0 = K.compute_coll_dists(sscc, joints, sdf)
+    np.testing.assert_allclose(torch.minimum(d0, torch.tensor(margin + 0.05, device="cuda")).sub(margin).cpu().numpy(),
+                               V[:, 0].cpu().numpy(), rtol=1e-12, atol=1e-12)
+    # 32 problems (2048 waypoints) against the oracle
+    idx = np.linspace(0, P_ - 1, 32).astype(int)
+    n_tr = 0
+    for p in idx:
+        vo, bo = R.ineq_const(so, jo, sdf_o, X[p].reshape(-1).cpu().numpy(), n_wp, margin)
+        np.testing.assert_allclose(V[p].reshape(-1).cpu().numpy(), vo, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(B[p].cpu().numpy(), bo, rtol=0, atol=1e-7)
+        assert np.array_equal(V[p].reshape(-1).cpu().numpy() == trunc_val, vo == trunc_val)
+        n_tr += int((vo == trunc_val).sum())
+    assert 0 < n_tr < 32 * n_wp * S
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's solver-level callers with the solver that exists here (scipy SLSQP = planning.jl:388-394)
+# ------------------------------------------------------------------------------------------------
+def _oracle_plan(so, jo, sdf_o, q_start, q_goal, n_wp, margin, ftol_abs):
+    """plan_trajectory's SCIPY back-end (planning.jl:388-394) driven by the ORACLE's evaluations."""
+    from scipy.optimize import minimize
+    nd = len(q_start)
+    A = R.objective_matrix(n_wp, np.ones(nd))
+    lo = [j.lower for j in jo] + [-np.inf] * (nd - len(jo))
+    hi = [j.upper for j in jo] + [np.inf] * (nd - len(jo))
+    bounds = [(a if np.isfinite(a) else None, b if np.isfinite(b) else None) for a, b in zip(lo, hi)] * n_wp
+    S = len(so.sphere_links)
+
+    def g(xi):
+        return R.ineq_const(so, jo, sdf_o, xi, n_wp, margin)[0]
+
+    def dg(xi):
+        blocks = R.ineq_const(so, jo, sdf_o, xi, n_wp, margin)[1]
+        J = np.zeros((nd * n_wp, S * n_wp))
+        for i in range(n_wp):
+            J[i * nd:(i + 1) * nd, i * S:(i + 1) * S] = blocks[i]
+        return J.T
+    cons = [("config", 1, q_start), ("config", n_wp, q_goal)]
+    xi0 = np.concatenate([q_start + (q_goal - q_start) / (n_wp - 1) * i for i in range(n_wp)])
+    return minimize(lambda x: R.objective(A, x)[0], xi0, jac=lambda x: R.objective(A, x)[1], method="SLSQP", bounds=bounds,
+                    options={"ftol": ftol_abs, "maxiter": 200},
+                    constraints=[{"type": "ineq", "fun": g, "jac": dg},
+                                 {"type": "eq", "fun": lambda x: R.eq_const(so.mech, jo, x, n_wp, cons)[0],
+                                  "jac": lambda x: R.eq_const(so.mech, jo, x, n_wp, cons)[1].T}])
+
+
+@pytest.mark.parametrize("with_base", [False, True])
+def test_inverse_kinematics_and_plan_trajectory_slsqp(with_base):
+    """test/test_inverse_kinematics.jl:16-23 and test/test_planning.jl:3-46 with SLSQP (scipy: the reference's own
+    SCIPY back-end; NLopt is not installed): IK reaches (0.3, -0.4, 1.2) within 1e-3, the planned trajectory keeps
+    every sphere of every waypoint above -1e-2, and agrees with the same solver driven by the oracle."""
+    m, joints, sscc = scenes.product_fetch(with_base)
+    mo, jo, so = scenes.oracle_fetch(with_base)
+    nd = 8 + (3 if with_base else 0)
+    link = K.find_link(m, "gripper_link")
+    target = K.Transform(np.array([0.3, -0.4, 1.2]))
+    q_start = np.zeros(nd)
+    K.set_joint_angles(m, joints, q_start)
+    q_goal, res = K.inverse_kinematics(m, link, joints, target, with_rot=True)
+    assert res.success
+    K.set_joint_angles(m, joints, q_goal)
+    pose = K.get_transform(m, link)
+    np.testing.assert_allclose(K.translation(pose), [0.3, -0.4, 1.2], atol=1e-3)
+    np.testing.assert_allclose(K.rpy(pose), [0, 0, 0], atol=1e-3)
+    # planning scenario of test_planning.jl: thin box, n_wp = 10, goal from a position-only IK
+    K.set_joint_angles(m, joints, q_start)
+    q_goal, res = K.inverse_kinematics(m, link, joints, target, with_rot=False)
+    assert res.success
+    pose_b = np.eye(4)
+    pose_b[:3, 3] = [0.4, -0.25, 0.7]
+    box, box_o = K.BoxSDF(K.Transform(pose_b), [0.05, 0.05, 0.5]), R.BoxSDF(pose_b, [0.05, 0.05, 0.5])
+    n_wp = 10
+    q_seq, ret = K.plan_trajectory(sscc, joints, box, q_start, q_goal, n_wp, ftol_abs=1e-5, solver="SCIPY")
+    assert ret.success, ret.message
+    K.set_joint_angles(m, joints, dev(q_seq))
+    d = K.compute_coll_dists(sscc, joints, box).cpu().numpy()
+    assert d.shape == (n_wp, 16) and np.all(d > -1e-2)              # test_planning.jl:41-45
+    np.testing.assert_allclose(q_seq[0], q_start, atol=1e-6)
+    np.testing.assert_allclose(q_seq[-1], q_goal, atol=1e-6)
+    ret_o = _oracle_plan(so, jo, box_o, q_start, q_goal, n_wp, 0.02, 1e-5)
+    assert ret_o.success
+    np.testing.assert_allclose(ret.fun, ret_o.fun, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(q_seq.reshape(-1), ret_o.x, atol=1e-3)
+    with pytest.raises(K.KinError):
+        K.plan_trajectory(sscc, joints, box, q_start, q_goal, n_wp, solver="NLOPT")
+
+
+def test_collision_aware_inverse_kinematics_slsqp_hard_constraint():
+    """inverse_kinematics.jl:1-21: the two-stage solve with the HARD constraint dists - 0.02 >= 0 (tol 1e-8 in the
+    reference).  A target behind the thin box of test_planning.jl: the unconstrained solution runs the arm
+    through it, the constrained one keeps every sphere >= margin (to the solver's tolerance)."""
+    m, joints, sscc = scenes.product_fetch(False)
+    link = K.find_link(m, "gripper_link")
+    pose_b = np.eye(4)
+    pose_b[:3, 3] = [0.4, -0.25, 0.8]
+    box = K.BoxSDF(K.Transform(pose_b), [0.05, 0.05, 0.5])
+    q0 = np.array([0.2, 0, 0, 0, 0.5, 0, 0.5, 0])
+    found = 0
+    rng = np.random.default_rng(7)
+    for _ in range(12):
+        tgt = K.Transform(np.array([rng.uniform(0.55, 0.8), rng.uniform(-0.3, 0.0), rng.uniform(0.7, 1.1)]))
+        K.set_joint_angles(m, joints, q0)
+        q_free, r_free = K.inverse_kinematics(m, link, joints, tgt, with_rot=False)
+        d_free = K.compute_coll_dists(sscc, joints, box)
+        if d_free.min() > 0.02:
+            continue
+        K.set_joint_angles(m, joints, q0)
+        q_c, r_c = K.inverse_kinematics(m, link, joints, tgt, sscc=sscc, sdf=box, with_rot=False)
+        d_c = K.compute_coll_dists(sscc, joints, box)
+        if r_c.success:
+            found += 1
+            assert d_c.min() >= 0.02 - 1e-6                       # the constraint holds at the solution
+            np.testing.assert_allclose(K.translation(K.get_transform(m, link)), K.translation(tgt), atol=2e-3)
+    assert found >= 2

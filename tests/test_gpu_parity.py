@@ -475,20 +475,38 @@ def test_stale_scratch_differs_from_clean_as_in_the_reference():
 # FP32 mode (1e-5)
 # ------------------------------------------------------------------------------------------------
 def test_fp32_mode():
+    """north_star: "within a stated 1e-5 in the optional FP32 mode".  Transforms, Jacobians and distances are held
+    to 1e-5 absolute.  The collision gradient is g = n' J with n the unit normal of the argmin box; n has a
+    condition number of 1 / d (d = centre-to-box distance), so FP32 rounding of the sphere centre (~1e-6 after the
+    9-joint chain) moves it by ~1e-6 / d, and a different argmin box or active-face set flips it altogether.
+    Stated bound, asserted below: the argmin box agrees with the FP64 oracle on >= 99.5 % of the spheres; where it
+    agrees and the sphere is at least 0.1 m from the surface the gradient is within 1e-5; closer in, within
+    1e-5 + 2e-6 / d (on >= 99.9 % -- the rest sit within float rounding of a face / edge switch of the same box)."""
     m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
-    q = scenes.random_configs(jo, 512, False, seed=31)
+    q = scenes.random_configs(jo, 4096, False, seed=31)
     K.set_joint_angles(m, joints, dev(q, torch.float32))
     T = K.get_transform(m, m.links)
     assert T.dtype == torch.float32
     np.testing.assert_allclose(host(T), R.batch_fk(mo, jo, q, mo.links[:25] + mo.links[25:])[:, :, :3, :], rtol=0, atol=1e-5)
     J = K.get_jacobian(m, K.find_link(m, "gripper_link"), joints, True)
     np.testing.assert_allclose(host(J), R.batch_jacobian(mo, jo, q, [R.find_link(mo, "gripper_link")], True)[:, 0], rtol=0, atol=1e-5)
-    vals, grads = K.compute_coll_dists_and_grads(sscc, joints, sdf, grad_mode=K.GRAD_ANALYTIC, scratch_mode=K.SCRATCH_CLEAN)
-    v_ref, g_ref, _ = R.batch_collision(so, jo, sdf_o, q, np.inf, R.GRAD_ANALYTIC, R.SCRATCH_CLEAN)
+    vals, grads, am = K.compute_coll_dists_and_grads(sscc, joints, sdf, grad_mode=K.GRAD_ANALYTIC, scratch_mode=K.SCRATCH_CLEAN,
+                                                     return_argmin=True)
+    assert vals.dtype == torch.float32 and grads.dtype == torch.float32
+    v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, q, np.inf, R.GRAD_ANALYTIC, R.SCRATCH_CLEAN)
     np.testing.assert_allclose(host(vals), v_ref, rtol=0, atol=1e-5)
-    # a box-face switch within float rounding flips the analytic gradient: compare where the argmin agrees
-    ok = np.abs(host(grads) - g_ref.transpose(0, 2, 1)).max(axis=1) < 1e-4
-    assert ok.mean() > 0.995
+    same = am.cpu().numpy() == am_ref                                   # (N, S)
+    print("fp32: argmin box agrees on %.3f %% of %d spheres" % (100 * same.mean(), same.size))
+    assert same.mean() >= 0.995
+    radii = np.array(so.sphere_radii)
+    d = np.abs(v_ref + radii[None, :])                                  # |sdf(centre)|: distance of the centre to the surface
+    err = np.abs(host(grads) - g_ref.transpose(0, 2, 1)).max(axis=1)    # (N, S): worst column per sphere
+    far = same & (d >= 0.1)
+    print("fp32 gradient: max err %.2e on %d far spheres; near spheres: %.4f %% within 1e-5 + 2e-6/d"
+          % (err[far].max(), far.sum(), 100 * (err[same & ~far] <= 1e-5 + 2e-6 / np.maximum(d[same & ~far], 1e-6)).mean()))
+    assert err[far].max() <= 1e-5
+    near = same & ~far
+    assert (err[near] <= 1e-5 + 2e-6 / np.maximum(d[near], 1e-6)).mean() >= 0.999
 
 
 # ------------------------------------------------------------------------------------------------
@@ -503,6 +521,79 @@ def _fused_call(dm, n, qptr, layout, fk, jac, T, J, V, G, A):
     c.truncation_dist = float("inf")
     c.vals_out, c.grads_out, c.argmin_out = V, G, A
     return c
+
+
+def test_host_entry_point_tiled_layout_ragged_sizes():
+    """kin_eval_host with KIN_LAYOUT_TILED32 and N % 32 != 0, below and above one staging chunk: the staging carves
+    are sized for whole tiles (host buffers hold roundup(N, 32) records)."""
+    from kinematics_jl_b200.device import tile32, untile32
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
+    fk = np.arange(1, 26, dtype=np.int32)
+    jac = np.array([K.find_link(m, "gripper_link").id], dtype=np.int32)
+    nl, S, nd = 25, 16, 8
+    for N in (1, 33, 1000, 65536 + 77):
+        q = scenes.random_configs(jo, N, False, seed=43)
+        K.set_joint_angles(m, joints, dev(q[:1]))
+        K.compute_coll_dists(sscc, joints, sdf)
+        dm = device_model(m)
+        NT = (N + 31) // 32
+        qt = tile32(torch.as_tensor(q)).numpy()                          # (NT, nd, 32), zero padded
+        shapes = {"T": nl * 12, "J": 6 * nd, "V": S, "G": nd * S}
+        guard = 4096                                                     # canary behind every host buffer
+        bufs = {k: np.full(NT * c * 32 + guard, -7.0) for k, c in shapes.items()}
+        amb = np.full(NT * S * 32 + guard, -7, dtype=np.int32)
+        c = _fused_call(dm, N, qt.ctypes.data, L.TILED32, fk, jac, bufs["T"].ctypes.data, bufs["J"].ctypes.data,
+                        bufs["V"].ctypes.data, bufs["G"].ctypes.data, amb.ctypes.data)
+        L.check(L.lib().kin_eval_host(dm.h, C.byref(c)))
+        for k, cnt in shapes.items():
+            assert np.all(bufs[k][NT * cnt * 32:] == -7.0), k             # nothing written past the padded tiles
+        assert np.all(amb[NT * S * 32:] == -7)
+        un = lambda a, cnt: untile32(torch.as_tensor(a[:NT * cnt * 32].reshape(NT, cnt, 32)), N).numpy()
+        sub = slice(max(0, N - 300), N)                                  # the ragged tail
+        T = un(bufs["T"], nl * 12)[sub].reshape(-1, nl, 4, 3).transpose(0, 1, 3, 2)
+        np.testing.assert_allclose(T, R.batch_fk(mo, jo, q[sub], mo.links[:25])[:, :, :3, :], rtol=RTOL, atol=ATOL)
+        v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, q[sub])
+        np.testing.assert_allclose(un(bufs["V"], S)[sub], v_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(un(bufs["G"], nd * S)[sub].reshape(-1, S, nd), g_ref, rtol=0, atol=1e-7)
+        assert np.array_equal(un(amb, S)[sub], am_ref)
+
+
+def test_moving_obstacle_updates_boxes_in_place():
+    """kin_model_set_boxes with an unchanged box count rewrites the box rows of the compiled programs in place
+    (sdf.jl:14-32: the attached SDF follows its mechanism); results follow the obstacle and match the oracle."""
+    m, joints, sscc = scenes.product_fetch(False)
+    mo, jo, so = scenes.oracle_fetch(False)
+    q = scenes.random_configs(jo, 500, False, seed=44)
+    K.set_joint_angles(m, joints, dev(q))
+    for k, xyz in enumerate(([1.0, 0.0, 0.8], [0.7, 0.2, 0.9], [0.5, -0.3, 0.6])):
+        pose = target_pose(xyz, 0.3 * k)
+        box, box_o = K.BoxSDF(K.Transform(pose), [0.3, 0.2, 0.4]), R.BoxSDF(pose, [0.3, 0.2, 0.4])
+        vals, grads, am = K.compute_coll_dists_and_grads(sscc, joints, box, return_argmin=True)
+        v_ref, g_ref, am_ref = R.batch_collision(so, jo, box_o, q)
+        np.testing.assert_allclose(host(vals), v_ref, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(host(grads), g_ref.transpose(0, 2, 1), rtol=0, atol=1e-7)
+
+
+def target_pose(xyz, yaw):
+    P = np.eye(4)
+    P[:3, :3] = [[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]]
+    P[:3, 3] = xyz
+    return P
+
+
+def test_debug_build_bounds_checks_pass():
+    """The -DKIN_DEBUG library (table / scratch indices range-checked inside the kernels, the analogue of the
+    reference's @debugassert with debugging() = true, test/runtests.jl:8) runs the smoke scene without tripping."""
+    import subprocess
+    import sys
+    if not os.path.exists(L.SO_PATH_DEBUG):
+        pytest.skip("libkin_b200_debug.so not built")
+    code = ("import sys; sys.path.insert(0, %r); import __graft_entry__ as g; "
+            "from kinematics_jl_b200 import lib as L; assert L.lib().kin_debug_build() == 1; g.smoke()") % os.path.dirname(DATA)
+    env = dict(os.environ, KIN_DEBUG="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "smoke ok" in out.stdout and "KIN_DEBUG assertion failed" not in out.stdout + out.stderr
 
 
 @pytest.mark.parametrize("layout", [L.AOS, L.SOA])

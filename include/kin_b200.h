@@ -263,6 +263,21 @@ KIN_API int64_t kin_launch_count(void);
 KIN_API int kin_query_launch(KinModel *model, const KinCall *call, int32_t *regs, int32_t *smem_bytes,
                      int32_t *block, int32_t *grid);
 
+/* Model-specialised kernels.  For batches of >= 32768 configurations (KIN_JIT_MIN_BATCH) in the SoA / tiled layouts
+ * the library generates the source of a kernel for this model and these requested outputs (csrc/kin_codegen.cpp: the
+ * chain walk becomes straight-line code with the model's constants folded in; results are bit-identical to the
+ * interpreting kernels up to the sign of a zero) and compiles it with NVRTC for sm_100a on first use (1-3 s, then
+ * cached in the model and on disk under KIN_JIT_CACHE_DIR, default /tmp/kin_b200_jit-<uid>).  libnvrtc is loaded with
+ * dlopen (KIN_NVRTC_PATH overrides the search); without it, or with KIN_DISABLE_JIT set, every call runs the
+ * ahead-of-time interpreting kernels.  kin_query_launch reports a NEGATIVE block size for a specialised kernel.
+ *   kin_jit_status   "ok: <library> (<version>)" or the reason NVRTC is unavailable
+ *   kin_jit_stats    kernels compiled / taken from the disk cache / launched / failed since load
+ *   kin_codegen_dump host-only: writes the generated source of the kernel `call` would run (its pointers are only
+ *                    tested for NULL) into out_dir; with compile != 0 also the NVRTC cubin + log.  No device needed. */
+KIN_API const char *kin_jit_status(void);
+KIN_API int kin_jit_stats(int64_t *compiles, int64_t *cache_hits, int64_t *launches, int64_t *failures);
+KIN_API int kin_codegen_dump(const KinModelDesc *desc, const KinCall *call, int32_t compile, const char *out_dir);
+
 /* FP64 peak of the current device, measured: 8 independent DFMA chains per thread, 8 x 256 threads per SM.  Returns
  * TFLOP/s (2 flops per DFMA), DFMA per clock per SM at the device's nominal maximum SM clock, and that clock.  This is
  * the denominator of the "FP64 pipe" fractions in DESIGN.md / profiles (SURVEY 6 asks for it). */

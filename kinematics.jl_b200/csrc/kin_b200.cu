@@ -17,11 +17,16 @@
 #include "kin_kernels.cuh"
 #include "kin_kernels_ws.cuh"
 #include "kin_model.hpp"
+#include "kin_codegen.hpp"
+#include "kin_jit.hpp"
+
+#include <chrono>
+#include <fstream>
 
 namespace {
 
 thread_local std::string g_err;
-std::atomic<long long> g_launches{0};
+std::atomic<long long> g_launches{0}, g_jit_compiles{0}, g_jit_cache_hits{0}, g_jit_launches{0}, g_jit_failures{0};
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -37,8 +42,21 @@ int fail_cuda(cudaError_t e, const char *what) {
         if (e__ != cudaSuccess) return fail_cuda(e__, #expr);   \
     } while (0)
 
+// One NVRTC-compiled, model-specialised kernel (kin_codegen.hpp) of a program, per option set.
+struct JitKernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kern = nullptr;
+    bool ok = false, from_cache = false;
+    int regs = 0, block = 0, occ = 0, slots = 0, smem_limit = 0;
+    double compile_ms = 0;
+    std::string log;
+    ~JitKernel() { if (lib) cudaLibraryUnload(lib); }
+};
+
 struct DeviceProgram {
     kin::Program prog;
+    std::mutex jit_mu;
+    std::map<std::string, std::shared_ptr<JitKernel>> jit;
     int32_t *d_int = nullptr;
     double *d_r64 = nullptr;
     float *d_r32 = nullptr;
@@ -281,7 +299,153 @@ int validate_call(const KinModel *m, const KinCall *c) {
     return KIN_OK;
 }
 
+// ---- model-specialised kernels (kin_codegen.hpp / kin_jit.hpp) ----
+constexpr long long kJitMinBatch = 32 * 1024;      // below this the compile is not worth it: interpreting kernels
+
+long long env_ll(const char *name, long long dflt) {
+    const char *e = std::getenv(name);
+    return e && *e ? std::atoll(e) : dflt;
+}
+
+kin::GenOptions gen_options(const KinCall *c, const DeviceProgram *dp) {
+    const kin::ProgHeader &h = dp->prog.h;
+    kin::GenOptions o;
+    o.precision = c->precision == KIN_F32 ? 1 : 0;
+    o.layout = c->layout;
+    o.want_T = c->T_out != nullptr && h.n_fk > 0;
+    o.want_J = c->J_out != nullptr && h.n_jac > 0;
+    o.coll = c->vals_out != nullptr && h.n_sph > 0;
+    o.with_rot = c->with_rot ? 1 : 0;
+    o.rpy_jac = (o.want_J && c->with_rot && c->rpy_jac) ? 1 : 0;
+    o.keep_irrelevant = (o.want_J && c->keep_irrelevant) ? 1 : 0;
+    o.want_grads = o.coll && c->grads_out != nullptr;
+    o.want_argmin = o.coll && c->argmin_out != nullptr;
+    o.stale = o.want_grads && c->scratch_mode == KIN_SCRATCH_REFERENCE;
+    o.ws = false;
+    // residency: the collision phase holds the joint frames in registers (up to 255 per thread: 2 x 128 threads per
+    // SM); the FK / Jacobian-only kernel needs far fewer
+    o.block = (int)env_ll("KIN_JIT_BLOCK", 128);
+    o.min_blocks = (int)env_ll("KIN_JIT_MINB", o.coll ? 2 : 3);
+    return o;
+}
+
+bool jit_wanted(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
+    (void)m;
+    if (std::getenv("KIN_DISABLE_JIT")) return false;
+    if (c->layout != KIN_LAYOUT_SOA && c->layout != KIN_LAYOUT_TILED32) return false;
+    if (c->vals_out && dp->prog.h.n_sph > 0 && dp->prog.h.n_dof > 16) return false;     // frames would not fit in registers
+    if (c->n < env_ll("KIN_JIT_MIN_BATCH", kJitMinBatch) && !std::getenv("KIN_FORCE_JIT")) return false;
+    return true;
+}
+
+std::string jit_main_source() {
+    return "#include \"kin_gen_config.h\"\n#include \"kin_device_math.cuh\"\n#include \"kin_gen_skeleton.cuh\"\n";
+}
+
+kin::JitHeaders jit_headers(const kin::GenSource &g) {
+    kin::JitHeaders hs;
+    std::string cfg = g.config;
+    cfg += "namespace kin { constexpr int BOX_REALS = " + std::to_string(kin::BOX_REALS) + "; }\n";
+    hs.emplace_back("kin_gen_config.h", cfg);
+    hs.emplace_back("kin_device_math.cuh", kin::embedded_device_math());
+    hs.emplace_back("kin_gen_skeleton.cuh", kin::embedded_gen_skeleton());
+    hs.emplace_back("kin_gen_phase1.inc", g.phase1);
+    hs.emplace_back("kin_gen_phase2.inc", g.phase2);
+    return hs;
+}
+
+// per-thread scratch slots of the generated kernel (kin_gen_skeleton.cuh)
+int jit_slots(const kin::GenOptions &o, const kin::ProgHeader &h) {
+    if (!o.coll) return 0;
+    return 3 * h.n_sph + (o.stale ? 3 * h.n_dof : 0) + 2 * kin::SPH_GROUP;
+}
+
+size_t jit_smem(const kin::GenOptions &o, const kin::ProgHeader &h, const JitKernel &k) {
+    if (!o.coll) return 0;
+    const size_t rs = o.precision ? sizeof(float) : sizeof(double);
+    const size_t tab = ((size_t)h.n_box * kin::BOX_REALS + h.n_sph + 1) & ~size_t(1);
+    return rs * (tab + (size_t)k.slots * k.block);
+}
+
+// Returns the compiled kernel for this call's option set (compiling it on first use), or null when specialisation
+// is unavailable for it (NVRTC missing, compile error, does not fit): the caller then uses the interpreting kernels.
+std::shared_ptr<JitKernel> get_jit(KinModel *m, const KinCall *c, DeviceProgram *dp) {
+    const kin::GenOptions o = gen_options(c, dp);
+    const std::string key = o.key();
+    std::lock_guard<std::mutex> lock(dp->jit_mu);
+    auto it = dp->jit.find(key);
+    if (it != dp->jit.end()) return it->second->ok ? it->second : nullptr;
+    auto k = std::make_shared<JitKernel>();
+    dp->jit[key] = k;
+    const auto t0 = std::chrono::steady_clock::now();
+    kin::GenSource g;
+    std::string err;
+    if (!kin::generate_source(dp->prog, o, g, err)) { k->log = "codegen: " + err; g_jit_failures.fetch_add(1); return nullptr; }
+    std::vector<char> cubin;
+    bool cached = false;
+    if (!kin::jit_compile(jit_main_source(), jit_headers(g), "sm_100a", cubin, k->log, &cached)) {
+        g_jit_failures.fetch_add(1);
+        if (std::getenv("KIN_JIT_VERBOSE")) std::fprintf(stderr, "[libkin_b200] specialisation failed, using the interpreting kernel: %s\n", k->log.c_str());
+        return nullptr;
+    }
+    k->from_cache = cached;
+    (cached ? g_jit_cache_hits : g_jit_compiles).fetch_add(1);
+    cudaError_t e = cudaLibraryLoadData(&k->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kern, k->lib, "kin_gen_kernel");
+    cudaFuncAttributes fa;
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, (const void *)k->kern);
+    if (e != cudaSuccess) {
+        k->log = std::string("loading the compiled kernel: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        g_jit_failures.fetch_add(1);
+        return nullptr;
+    }
+    k->regs = fa.numRegs;
+    k->block = o.block;
+    k->slots = jit_slots(o, dp->prog.h);
+    const size_t smem = jit_smem(o, dp->prog.h, *k);
+    if (smem > (size_t)m->dev_smem) { k->log = "scratch does not fit in shared memory"; g_jit_failures.fetch_add(1); return nullptr; }
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute((const void *)k->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m->dev_smem);
+        if (e != cudaSuccess) { k->log = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); cudaGetLastError(); g_jit_failures.fetch_add(1); return nullptr; }
+    }
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k->occ, (const void *)k->kern, k->block, smem);
+    if (e != cudaSuccess || k->occ < 1) { k->log = "occupancy query failed"; cudaGetLastError(); g_jit_failures.fetch_add(1); return nullptr; }
+    k->compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (std::getenv("KIN_JIT_VERBOSE"))
+        std::fprintf(stderr, "[libkin_b200] specialised kernel %s: %d registers, %zu B shared, %d CTAs/SM, %.0f ms%s\n", key.c_str(), k->regs, smem,
+                     k->occ, k->compile_ms, cached ? " (disk cache)" : "");
+    k->ok = true;
+    return k;
+}
+
+int launch_jit(KinModel *m, const KinCall *c, DeviceProgram *dp, JitKernel &k, cudaStream_t stream) {
+    const kin::GenOptions o = gen_options(c, dp);
+    const kin::ProgHeader &h = dp->prog.h;
+    kin::GenArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.q = c->q;
+    a.T_out = c->T_out; a.J_out = c->J_out; a.vals_out = c->vals_out; a.grads_out = c->grads_out; a.argmin_out = c->argmin_out;
+    a.boxes = o.precision ? (const void *)(dp->d_r32 + h.ro_box) : (const void *)(dp->d_r64 + h.ro_box);
+    a.n = c->n; a.ld = c->batch_stride ? c->batch_stride : c->n;
+    a.n_box = h.n_box; a.grad_mode = c->grad_mode;
+    a.truncation_dist = c->truncation_dist; a.vals_offset = c->vals_offset;
+    const long long tiles = (c->n + k.block - 1) / k.block;
+    long long grid = (long long)k.occ * m->n_sm;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) return KIN_OK;
+    void *args[] = {&a};
+    CUDA_TRY(cudaLaunchKernel((const void *)k.kern, dim3((unsigned)grid), dim3((unsigned)k.block), args, jit_smem(o, h, k), stream));
+    g_launches.fetch_add(1);
+    g_jit_launches.fetch_add(1);
+    return KIN_OK;
+}
+
 int launch(KinModel *m, const KinCall *c, DeviceProgram *dp, cudaStream_t stream) {
+    if (jit_wanted(m, c, dp)) {
+        std::shared_ptr<JitKernel> jk = get_jit(m, c, dp);
+        if (jk) return launch_jit(m, c, dp, *jk, stream);
+    }
     const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
     kin::KernelArgs a;
     std::memset(&a, 0, sizeof a);
@@ -351,6 +515,57 @@ int kin_debug_build(void) {
 #endif
 }
 int64_t kin_launch_count(void) { return g_launches.load(); }
+
+const char *kin_jit_status(void) {
+    static thread_local std::string s;
+    s = kin::jit_status();
+    return s.c_str();
+}
+
+int kin_jit_stats(int64_t *compiles, int64_t *cache_hits, int64_t *launches, int64_t *failures) {
+    if (compiles) *compiles = g_jit_compiles.load();
+    if (cache_hits) *cache_hits = g_jit_cache_hits.load();
+    if (launches) *launches = g_jit_launches.load();
+    if (failures) *failures = g_jit_failures.load();
+    return KIN_OK;
+}
+
+// Host-only: generate the specialised source a call would run (pointers of `call` are only tested for NULL) into
+// out_dir, and with compile != 0 also compile it with NVRTC (kin_gen.cubin, kin_gen.log).  No device needed.
+int kin_codegen_dump(const KinModelDesc *d, const KinCall *c, int32_t compile, const char *out_dir) {
+    if (!d || !c || !out_dir) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
+    kin::HostModel hm;
+    int rc = host_model_from_desc(d, hm);
+    if (rc != KIN_OK) return rc;
+    const bool want_coll = c->vals_out != nullptr;
+    const bool want_stale = want_coll && c->grads_out && c->scratch_mode == KIN_SCRATCH_REFERENCE;
+    const int n_fk = c->T_out ? c->n_fk_links : 0, n_jac = c->J_out ? c->n_jac_links : 0;
+    std::vector<int> fk(n_fk), jac(n_jac);
+    for (int i = 0; i < n_fk; ++i) fk[i] = c->fk_links[i] - 1;
+    for (int i = 0; i < n_jac; ++i) jac[i] = c->jac_links[i] - 1;
+    DeviceProgram dp;
+    std::string err;
+    if (!kin::compile_program(hm, fk, jac, want_coll, want_stale, kin::JF_REGS, dp.prog, err)) return fail(KIN_ERR_INVALID_ARGUMENT, err);
+    const kin::GenOptions o = gen_options(c, &dp);
+    kin::GenSource g;
+    if (!kin::generate_source(dp.prog, o, g, err)) return fail(KIN_ERR_INVALID_ARGUMENT, "codegen: " + err);
+    const std::string dir(out_dir);
+    const kin::JitHeaders hs = jit_headers(g);
+    auto put = [&](const std::string &name, const std::string &text) { std::ofstream f(dir + "/" + name, std::ios::binary); f << text; };
+    put("kin_gen.cu", jit_main_source());
+    for (const auto &hd : hs) put(hd.first, hd.second);
+    if (compile) {
+        std::vector<char> cubin;
+        std::string log;
+        bool cached = false;
+        const bool ok = kin::jit_compile(jit_main_source(), hs, "sm_100a", cubin, log, &cached);
+        put("kin_gen.log", log);
+        if (!ok) return fail(KIN_ERR_CUDA, "NVRTC: " + log);
+        std::ofstream f(dir + "/kin_gen.cubin", std::ios::binary);
+        f.write(cubin.data(), (std::streamsize)cubin.size());
+    }
+    return KIN_OK;
+}
 
 int kin_model_create(const KinModelDesc *d, KinModel **out) {
     if (!d || !out) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
@@ -481,6 +696,19 @@ int kin_query_launch(KinModel *m, const KinCall *c, int32_t *regs, int32_t *smem
     if (rc != KIN_OK) return rc;
     DeviceProgram *dp = dp_.get();
     const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
+    if (jit_wanted(m, c, dp)) {
+        std::shared_ptr<JitKernel> jk = get_jit(m, c, dp);
+        if (jk) {
+            const long long tiles = (c->n + jk->block - 1) / jk->block;
+            long long g = (long long)jk->occ * m->n_sm;
+            if (g > tiles) g = tiles;
+            if (regs) *regs = jk->regs;
+            if (smem_bytes) *smem_bytes = (int32_t)jit_smem(gen_options(c, dp), dp->prog.h, *jk);
+            if (block) *block = -jk->block;          // negative block size: the model-specialised (NVRTC) kernel
+            if (grid) *grid = (int32_t)g;
+            return KIN_OK;
+        }
+    }
     if (ws_eligible(m, c, dp)) {
         cudaFuncAttributes fa;
         const bool pre = ws_pre(m, c, dp);

@@ -1,0 +1,46 @@
+// kin_codegen.hpp -- model-specialised CUDA source for one compiled kinematic program (kin_program.h).
+//
+// The ahead-of-time kernels (kin_kernels.cuh) INTERPRET the program tables per configuration: node loop, table
+// loads, flag tests, run-time relevance masks -- 71 % of their issued instructions are that interpretation, not
+// arithmetic (profiles/r01c_fused_ws_sass_mix.txt).  For large batches the library instead generates the source of
+// a kernel for THIS model and THESE requested outputs and compiles it with NVRTC for sm_100a (kin_jit.cpp):
+//   * phase 1 (forward kinematics, joint frames, link transforms, Jacobians, sphere centres: algorithm.jl:1-114,
+//     mechanism.jl:90-103, collision.jl:39-49) becomes straight-line code.  The generator evaluates the chain
+//     SYMBOLICALLY: every transform entry is either a known constant or a named variable, multiplications by exact
+//     0 / +-1 and additions of exact 0 disappear, constants fold on the host with the same correctly rounded
+//     operations -- which leaves every remaining operation, and therefore every result, bit-identical to the
+//     interpreting kernel (up to the sign of a zero);
+//   * phase 2 (union SDF, truncation, gradient, chain rule: sdf.jl:34-41,108-119, collision.jl:67-94) is the same
+//     C++ as the interpreting kernel, instantiated once per run of spheres with equal relevance mask, with the mask,
+//     the column count and types, and the scratch / gradient / argmin switches as template constants.
+// The generated text is compiled together with kin_device_math.cuh and kin_gen_skeleton.cuh (both embedded in the
+// library).
+#pragma once
+#include <string>
+
+#include "kin_model.hpp"
+
+namespace kin {
+
+struct GenOptions {
+    int precision = 0;          // 0 = f64, 1 = f32
+    int layout = 0;             // 0 = SoA, 2 = tiled (AoS stays on the interpreting kernel)
+    bool want_T = false, want_J = false, coll = false;
+    int with_rot = 0, rpy_jac = 0, keep_irrelevant = 0;
+    bool want_grads = false, want_argmin = false, stale = false;
+    bool ws = false;            // warp-specialised skeleton (producer = phase 1, consumers = phase 2)
+    int block = 128, min_blocks = 1;
+    std::string key() const;    // cache key of the option set
+};
+
+struct GenSource {
+    std::string config;         // "kin_gen_config.h": constants of the model + options
+    std::string phase1;         // "kin_gen_phase1.inc": straight-line phase 1
+    std::string phase2;         // "kin_gen_phase2.inc": the phase-2 run calls
+    int n_ops = 0;              // arithmetic operations emitted in phase 1 (diagnostics)
+};
+
+// Returns false (with err) when the program cannot be specialised (the caller then uses the interpreting kernel).
+bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std::string &err);
+
+}  // namespace kin

@@ -299,9 +299,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) kin_eval_ws_kernel(const __grid
                                 if (A.with_rot) {
                                     if (rev) {
                                         if (A.rpy_jac) {
-                                            __stcs(&o[3 * es], k[0] * f.a[0] - k[1] * f.a[1]);
-                                            __stcs(&o[4 * es], fma_(k[2], f.a[0], k[3] * f.a[1]));
-                                            __stcs(&o[5 * es], fma_(k[4], f.a[0], k[5] * f.a[1]) + f.a[2]);
+                                            real o3, o4, o5;
+                                            rpy_rows(k, f.a[0], f.a[1], f.a[2], o3, o4, o5);
+                                            __stcs(&o[3 * es], o3); __stcs(&o[4 * es], o4); __stcs(&o[5 * es], o5);
                                         } else {
                                             __stcs(&o[3 * es], f.a[0]); __stcs(&o[4 * es], f.a[1]); __stcs(&o[5 * es], f.a[2]);
                                         }

@@ -24,7 +24,8 @@ _ip = C.POINTER(C.c_int32)
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static"]
-SOURCES = ["kin_b200.cu", "kin_model.cpp"]
+SOURCES = ["kin_b200.cu", "kin_model.cpp", "kin_codegen.cpp", "kin_jit.cpp"]
+EMBEDDED = ["kin_device_math.cuh", "kin_gen_skeleton.cuh"]      # linked in as text for NVRTC (kin_jit.cpp)
 
 
 class KinError(RuntimeError):
@@ -52,7 +53,8 @@ class KinCall(C.Structure):
 EXPORTS = ["kin_last_error", "kin_abi_version", "kin_build_id", "kin_debug_build", "kin_model_create", "kin_model_destroy", "kin_model_set_spheres",
            "kin_model_set_boxes", "kin_model_n_dof", "kin_model_n_spheres", "kin_model_n_boxes", "kin_eval",
            "kin_eval_host", "kin_fk_links", "kin_fk_jacobian", "kin_collision", "kin_launch_count",
-           "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual", "kin_pose_residual_multi", "kin_lm_step", "kin_lm_accept", "kin_probe_fp64"]
+           "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual", "kin_pose_residual_multi", "kin_lm_step", "kin_lm_accept", "kin_probe_fp64",
+           "kin_jit_status", "kin_jit_stats", "kin_codegen_dump"]
 
 
 def source_files():
@@ -95,9 +97,21 @@ def needs_build(debug: bool = False) -> bool:
     return so_build_id(so_path(debug)) != source_id()
 
 
+def _embed_object() -> str:
+    """ld -r -b binary: the two header texts NVRTC needs at run time as one relocatable object
+    (_binary_<file>_start / _end symbols; run inside csrc/ so that the names carry no directory)."""
+    obj = os.path.join(HERE, "build", "kin_embedded.o")
+    os.makedirs(os.path.dirname(obj), exist_ok=True)
+    out = subprocess.run(["ld", "-r", "-b", "binary", "-z", "noexecstack", "-o", obj] + EMBEDDED, cwd=CSRC, capture_output=True, text=True)
+    if out.returncode != 0:
+        raise KinError("ld -b binary failed:\n" + out.stdout + out.stderr)
+    return obj
+
+
 def _nvcc_cmd(debug: bool, verbose: bool):
     return ["nvcc"] + NVCC_FLAGS + (["-DKIN_DEBUG"] if debug else []) + ['-DKIN_BUILD_ID="%s"' % source_id()] + \
-           (["-Xptxas", "-v"] if verbose else []) + ["-o", so_path(debug)] + [os.path.join(CSRC, s) for s in SOURCES]
+           (["-Xptxas", "-v"] if verbose else []) + ["-o", so_path(debug)] + [os.path.join(CSRC, s) for s in SOURCES] + \
+           [_embed_object(), "-ldl"]
 
 
 def build(force: bool = False, verbose: bool = False, debug: bool = False, both: bool = False) -> str:
@@ -121,6 +135,23 @@ def build(force: bool = False, verbose: bool = False, debug: bool = False, both:
 _LIB = None
 
 
+def _find_nvrtc():
+    """libnvrtc of the CUDA toolkit, else the one bundled with the torch wheels (nvidia/cuda_nvrtc)."""
+    import glob
+    pats = ["/usr/local/cuda/lib64/libnvrtc.so.1[0-9]", "/usr/local/cuda/targets/*/lib/libnvrtc.so.1[0-9]"]
+    try:
+        import nvidia
+        for base in getattr(nvidia, "__path__", []):
+            pats.append(os.path.join(base, "cuda_nvrtc", "lib", "libnvrtc.so.1[0-9]"))
+    except ImportError:
+        pass
+    for p in pats:
+        hits = sorted(glob.glob(p))
+        if hits:
+            return hits[-1]
+    return None
+
+
 def lib():
     """Load libkin_b200.so (libkin_b200_debug.so when KIN_DEBUG=1 is set); raises KinError when it has not been
     built or was built from other sources than the ones beside it (no fallback path exists)."""
@@ -131,6 +162,10 @@ def lib():
         if not os.path.exists(path):
             raise KinError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`; "
                            "there is no CPU fallback" % path)
+        if "KIN_NVRTC_PATH" not in os.environ:          # where kin_jit.cpp should dlopen NVRTC from
+            cand = _find_nvrtc()
+            if cand:
+                os.environ["KIN_NVRTC_PATH"] = cand
         L = C.CDLL(path)
         try:
             L.kin_build_id.restype = C.c_char_p
@@ -162,6 +197,10 @@ def lib():
         L.kin_lm_step.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 8
         L.kin_lm_accept.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 10
         L.kin_probe_fp64.argtypes = [_dp, _dp, _dp]
+        L.kin_jit_status.restype = C.c_char_p
+        _lp = C.POINTER(C.c_int64)
+        L.kin_jit_stats.argtypes = [_lp, _lp, _lp, _lp]
+        L.kin_codegen_dump.argtypes = [C.POINTER(KinModelDesc), C.POINTER(KinCall), C.c_int32, C.c_char_p]
         L.kin_program_dump.argtypes = [C.POINTER(KinModelDesc), _ip, C.c_int32, _ip, C.c_int32, C.c_int32, C.c_int32,
                                        _ip, C.c_int32, _ip, C.c_int32, _dp, C.c_int32]
         _LIB = L

@@ -173,3 +173,42 @@ def test_program_synthetic_branching_tree(with_base, n_ctrl):
         np.testing.assert_allclose(o2["vals"], vals, rtol=1e-12, atol=1e-13)
         assert np.array_equal(o2["argmin"], am)
         np.testing.assert_allclose(o2["grads"], grads.transpose(0, 2, 1), rtol=0, atol=1e-7)
+
+
+def test_codegen_and_nvrtc_compile_without_a_gpu(tmp_path):
+    """The model-specialised kernel source (csrc/kin_codegen.cpp) is generated and compiled with NVRTC for sm_100a
+    on the CPU box: Fetch FK of all links + gripper Jacobian, and the fused call with the 16-sphere fixture."""
+    import ctypes as C
+    import scene_fetch
+    from kinematics_jl_b200 import lib as L
+    from kinematics_jl_b200.device import make_desc
+    lib = L.lib()
+    if not lib.kin_jit_status().startswith(b"ok"):
+        pytest.skip("NVRTC not available: " + lib.kin_jit_status().decode())
+    m, joints, sscc = scene_fetch.product_fetch(False)
+    poses, widths = scenes.fridge_boxes_host()
+    d, keep = make_desc(m, [j.id for j in joints], spheres=(sscc._parents, sscc._centers, sscc.sphere_radii), boxes=(poses, widths))
+    fk = np.arange(1, 26, dtype=np.int32)
+    jac = np.array([K.find_link(m, "gripper_link").id], dtype=np.int32)
+    ip = C.POINTER(C.c_int32)
+    for fused in (False, True):
+        c = L.KinCall()
+        c.precision, c.layout, c.n, c.q = L.F64, L.SOA, 1 << 20, 1
+        c.n_fk_links, c.fk_links, c.T_out = 25, fk.ctypes.data_as(ip), 1
+        c.n_jac_links, c.jac_links, c.J_out, c.with_rot = 1, jac.ctypes.data_as(ip), 1, 1
+        c.truncation_dist = float("inf")
+        if fused:
+            c.vals_out, c.grads_out = 1, 1
+        out = tmp_path / ("fused" if fused else "fkj")
+        out.mkdir()
+        L.check(lib.kin_codegen_dump(C.byref(d), C.byref(c), 1, str(out).encode()))
+        p1 = (out / "kin_gen_phase1.inc").read_text()
+        # constants are folded: the 25-link FK of Fetch needs fewer than 400 arithmetic statements (the
+        # interpreting kernel executes ~1800 per configuration), and all 300 + 48 outputs are stored
+        n_arith = sum(p1.count(op) for op in ("fma_(", "mul_(", "add_(", "sub_("))
+        assert 100 < n_arith < 400
+        assert p1.count("KST_T(") == 300 and p1.count("KST_J(") == 48
+        assert (out / "kin_gen.cubin").stat().st_size > 10000
+        if fused:
+            p2 = (out / "kin_gen_phase2.inc").read_text()
+            assert p2.count("phase2_run<") == 4            # wrist / torso / upperarm / elbow: four relevance masks

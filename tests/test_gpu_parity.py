@@ -203,6 +203,7 @@ def test_warp_specialised_kernel_is_bitwise_identical(layout, n, with_base, monk
     warps walk the chain, consumer warps do the sphere work).  It runs the same arithmetic in the same order as
     kin_eval_kernel, so every output must be bitwise identical -- for ragged batches, with and without
     truncation, in both scratch modes and all gradient modes."""
+    monkeypatch.setenv("KIN_DISABLE_JIT", "1")      # these tests compare the two AHEAD-OF-TIME kernels
     m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(with_base)
     q = scenes.random_configs(jo, n, with_base, seed=17, zeros_every=97)
     from kinematics_jl_b200.device import current_q, evaluate
@@ -246,6 +247,7 @@ def test_warp_specialised_kernel_argument_combinations_and_streams(monkeypatch):
     """The warp-specialised kernel with outputs switched off one by one (collision only, distances only, no
     argmin, translation-only geometric Jacobian), bitwise against kin_eval_kernel; then two launches in flight on
     two streams at once (each takes its own hand-over ring from the model's pool) against the serial result."""
+    monkeypatch.setenv("KIN_DISABLE_JIT", "1")      # these tests compare the two AHEAD-OF-TIME kernels
     from kinematics_jl_b200.device import current_q, evaluate
     m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
     n = 40000
@@ -303,6 +305,7 @@ def test_warp_specialised_kernel_on_a_second_model_vs_oracle(with_base, monkeypa
     attachments carry non-trivial constant transforms), 10 spheres on 3 links in an order that is NOT the chain
     order, a union of 3 rotated boxes: warp-specialised kernel against the oracle and bitwise against
     kin_eval_kernel."""
+    monkeypatch.setenv("KIN_DISABLE_JIT", "1")      # these tests compare the two AHEAD-OF-TIME kernels
     from kinematics_jl_b200.device import current_q, evaluate
     from kinematics_jl_b200.transform import rotz
     g = json.load(open(os.path.join(DATA, "ground_truth.json")))
@@ -469,6 +472,101 @@ def test_stale_scratch_differs_from_clean_as_in_the_reference():
     _, g_clean = K.compute_coll_dists_and_grads(sscc, joints, sdf, scratch_mode=K.SCRATCH_CLEAN)
     assert np.array_equal(g_ref[:, :4], g_clean[:, :4])
     assert np.all(g_clean[1:, 4:8] == 0.0) and np.any(g_ref[1:7, 4:8] != 0.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# model-specialised (NVRTC) kernels: bit-identical to the interpreting kernels, and checked against the oracle
+# ------------------------------------------------------------------------------------------------
+def _eval_all(m, joints, sscc, sdf, Q, layout, jit, monkeypatch, **kw):
+    from kinematics_jl_b200.device import current_q, evaluate
+    monkeypatch.delenv("KIN_DISABLE_JIT", raising=False)
+    monkeypatch.delenv("KIN_FORCE_JIT", raising=False)
+    monkeypatch.setenv("KIN_FORCE_JIT" if jit else "KIN_DISABLE_JIT", "1")
+    K.set_joint_angles(m, joints, Q)
+    if sscc is not None:
+        K.compute_coll_dists(sscc, joints, sdf)
+    dm = device_model(m)
+    Qc, ql, N = current_q(m)
+    gl = K.find_link(m, "gripper_link").id
+    out = evaluate(dm, Qc, ql, N, layout=layout, fk_links=list(range(1, 26)), jac_links=[gl, K.find_link(m, "elbow_flex_link").id],
+                   collision=sscc is not None, want_argmin=sscc is not None, launch_info=True, **kw)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("with_base", [False, True])
+@pytest.mark.parametrize("layout", [L.SOA, L.TILED32])
+@pytest.mark.parametrize("n", [1, 77, 40000])
+def test_specialised_kernel_is_bitwise_identical(layout, n, with_base, monkeypatch):
+    """The NVRTC-compiled, model-specialised kernel (straight-line phase 1 with the model's constants folded in,
+    phase 2 instantiated per relevance mask) against the interpreting ahead-of-time kernel on the same inputs: every
+    output equal bit for bit (== treats the two zeros as equal: the sign of a zero is the one thing folding changes)."""
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(with_base)
+    q = scenes.random_configs(jo, n, with_base, seed=23, zeros_every=50)
+    Q = dev(q)
+    lib = L.lib()
+    combos = [dict(with_rot=True, rpy_jac=False, truncation_dist=np.inf, grad_mode=L.GRAD_FD, scratch_mode=L.SCRATCH_REFERENCE),
+              dict(with_rot=True, rpy_jac=True, truncation_dist=0.08, grad_mode=L.GRAD_FD, scratch_mode=L.SCRATCH_CLEAN, vals_offset=0.03),
+              dict(with_rot=False, keep_irrelevant=False, truncation_dist=np.inf, grad_mode=L.GRAD_ANALYTIC, scratch_mode=L.SCRATCH_REFERENCE)]
+    for kw in combos:
+        a = _eval_all(m, joints, sscc, sdf, Q, layout, False, monkeypatch, **kw)
+        assert a["launch"]["block"] > 0
+        b = _eval_all(m, joints, sscc, sdf, Q, layout, True, monkeypatch, **kw)
+        assert b["launch"]["block"] < 0, lib.kin_jit_status()          # negative block size = specialised kernel
+        for key in ("T", "J", "vals", "grads", "argmin"):
+            assert torch.equal(a[key], b[key]), (key, kw)
+    # FK / Jacobian only (no collision): the straight-line kernel without any shared memory
+    a = _eval_all(m, joints, None, None, Q, layout, False, monkeypatch, with_rot=True, rpy_jac=True)
+    b = _eval_all(m, joints, None, None, Q, layout, True, monkeypatch, with_rot=True, rpy_jac=True)
+    assert b["launch"]["block"] < 0 and b["launch"]["smem_bytes"] == 0
+    assert torch.equal(a["T"], b["T"]) and torch.equal(a["J"], b["J"])
+    # and against the oracle (the specialised results)
+    sub = slice(0, min(n, 300))
+    np.testing.assert_allclose(host(b["T"][sub]), R.batch_fk(mo, jo, q[sub], mo.links[:25])[:, :, :3, :], rtol=RTOL, atol=ATOL)
+    Jo = R.batch_jacobian(mo, jo, q[sub], [R.find_link(mo, "gripper_link"), R.find_link(mo, "elbow_flex_link")], True, rpy_jac=True)
+    np.testing.assert_allclose(host(b["J"][sub]), Jo, rtol=1e-11, atol=1e-11)
+    compiles, hits, launches, failures = (C.c_int64() for _ in range(4))
+    lib.kin_jit_stats(C.byref(compiles), C.byref(hits), C.byref(launches), C.byref(failures))
+    assert failures.value == 0 and launches.value > 0
+
+
+def test_specialised_kernel_fp32_and_general_models(monkeypatch):
+    """FP32 instantiation of the specialised kernel (same folding in float) and models that exercise the general
+    paths of the generator: a branching tree with general axes / rpy origins / frozen joints, and the PR2 chain."""
+    import scenes_synthetic
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
+    q = scenes.random_configs(jo, 3000, False, seed=29)
+    a = _eval_all(m, joints, sscc, sdf, dev(q, torch.float32), L.SOA, False, monkeypatch, grad_mode=L.GRAD_ANALYTIC, scratch_mode=L.SCRATCH_CLEAN)
+    b = _eval_all(m, joints, sscc, sdf, dev(q, torch.float32), L.SOA, True, monkeypatch, grad_mode=L.GRAD_ANALYTIC, scratch_mode=L.SCRATCH_CLEAN)
+    assert b["launch"]["block"] < 0 and b["T"].dtype == torch.float32
+    for key in ("T", "J", "vals", "grads", "argmin"):
+        assert torch.equal(a[key], b[key]), key
+    # synthetic branching mechanism (tests/scenes_synthetic.py: general axes, rpy origins, frozen joints, save slots,
+    # spheres on three branches, rotated boxes), all links, both kernels and the oracle
+    for with_base in (False, True):
+        mp_, jp, sp_, sdfp = scenes_synthetic.product(with_base)
+        mo_, jo_, so_, sdfo_ = scenes_synthetic.oracle(with_base)
+        qs = scenes_synthetic.random_q(jo_, 500, with_base, seed=30)
+        outs = []
+        for jit in (False, True):
+            monkeypatch.delenv("KIN_DISABLE_JIT", raising=False)
+            monkeypatch.delenv("KIN_FORCE_JIT", raising=False)
+            monkeypatch.setenv("KIN_FORCE_JIT" if jit else "KIN_DISABLE_JIT", "1")
+            K.set_joint_angles(mp_, jp, soa(dev(qs)))
+            T = K.get_transform(mp_, mp_.links)
+            J = K.get_jacobian(mp_, mp_.links, jp, True, rpy_jac=True)
+            v, g, am = K.compute_coll_dists_and_grads(sp_, jp, sdfp, return_argmin=True)
+            outs.append([x.clone() for x in (T, J, v, g, am)])
+        for x, y in zip(*outs):
+            assert torch.equal(x, y)
+        np.testing.assert_allclose(host(outs[1][0]), R.batch_fk(mo_, jo_, qs, mo_.links)[:, :, :3, :], rtol=RTOL, atol=ATOL)
+        v_ref, g_ref, am_ref = R.batch_collision(so_, jo_, sdfo_, qs)
+        np.testing.assert_allclose(host(outs[1][2]), v_ref, rtol=RTOL, atol=ATOL)
+        assert np.array_equal(outs[1][4].cpu().numpy(), am_ref)
+        np.testing.assert_allclose(host(outs[1][3]), g_ref.transpose(0, 2, 1), rtol=0, atol=1e-7)
+    compiles, hits, launches, failures = (C.c_int64() for _ in range(4))
+    L.lib().kin_jit_stats(C.byref(compiles), C.byref(hits), C.byref(launches), C.byref(failures))
+    assert failures.value == 0
 
 
 # ------------------------------------------------------------------------------------------------

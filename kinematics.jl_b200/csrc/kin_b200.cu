@@ -2,6 +2,7 @@
 // launch configuration and the host-staged variant.  The kernel itself is kin_kernels.cuh.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -48,6 +49,7 @@ struct JitKernel {
     cudaKernel_t kern = nullptr;
     bool ok = false, from_cache = false;
     int regs = 0, block = 0, occ = 0, slots = 0, smem_limit = 0;
+    bool cooperative = false;       // grid-wide barrier inside (input batching): launched cooperatively
     double compile_ms = 0;
     std::string log;
     ~JitKernel() { if (lib) cudaLibraryUnload(lib); }
@@ -307,7 +309,7 @@ long long env_ll(const char *name, long long dflt) {
     return e && *e ? std::atoll(e) : dflt;
 }
 
-kin::GenOptions gen_options(const KinCall *c, const DeviceProgram *dp) {
+kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
     const kin::ProgHeader &h = dp->prog.h;
     kin::GenOptions o;
     o.precision = c->precision == KIN_F32 ? 1 : 0;
@@ -324,8 +326,20 @@ kin::GenOptions gen_options(const KinCall *c, const DeviceProgram *dp) {
     o.ws = false;
     // residency: the collision phase holds the joint frames in registers (up to 255 per thread: 2 x 128 threads per
     // SM); the FK / Jacobian-only kernel needs far fewer
-    o.block = (int)env_ll("KIN_JIT_BLOCK", 128);
-    o.min_blocks = (int)env_ll("KIN_JIT_MINB", o.coll ? 2 : 3);
+    o.block = (int)env_ll("KIN_JIT_BLOCK", o.coll ? 128 : 256);
+    o.min_blocks = (int)env_ll("KIN_JIT_MINB", o.coll ? 2 : 1);
+    // input batching (kin_gen_skeleton.cuh): the FK / Jacobian-only kernels are bound by the DRAM write path and use
+    // no other shared memory, so the configurations of as many tiles as fit twice in ~200 KB are fetched per batch
+    // behind a grid-wide barrier (one CTA per SM, cooperative launch)
+    o.qbatch = 0;
+    if (!o.coll && h.n_dof > 0 && !std::getenv("KIN_JIT_NO_QBATCH")) {
+        const size_t rs = o.precision ? sizeof(float) : sizeof(double);
+        const size_t budget = std::min<size_t>((size_t)(m ? m->dev_smem : 227 * 1024), 200 * 1024);
+        long long qb = (long long)(budget / (2 * (size_t)h.n_dof * o.block * rs));
+        qb = std::min<long long>(qb, 16);
+        qb = env_ll("KIN_JIT_QBATCH", qb);
+        if (qb >= 2) { o.qbatch = (int)qb; o.min_blocks = 1; }
+    }
     return o;
 }
 
@@ -361,16 +375,17 @@ int jit_slots(const kin::GenOptions &o, const kin::ProgHeader &h) {
 }
 
 size_t jit_smem(const kin::GenOptions &o, const kin::ProgHeader &h, const JitKernel &k) {
-    if (!o.coll) return 0;
     const size_t rs = o.precision ? sizeof(float) : sizeof(double);
-    const size_t tab = ((size_t)h.n_box * kin::BOX_REALS + h.n_sph + 1) & ~size_t(1);
-    return rs * (tab + (size_t)k.slots * k.block);
+    size_t reals = 0;
+    if (o.coll) reals += (((size_t)h.n_box * kin::BOX_REALS + h.n_sph + 1) & ~size_t(1)) + (size_t)k.slots * k.block;
+    if (o.qbatch > 0) reals += (size_t)2 * o.qbatch * h.n_dof * k.block;
+    return rs * reals;
 }
 
 // Returns the compiled kernel for this call's option set (compiling it on first use), or null when specialisation
 // is unavailable for it (NVRTC missing, compile error, does not fit): the caller then uses the interpreting kernels.
 std::shared_ptr<JitKernel> get_jit(KinModel *m, const KinCall *c, DeviceProgram *dp) {
-    const kin::GenOptions o = gen_options(c, dp);
+    const kin::GenOptions o = gen_options(m, c, dp);
     const std::string key = o.key();
     std::lock_guard<std::mutex> lock(dp->jit_mu);
     auto it = dp->jit.find(key);
@@ -411,6 +426,7 @@ std::shared_ptr<JitKernel> get_jit(KinModel *m, const KinCall *c, DeviceProgram 
     }
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k->occ, (const void *)k->kern, k->block, smem);
     if (e != cudaSuccess || k->occ < 1) { k->log = "occupancy query failed"; cudaGetLastError(); g_jit_failures.fetch_add(1); return nullptr; }
+    k->cooperative = o.qbatch > 0;
     k->compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (std::getenv("KIN_JIT_VERBOSE"))
         std::fprintf(stderr, "[libkin_b200] specialised kernel %s: %d registers, %zu B shared, %d CTAs/SM, %.0f ms%s\n", key.c_str(), k->regs, smem,
@@ -420,7 +436,7 @@ std::shared_ptr<JitKernel> get_jit(KinModel *m, const KinCall *c, DeviceProgram 
 }
 
 int launch_jit(KinModel *m, const KinCall *c, DeviceProgram *dp, JitKernel &k, cudaStream_t stream) {
-    const kin::GenOptions o = gen_options(c, dp);
+    const kin::GenOptions o = gen_options(m, c, dp);
     const kin::ProgHeader &h = dp->prog.h;
     kin::GenArgs a;
     std::memset(&a, 0, sizeof a);
@@ -435,7 +451,26 @@ int launch_jit(KinModel *m, const KinCall *c, DeviceProgram *dp, JitKernel &k, c
     if (grid > tiles) grid = tiles;
     if (grid < 1) return KIN_OK;
     void *args[] = {&a};
-    CUDA_TRY(cudaLaunchKernel((const void *)k.kern, dim3((unsigned)grid), dim3((unsigned)k.block), args, jit_smem(o, h, k), stream));
+    if (k.cooperative) {
+        // two zero-initialised barrier words per launch (stream-ordered, so concurrent launches have their own)
+        unsigned *sync = nullptr;
+        CUDA_TRY(cudaMallocFromPoolAsync((void **)&sync, 2 * sizeof(unsigned), m->pool, stream));
+        cudaError_t e = cudaMemsetAsync(sync, 0, 2 * sizeof(unsigned), stream);
+        a.sync = sync;
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)k.block);
+        cfg.dynamicSmemBytes = jit_smem(o, h, k); cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeCooperative;
+        attr.val.cooperative = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        if (e == cudaSuccess) e = cudaLaunchKernelExC(&cfg, (const void *)k.kern, args);
+        cudaFreeAsync(sync, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "launching the specialised kernel (cooperative)");
+    } else {
+        CUDA_TRY(cudaLaunchKernel((const void *)k.kern, dim3((unsigned)grid), dim3((unsigned)k.block), args, jit_smem(o, h, k), stream));
+    }
     g_launches.fetch_add(1);
     g_jit_launches.fetch_add(1);
     return KIN_OK;
@@ -546,7 +581,7 @@ int kin_codegen_dump(const KinModelDesc *d, const KinCall *c, int32_t compile, c
     DeviceProgram dp;
     std::string err;
     if (!kin::compile_program(hm, fk, jac, want_coll, want_stale, kin::JF_REGS, dp.prog, err)) return fail(KIN_ERR_INVALID_ARGUMENT, err);
-    const kin::GenOptions o = gen_options(c, &dp);
+    const kin::GenOptions o = gen_options(nullptr, c, &dp);
     kin::GenSource g;
     if (!kin::generate_source(dp.prog, o, g, err)) return fail(KIN_ERR_INVALID_ARGUMENT, "codegen: " + err);
     const std::string dir(out_dir);
@@ -703,7 +738,7 @@ int kin_query_launch(KinModel *m, const KinCall *c, int32_t *regs, int32_t *smem
             long long g = (long long)jk->occ * m->n_sm;
             if (g > tiles) g = tiles;
             if (regs) *regs = jk->regs;
-            if (smem_bytes) *smem_bytes = (int32_t)jit_smem(gen_options(c, dp), dp->prog.h, *jk);
+            if (smem_bytes) *smem_bytes = (int32_t)jit_smem(gen_options(m, c, dp), dp->prog.h, *jk);
             if (block) *block = -jk->block;          // negative block size: the model-specialised (NVRTC) kernel
             if (grid) *grid = (int32_t)g;
             return KIN_OK;

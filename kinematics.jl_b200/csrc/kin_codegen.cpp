@@ -10,8 +10,8 @@ namespace kin {
 
 std::string GenOptions::key() const {
     char b[160];
-    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d", precision, layout, (int)want_T, (int)want_J,
-                  (int)coll, with_rot, rpy_jac, keep_irrelevant, (int)want_grads, (int)want_argmin, (int)stale, (int)ws, block, min_blocks);
+    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d", precision, layout, (int)want_T, (int)want_J,
+                  (int)coll, with_rot, rpy_jac, keep_irrelevant, (int)want_grads, (int)want_argmin, (int)stale, (int)ws, block, min_blocks, qbatch);
     return b;
 }
 
@@ -95,7 +95,6 @@ class Emitter {
         if (a.c && a.v == -1.0) return sub(c, b);
         if (b.c && b.v == -1.0) return sub(c, a);
         if (c.c && c.v == 0.0) return mul(a, b);
-        if (a.c && b.c) return add(mul(a, b), c) /* unreachable in practice */;
         return var("fma_(" + str(a) + ", " + str(b) + ", " + str(c) + ")");
     }
 
@@ -341,7 +340,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
     c << "#define KREAL " << (f32 ? "float" : "double") << "\n";
     c << "#define KWANT_T " << (o.want_T ? 1 : 0) << "\n#define KWANT_J " << (o.want_J ? 1 : 0) << "\n#define KCOLL " << (o.coll ? 1 : 0)
       << "\n#define KTILED " << (o.layout == 2 ? 1 : 0) << "\n#define KWS " << (o.ws ? 1 : 0) << "\n";
-    c << "#define KBS " << o.block << "\n#define KMINB " << o.min_blocks << "\n";
+    c << "#define KBS " << o.block << "\n#define KMINB " << o.min_blocks << "\n#define KQB " << o.qbatch << "\n";
     c << "namespace kin {\n";
     c << "constexpr int KND = " << ND << ", KDC = " << DC << ", KS = " << S << ", KNFK = " << (o.want_T ? h.n_fk : 0) << ", KNJAC = "
       << (o.want_J ? h.n_jac : 0) << ", KROWS = " << rows << ";\n";

@@ -30,6 +30,7 @@ struct GenOptions {
     bool want_grads = false, want_argmin = false, stale = false;
     bool ws = false;            // warp-specialised skeleton (producer = phase 1, consumers = phase 2)
     int block = 128, min_blocks = 1;
+    int qbatch = 0;             // > 0: tiles per input batch (cp.async into shared memory behind a grid-wide barrier)
     std::string key() const;    // cache key of the option set
 };
 

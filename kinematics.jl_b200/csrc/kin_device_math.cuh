@@ -280,6 +280,17 @@ __device__ __forceinline__ void jac_col(const JFrame<real> &f, bool revolute, re
 template <typename real>
 __device__ __forceinline__ void rpy_rows(const real k[6], real ax, real ay, real az, real &o3, real &o4, real &o5);
 
+// cp.async of one element global -> shared (LDGSTS): the next tile's configuration lands in the scratch
+// while the current tile is being computed
+__device__ __forceinline__ void cp_async_elem(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_elem(float *smem_dst, const float *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Kernel parameter of the model-specialised kernels (kin_gen_skeleton.cuh); shared with the host (kin_b200.cu).
 struct GenArgs {
     const void *q;
@@ -287,6 +298,7 @@ struct GenArgs {
     int32_t *argmin_out;
     const void *boxes;           // device: n_box rows of BOX_REALS reals (rewritten in place by kin_model_set_boxes)
     void *ws_ring;               // warp-specialised variant: global hand-over ring
+    unsigned *sync;              // input batching (KQB > 0): two zero-initialised words of the grid-wide barrier
     long long n, ld;
     int n_box, grad_mode;
     double truncation_dist, vals_offset;

@@ -109,16 +109,51 @@ __device__ __forceinline__ void phase2_run(const int sb, const int se, const rea
 // =====================================================================================================================
 // Monolithic kernel: phase 1 and phase 2 in the same thread.
 // Dynamic shared memory: [box table n_box * BOX_REALS][radii KS] then the per-thread scratch [slot][thread]:
-//   3 KS sphere-centre coordinates, 3 KND stale-Jacobian columns (KSTALE), 2 SPH_GROUP hand-over slots.
+//   3 KS sphere-centre coordinates, 3 KND stale-Jacobian columns (KSTALE), 2 SPH_GROUP hand-over slots;
+// then (KQB > 0) the input batches [2][KQB][KND][BS].
+//
+// KQB > 0: INPUT BATCHING.  The kernels are bound by the DRAM write path (2784 B of results per configuration against
+// 64 B of input), and on HBM3e a trickle of small reads in the middle of a saturated write stream is disproportionately
+// expensive: a store-only kernel with this output pattern sustains 6.05 TB/s, the same kernel reading its 8 inputs per
+// thread 5.22 TB/s (profiles/probe_store.cu) -- every read interrupts the write drain of the channels it touches.
+// So the configurations of KQB tiles per CTA are fetched at once with cp.async into shared memory, one batch ahead
+// (double buffered), and ALL CTAs issue the fetch of a batch at the same moment, behind a grid-wide barrier: the DRAM
+// sees one read burst per batch (about every 100 us) instead of 4 reads per microsecond.  The probe recovers 5.93 TB/s
+// that way.  The grid is launched cooperatively (all CTAs resident), the barrier words live in A.sync.
 // =====================================================================================================================
 #if !KWS
+#if KQB > 0
+__device__ __forceinline__ void kin_grid_barrier(unsigned *sync, unsigned n_cta) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned *gen_p = sync + 1;
+        const unsigned gen = *gen_p;
+        __threadfence();
+        if (atomicAdd(sync, 1u) == n_cta - 1) {
+            *sync = 0;
+            __threadfence();
+            *gen_p = gen + 1;
+        } else {
+            unsigned polls = 0;
+            while (*gen_p == gen) {
+                __nanosleep(64);
+                if (++polls > (1u << 28)) __trap();     // a barrier that never completes must not hang the GPU
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+#endif
+
 extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __grid_constant__ kin::GenArgs A) {
     using namespace kin;
     constexpr int BS = KBS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
+    real *smem_next = reinterpret_cast<real *>(smem_raw);
 #if KCOLL
-    real *tb = reinterpret_cast<real *>(smem_raw);
+    real *tb = smem_next;
     const int n_box = A.n_box;
     const int tab_reals = (n_box * BOX_REALS + KS + 1) & ~1;
     real *rad = tb + n_box * BOX_REALS;
@@ -126,6 +161,7 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
     real *cent0 = scr;
     real *stale0 = scr + 3 * KS * BS;
     real *hand = stale0 + (KSTALE ? 3 * KND : 0) * BS;
+    smem_next = tb + tab_reals + (3 * KS + (KSTALE ? 3 * KND : 0) + 2 * SPH_GROUP) * BS;
     {
         const real *src = reinterpret_cast<const real *>(A.boxes);
         for (int i = tid; i < n_box * BOX_REALS; i += BS) tb[i] = src[i];
@@ -136,44 +172,106 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
 #endif
     const size_t es = KTILED ? size_t(32) : (size_t)A.ld;
     const long long n_tiles = (A.n + BS - 1) / BS;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // threads past the end of the batch redo the last configuration (identical values, benign duplicate stores)
-        const long long n = min(tile * BS + tid, (long long)A.n - 1);
-        #define KREC_BASE(rec) (KTILED ? (n >> 5) * ((long long)(rec) * 32) + (n & 31) : n)
-        const real *qn = reinterpret_cast<const real *>(A.q) + KREC_BASE(KND);
-        #define KQ(c) qn[(size_t)(c) * es]
-#if KWANT_T
-        real *Tn = reinterpret_cast<real *>(A.T_out) + KREC_BASE(12 * KNFK);
-        #define KST_T(k, v) __stcs(Tn + (size_t)(k) * es, (v))
+    auto q_ptr = [&](long long tile_) {
+        const long long n_ = min(tile_ * BS + tid, (long long)A.n - 1);
+        return reinterpret_cast<const real *>(A.q) + (KTILED ? (n_ >> 5) * ((long long)KND * 32) + (n_ & 31) : n_);
+    };
+#if KQB > 0
+    real *sq = smem_next;                                     // [2][KQB][KND][BS]
+    const long long my_tiles = (long long)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long max_tiles = (n_tiles + gridDim.x - 1) / gridDim.x, max_batches = (max_tiles + KQB - 1) / KQB;
+    auto issue = [&](long long b, int buf) {
+        #pragma unroll 1
+        for (int r = 0; r < KQB; ++r) {
+            const long long k = b * KQB + r;
+            if (k < my_tiles) {
+                const real *qp = q_ptr(blockIdx.x + k * gridDim.x);
+                real *dst = sq + ((size_t)(buf * KQB + r) * KND) * BS + tid;
+                #pragma unroll
+                for (int c = 0; c < KND; ++c) cp_async_elem(dst + c * BS, qp + (size_t)c * es);
+            }
+        }
+        cp_async_commit();
+    };
+    kin_grid_barrier(A.sync, gridDim.x);
+    issue(0, 0);
+    for (long long b = 0; b < max_batches; ++b) {
+        const int buf = (int)(b & 1);
+        kin_grid_barrier(A.sync, gridDim.x);                  // every SM fetches its next batch NOW
+        issue(b + 1, buf ^ 1);
+        cp_async_wait<1>();
+        __syncthreads();
+        #pragma unroll 1
+        for (int r = 0; r < KQB; ++r) {
+            const long long k = b * KQB + r;
+            if (k >= my_tiles) break;
+            const long long tile = blockIdx.x + k * gridDim.x;
+            const real *sqt = sq + ((size_t)(buf * KQB + r) * KND) * BS + tid;
+            #define KQ(c) sqt[(c) * BS]
 #else
-        #define KST_T(k, v)
+    // no batching: the configuration of the NEXT tile is loaded into registers while the current one is computed
+    real qcur[KND > 0 ? KND : 1];
+    if ((long long)blockIdx.x < n_tiles) {
+        const real *qp = q_ptr(blockIdx.x);
+        #pragma unroll
+        for (int c = 0; c < KND; ++c) qcur[c] = __ldcs(qp + (size_t)c * es);
+    }
+    {
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            real qnxt[KND > 0 ? KND : 1];
+            {
+                const long long tn = tile + gridDim.x < n_tiles ? tile + gridDim.x : tile;
+                const real *qp = q_ptr(tn);
+                #pragma unroll
+                for (int c = 0; c < KND; ++c) qnxt[c] = __ldcs(qp + (size_t)c * es);
+            }
+            #define KQ(c) qcur[c]
+#endif
+            // ---------------- one tile: threads past the end of the batch redo the last configuration (identical
+            //                  values, benign duplicate stores) ----------------
+            const long long n = min(tile * BS + tid, (long long)A.n - 1);
+            #define KREC_BASE(rec) (KTILED ? (n >> 5) * ((long long)(rec) * 32) + (n & 31) : n)
+#if KWANT_T
+            real *Tn = reinterpret_cast<real *>(A.T_out) + KREC_BASE(12 * KNFK);
+            #define KST_T(k, v) __stcs(Tn + (size_t)(k) * es, (v))
+#else
+            #define KST_T(k, v)
 #endif
 #if KWANT_J
-        real *Jn = reinterpret_cast<real *>(A.J_out) + KREC_BASE(KROWS * KND * KNJAC);
-        #define KST_J(k, v) __stcs(Jn + (size_t)(k) * es, (v))
+            real *Jn = reinterpret_cast<real *>(A.J_out) + KREC_BASE(KROWS * KND * KNJAC);
+            #define KST_J(k, v) __stcs(Jn + (size_t)(k) * es, (v))
 #else
-        #define KST_J(k, v)
+            #define KST_J(k, v)
 #endif
 #if KCOLL
-        #define KCEN_SET(s, i, v) cent0[(3 * (s) + (i)) * BS] = (v)
+            #define KCEN_SET(s, i, v) cent0[(3 * (s) + (i)) * BS] = (v)
 #else
-        #define KCEN_SET(s, i, v)
+            #define KCEN_SET(s, i, v)
 #endif
-        #define KJF_OUT(j, i, v)
-        {
+            #define KJF_OUT(j, i, v)
+            {
 #include "kin_gen_phase1.inc"
 #if KCOLL
-            if (KSTALE && KGRADS) {
-                #pragma unroll
-                for (int i = 0; i < 3 * KND; ++i) stale0[i * BS] = real(0);   // jac = zeros(3, n_dof), collision.jl:76
-            }
-            real *Vp0 = reinterpret_cast<real *>(A.vals_out) + KREC_BASE(KS);
-            real *Gp0 = reinterpret_cast<real *>(A.grads_out) + KREC_BASE((long long)KND * KS);
-            int32_t *Ap0 = KARGMIN ? A.argmin_out + KREC_BASE(KS) : nullptr;
-            #define KP2ARGS tb, n_box, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, es
+                if (KSTALE && KGRADS) {
+                    #pragma unroll
+                    for (int i = 0; i < 3 * KND; ++i) stale0[i * BS] = real(0);   // jac = zeros(3, n_dof), collision.jl:76
+                }
+                real *Vp0 = reinterpret_cast<real *>(A.vals_out) + KREC_BASE(KS);
+                real *Gp0 = reinterpret_cast<real *>(A.grads_out) + KREC_BASE((long long)KND * KS);
+                int32_t *Ap0 = KARGMIN ? A.argmin_out + KREC_BASE(KS) : nullptr;
+                #define KP2ARGS tb, n_box, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, es
 #include "kin_gen_phase2.inc"
 #endif
+            }
+#if KQB > 0
+        }
+        __syncthreads();                                      // the batch buffer is refilled two iterations later
+    }
+#else
+            #pragma unroll
+            for (int c = 0; c < KND; ++c) qcur[c] = qnxt[c];
         }
     }
+#endif
 }
 #endif

@@ -20,8 +20,25 @@ extern const char _binary_kin_gen_skeleton_cuh_start[], _binary_kin_gen_skeleton
 
 namespace kin {
 
-std::string embedded_device_math() { return std::string(_binary_kin_device_math_cuh_start, _binary_kin_device_math_cuh_end); }
-std::string embedded_gen_skeleton() { return std::string(_binary_kin_gen_skeleton_cuh_start, _binary_kin_gen_skeleton_cuh_end); }
+// development aid: KIN_JIT_SRC_DIR=<csrc directory> reads the two texts from disk instead of the embedded copies
+static bool read_override(const char *name, std::string &out) {
+    const char *d = std::getenv("KIN_JIT_SRC_DIR");
+    if (!d || !*d) return false;
+    std::ifstream f(std::string(d) + "/" + name, std::ios::binary);
+    if (!f) return false;
+    out.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+    return true;
+}
+std::string embedded_device_math() {
+    std::string s;
+    if (read_override("kin_device_math.cuh", s)) return s;
+    return std::string(_binary_kin_device_math_cuh_start, _binary_kin_device_math_cuh_end);
+}
+std::string embedded_gen_skeleton() {
+    std::string s;
+    if (read_override("kin_gen_skeleton.cuh", s)) return s;
+    return std::string(_binary_kin_gen_skeleton_cuh_start, _binary_kin_gen_skeleton_cuh_end);
+}
 
 namespace {
 

@@ -58,17 +58,6 @@ struct KernelArgs {
     void *ws_ring;               // kin_eval_ws_kernel only: global hand-over ring (kin_kernels_ws.cuh)
 };
 
-// cp.async of one element global -> shared (LDGSTS): the next tile's configuration lands in the scratch
-// while the current tile is being computed
-__device__ __forceinline__ void cp_async_elem(double *smem_dst, const double *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_elem(float *smem_dst, const float *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // AoS layout only.  A thread owns one record, so a plain store of component k by 32 lanes hits 32
 // different sectors.  Instead the warp stages R values per lane in a warp-private shared buffer
 // ([k][33] padded) and writes the 32 x R block with the lanes running ALONG the records: consecutive

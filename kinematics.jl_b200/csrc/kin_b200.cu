@@ -326,19 +326,22 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
     o.ws = false;
     // residency: the collision phase holds the joint frames in registers (up to 255 per thread: 2 x 128 threads per
     // SM); the FK / Jacobian-only kernel needs far fewer
-    o.block = (int)env_ll("KIN_JIT_BLOCK", o.coll ? 128 : 256);
+    o.block = (int)env_ll("KIN_JIT_BLOCK", 128);
     o.min_blocks = (int)env_ll("KIN_JIT_MINB", o.coll ? 2 : 1);
     // input batching (kin_gen_skeleton.cuh): the FK / Jacobian-only kernels are bound by the DRAM write path and use
     // no other shared memory, so the configurations of as many tiles as fit twice in ~200 KB are fetched per batch
     // behind a grid-wide barrier (one CTA per SM, cooperative launch)
     o.qbatch = 0;
-    if (!o.coll && h.n_dof > 0 && !std::getenv("KIN_JIT_NO_QBATCH")) {
+    if (h.n_dof > 0 && !std::getenv("KIN_JIT_NO_QBATCH")) {
         const size_t rs = o.precision ? sizeof(float) : sizeof(double);
         const size_t budget = std::min<size_t>((size_t)(m ? m->dev_smem : 227 * 1024), 200 * 1024);
+        // measured (profiles/sweep_jit.py, 2^24 configurations): 128 threads x 12 tiles per batch, one CTA per SM:
+        // 8.72 -> 7.78 ms (0.84 -> 0.94 of the HBM peak); the collision kernels need their shared memory for the
+        // per-configuration scratch and are not write-bound: no batching there unless asked for (KIN_JIT_QBATCH_COLL)
         long long qb = (long long)(budget / (2 * (size_t)h.n_dof * o.block * rs));
         qb = std::min<long long>(qb, 16);
-        qb = env_ll("KIN_JIT_QBATCH", qb);
-        if (qb >= 2) { o.qbatch = (int)qb; o.min_blocks = 1; }
+        qb = o.coll ? env_ll("KIN_JIT_QBATCH_COLL", 0) : env_ll("KIN_JIT_QBATCH", qb);
+        if (qb >= 1 && (qb >= 2 || o.coll)) { o.qbatch = (int)qb; o.min_blocks = 1; }
     }
     return o;
 }

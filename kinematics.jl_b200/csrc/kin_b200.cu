@@ -324,14 +324,23 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
     o.want_argmin = o.coll && c->argmin_out != nullptr;
     o.stale = o.want_grads && c->scratch_mode == KIN_SCRATCH_REFERENCE;
     o.ws = false;
-    // residency: the collision phase holds the joint frames in registers (up to 255 per thread: 2 x 128 threads per
-    // SM); the FK / Jacobian-only kernel needs far fewer
-    o.block = (int)env_ll("KIN_JIT_BLOCK", 128);
-    o.min_blocks = (int)env_ll("KIN_JIT_MINB", o.coll ? 2 : 1);
+    // Launch shape and code-shape switches, from the sweeps in profiles/ (sweep_jit.py; ms per 2^22 fused configurations):
+    //   collision, SoA:   128 threads x 2 CTAs/SM with a CTA-wide barrier after every node of the straight-line phase 1
+    //                     (the warps of a CTA then share instruction fetches: the fused kernel is 90 KB of code, far
+    //                     beyond the instruction cache) and 32-bit component strides: 3.68 -> 3.13
+    //   collision, tiled: 256 threads x 1 CTA/SM, no barriers: 3.11
+    //   FK / Jacobian only: 128 threads x 1 CTA/SM + input batching (below)
+    const bool tiled = c->layout == KIN_LAYOUT_TILED32;
+    o.block = (int)env_ll("KIN_JIT_BLOCK", (o.coll && tiled) ? 256 : 128);
+    o.min_blocks = (int)env_ll("KIN_JIT_MINB", o.coll ? (tiled ? 1 : 2) : 1);
+    o.grad_mode = o.want_grads ? c->grad_mode : -1;
+    o.fd_cold = (int)env_ll("KIN_JIT_FD_COLD", 0);
+    o.ksync = (int)env_ll("KIN_JIT_KSYNC", (o.coll && !tiled) ? 1 : 0);
+    o.es32 = (o.layout == KIN_LAYOUT_SOA && (c->batch_stride ? c->batch_stride : c->n) < (1ll << 32)) ? (int)env_ll("KIN_JIT_ES32", 1) : 0;
+    o.qbatch = 0;
     // input batching (kin_gen_skeleton.cuh): the FK / Jacobian-only kernels are bound by the DRAM write path and use
     // no other shared memory, so the configurations of as many tiles as fit twice in ~200 KB are fetched per batch
     // behind a grid-wide barrier (one CTA per SM, cooperative launch)
-    o.qbatch = 0;
     if (h.n_dof > 0 && !std::getenv("KIN_JIT_NO_QBATCH")) {
         const size_t rs = o.precision ? sizeof(float) : sizeof(double);
         const size_t budget = std::min<size_t>((size_t)(m ? m->dev_smem : 227 * 1024), 200 * 1024);

@@ -10,8 +10,9 @@ namespace kin {
 
 std::string GenOptions::key() const {
     char b[160];
-    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d", precision, layout, (int)want_T, (int)want_J,
-                  (int)coll, with_rot, rpy_jac, keep_irrelevant, (int)want_grads, (int)want_argmin, (int)stale, (int)ws, block, min_blocks, qbatch);
+    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d", precision, layout, (int)want_T, (int)want_J,
+                  (int)coll, with_rot, rpy_jac, keep_irrelevant, (int)want_grads, (int)want_argmin, (int)stale, (int)ws, block, min_blocks, qbatch,
+                  ksync, es32, grad_mode, fd_cold);
     return b;
 }
 
@@ -232,6 +233,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
             if ((int)saved.size() <= ni[4]) saved.resize(ni[4] + 1);
             saved[ni[4]] = T;
         }
+        if (o.ksync) E.os << "KSYNC();\n";
 
         // ---- requested links hanging from this node ----
         for (int a = ni[5]; a < ni[6]; ++a) {
@@ -324,26 +326,49 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
             p2 << (j + 1 < ND ? ",\n" : "\n");
         }
         p2 << "};\n#endif\n";
-        int sb = 0;
-        while (sb < S) {
+        // runs of consecutive spheres with equal relevance mask; groups of up to SPH_GROUP spheres inside a run
+        struct Run { int sb, se; unsigned mask; };
+        std::vector<Run> runs;
+        for (int sb = 0; sb < S;) {
             const unsigned mask = (unsigned)I[h.io_sph_mask + sb];
             int se = sb + 1;
             while (se < S && (unsigned)I[h.io_sph_mask + se] == mask) ++se;
-            p2 << "phase2_run<real, KND, 0x" << std::hex << mask << std::dec << "u>(" << sb << ", " << se << ", KP2ARGS);\n";
+            runs.push_back({sb, se, mask});
             sb = se;
         }
+        // distinct masks share one instantiation of phase 2b
+        std::vector<unsigned> masks;
+        for (const Run &r : runs) {
+            bool seen = false;
+            for (unsigned mk : masks) seen |= mk == r.mask;
+            if (!seen) masks.push_back(r.mask);
+        }
+        p2 << "#pragma unroll 1\nfor (int s0 = 0; s0 < KS;) {\n    int se, mi;\n";
+        for (size_t r = 0; r < runs.size(); ++r) {
+            size_t mi = 0;
+            while (masks[mi] != runs[r].mask) ++mi;
+            p2 << "    " << (r ? "else " : "") << (r + 1 < runs.size() ? "if (s0 < " + std::to_string(runs[r].se) + ") " : "") << "{ se = " << runs[r].se
+               << "; mi = " << mi << "; }\n";
+        }
+        p2 << "    const int ge = min(s0 + SPH_GROUP, se);\n    phase2a_group<real>(s0, ge, KP2AARGS);\n    switch (mi) {\n";
+        for (size_t mi = 0; mi < masks.size(); ++mi)
+            p2 << "        case " << mi << ": phase2b_group<real, KND, 0x" << std::hex << masks[mi] << std::dec << "u>(s0, ge, KP2BARGS); break;\n";
+        p2 << "        default: break;\n    }\n    s0 = ge;\n}\n";
     }
     out.phase2 = p2.str();
 
     // ------------------------------------------------------------------ constants of the model + options
     std::ostringstream c;
     c << "#define KREAL " << (f32 ? "float" : "double") << "\n";
+    if (o.fd_cold) c << "#define KIN_FD_COLD 1\n";
     c << "#define KWANT_T " << (o.want_T ? 1 : 0) << "\n#define KWANT_J " << (o.want_J ? 1 : 0) << "\n#define KCOLL " << (o.coll ? 1 : 0)
       << "\n#define KTILED " << (o.layout == 2 ? 1 : 0) << "\n#define KWS " << (o.ws ? 1 : 0) << "\n";
-    c << "#define KBS " << o.block << "\n#define KMINB " << o.min_blocks << "\n#define KQB " << o.qbatch << "\n";
+    c << "#define KBS " << o.block << "\n#define KMINB " << o.min_blocks << "\n#define KQB " << o.qbatch << "\n#define KSYNC_ON "
+      << o.ksync << "\n#define KES32 " << o.es32 << "\n";
     c << "namespace kin {\n";
     c << "constexpr int KND = " << ND << ", KDC = " << DC << ", KS = " << S << ", KNFK = " << (o.want_T ? h.n_fk : 0) << ", KNJAC = "
       << (o.want_J ? h.n_jac : 0) << ", KROWS = " << rows << ";\n";
+    c << "constexpr int KGRADMODE = " << o.grad_mode << ";\n";
     c << "constexpr unsigned KREV = 0x" << std::hex << rev_mask << std::dec << "u;\n";
     c << "constexpr bool KSTALE = " << (o.stale ? "true" : "false") << ", KGRADS = " << (o.want_grads ? "true" : "false") << ", KARGMIN = "
       << (o.want_argmin ? "true" : "false") << ";\n";

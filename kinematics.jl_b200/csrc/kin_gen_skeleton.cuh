@@ -13,92 +13,95 @@ namespace kin {
 
 typedef KREAL real;
 
-// ---- phase 2 for the spheres [sb, se), which all have the relevance mask MASK: the code of kin_eval_kernel with
-//      the mask, the column count / types and the scratch / gradient / argmin switches as compile-time constants ----
+// ---- phase 2, as in kin_eval_kernel but split so that the code that does not depend on the relevance mask exists
+//      once: 2a (union SDF of a group of up to SPH_GROUP spheres; sdf.jl:108-114) is shared, 2b (value, truncation,
+//      gradient, chain rule: collision.jl:78-93) is instantiated per mask, with the mask, the column count / types and
+//      the scratch / gradient / argmin switches as compile-time constants ----
+template <typename real_>
+__device__ __forceinline__ void phase2a_group(const int s0, const int ge, const real_ *__restrict__ tb, const int n_box,
+                                              const real_ *cent0, real_ *hand) {
+    typedef real_ real;
+    constexpr int BS = KBS;
+    real px[SPH_GROUP], py[SPH_GROUP], pz[SPH_GROUP], kmin[SPH_GROUP];
+    int kidx[SPH_GROUP];
+    #pragma unroll
+    for (int g = 0; g < SPH_GROUP; ++g) {
+        const real *cs = cent0 + 3 * min(s0 + g, ge - 1) * BS;
+        px[g] = cs[0]; py[g] = cs[BS]; pz[g] = cs[2 * BS];
+        kmin[g] = CUDART_INF; kidx[g] = 0;
+    }
+    #pragma unroll 1
+    for (int b = 0; b < n_box; ++b) {         // UnionSDF: all boxes, first minimum wins (sdf.jl:108-114)
+        BoxRow<real> row;
+        load_box(tb + b * BOX_REALS, row);
+        real key[SPH_GROUP], qx[SPH_GROUP], qy[SPH_GROUP], qz[SPH_GROUP];
+        bool any_inside = false;
+        #pragma unroll
+        for (int g = 0; g < SPH_GROUP; ++g) {
+            key[g] = box_key_outside(row, px[g], py[g], pz[g], qx[g], qy[g], qz[g]);
+            any_inside |= !(key[g] > real(0));
+        }
+        if (any_inside) {
+            #pragma unroll
+            for (int g = 0; g < SPH_GROUP; ++g)
+                if (!(key[g] > real(0))) key[g] = box_inside_key(qx[g], qy[g], qz[g]);
+        }
+        #pragma unroll
+        for (int g = 0; g < SPH_GROUP; ++g)
+            if (key[g] < kmin[g]) { kmin[g] = key[g]; kidx[g] = b; }
+    }
+    #pragma unroll
+    for (int g = 0; g < SPH_GROUP; ++g) {
+        hand[g * BS] = key_to_dist(kmin[g]);
+        reinterpret_cast<int *>(&hand[(SPH_GROUP + g) * BS])[0] = kidx[g];
+    }
+}
+
+// per sphere, IN sphere order (the shared scratch of collision.jl:76,90 makes the order observable)
 template <typename real_, int ND, unsigned MASK>
-__device__ __forceinline__ void phase2_run(const int sb, const int se, const real_ *__restrict__ tb, const int n_box,
-                                           const real_ *__restrict__ rad, const real_ *cent0, real_ *stale0, real_ *hand,
-                                           const JFrame<real_> (&jfr)[ND > 0 ? ND : 1], const int grad_mode, const real_ trunc,
-                                           const real_ voff, real_ *Vp0, real_ *Gp0, int32_t *Ap0, const size_t es) {
+__device__ __forceinline__ void phase2b_group(const int s0, const int ge, const real_ *__restrict__ tb,
+                                              const real_ *__restrict__ rad, const real_ *cent0, real_ *stale0, const real_ *hand,
+                                              const JFrame<real_> (&jfr)[ND > 0 ? ND : 1], const int grad_mode, const real_ trunc,
+                                              const real_ voff, real_ *Vp0, real_ *Gp0, int32_t *Ap0, const size_t es) {
     typedef real_ real;
     constexpr int BS = KBS;
     #pragma unroll 1
-    for (int s0 = sb; s0 < se; s0 += SPH_GROUP) {
-        // ---- 2a: distances of SPH_GROUP spheres; one box-table row feeds all of them ----
-        {
-            real px[SPH_GROUP], py[SPH_GROUP], pz[SPH_GROUP], kmin[SPH_GROUP];
-            int kidx[SPH_GROUP];
+    for (int s = s0; s < ge; ++s) {
+        const int g = s - s0;
+        const real dmin = hand[g * BS];
+        const int kmin = reinterpret_cast<const int *>(&hand[(SPH_GROUP + g) * BS])[0];
+        const real dist0 = dmin - rad[s];
+        const bool truncated = dist0 > trunc;
+        __stcs(Vp0 + (size_t)s * es, (truncated ? trunc : dist0) - voff);
+        if (KARGMIN) __stcs(Ap0 + (size_t)s * es, kmin + 1);
+        if (!KGRADS) continue;
+        real *Gp = Gp0 + (size_t)s * ND * es;
+        if (truncated) {            // collision.jl:84-86
             #pragma unroll
-            for (int g = 0; g < SPH_GROUP; ++g) {
-                const real *cs = cent0 + 3 * min(s0 + g, se - 1) * BS;
-                px[g] = cs[0]; py[g] = cs[BS]; pz[g] = cs[2 * BS];
-                kmin[g] = CUDART_INF; kidx[g] = 0;
-            }
-            #pragma unroll 1
-            for (int b = 0; b < n_box; ++b) {         // UnionSDF: all boxes, first minimum wins (sdf.jl:108-114)
-                BoxRow<real> row;
-                load_box(tb + b * BOX_REALS, row);
-                real key[SPH_GROUP], qx[SPH_GROUP], qy[SPH_GROUP], qz[SPH_GROUP];
-                bool any_inside = false;
-                #pragma unroll
-                for (int g = 0; g < SPH_GROUP; ++g) {
-                    key[g] = box_key_outside(row, px[g], py[g], pz[g], qx[g], qy[g], qz[g]);
-                    any_inside |= !(key[g] > real(0));
-                }
-                if (any_inside) {
-                    #pragma unroll
-                    for (int g = 0; g < SPH_GROUP; ++g)
-                        if (!(key[g] > real(0))) key[g] = box_inside_key(qx[g], qy[g], qz[g]);
-                }
-                #pragma unroll
-                for (int g = 0; g < SPH_GROUP; ++g)
-                    if (key[g] < kmin[g]) { kmin[g] = key[g]; kidx[g] = b; }
-            }
-            #pragma unroll
-            for (int g = 0; g < SPH_GROUP; ++g) {
-                hand[g * BS] = key_to_dist(kmin[g]);
-                reinterpret_cast<int *>(&hand[(SPH_GROUP + g) * BS])[0] = kidx[g];
-            }
+            for (int j = 0; j < ND; ++j) __stcs(&Gp[(size_t)j * es], real(0));
+            continue;
         }
-        // ---- 2b: per sphere, IN sphere order (the shared scratch of collision.jl:76,90 makes the order observable) ----
-        #pragma unroll 1
-        for (int g = 0; g < SPH_GROUP && s0 + g < se; ++g) {
-            const int s = s0 + g;
-            const real dmin = hand[g * BS];
-            const int kmin = reinterpret_cast<const int *>(&hand[(SPH_GROUP + g) * BS])[0];
-            const real dist0 = dmin - rad[s];
-            const bool truncated = dist0 > trunc;
-            __stcs(Vp0 + (size_t)s * es, (truncated ? trunc : dist0) - voff);
-            if (KARGMIN) __stcs(Ap0 + (size_t)s * es, kmin + 1);
-            if (!KGRADS) continue;
-            real *Gp = Gp0 + (size_t)s * ND * es;
-            if (truncated) {            // collision.jl:84-86
-                #pragma unroll
-                for (int j = 0; j < ND; ++j) __stcs(&Gp[(size_t)j * es], real(0));
-                continue;
-            }
-            const real *cs = cent0 + 3 * s * BS;
-            const real px = cs[0], py = cs[BS], pz = cs[2 * BS];
-            real grad[3];
-            {
-                BoxRow<real> row;
-                load_box(tb + kmin * BOX_REALS, row);
-                box_gradient(row, grad_mode, px, py, pz, dmin, grad);
-            }
-            #pragma unroll
-            for (int j = 0; j < ND; ++j) {
-                real *st = stale0 + 3 * j * BS;
-                if ((MASK >> j) & 1u) {       // joint_jacobian!, algorithm.jl:65-81
-                    real cx, cy, cz;
-                    jac_col(jfr[j], ((KREV >> j) & 1u) != 0, px, py, pz, cx, cy, cz);
-                    if (KSTALE) { st[0] = cx; st[BS] = cy; st[2 * BS] = cz; }
-                    __stcs(&Gp[(size_t)j * es], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));   // transpose(grad) * jac
-                } else if (KSTALE) {          // column left over from an earlier sphere (collision.jl:76,90)
-                    const real cx = st[0], cy = st[BS], cz = st[2 * BS];
-                    __stcs(&Gp[(size_t)j * es], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));
-                } else {
-                    __stcs(&Gp[(size_t)j * es], real(0));      // a zero column (clean scratch): transpose(grad) * 0
-                }
+        const real *cs = cent0 + 3 * s * BS;
+        const real px = cs[0], py = cs[BS], pz = cs[2 * BS];
+        real grad[3];
+        {
+            BoxRow<real> row;
+            load_box(tb + kmin * BOX_REALS, row);
+            box_gradient(row, KGRADMODE >= 0 ? KGRADMODE : grad_mode, px, py, pz, dmin, grad);
+        }
+        #pragma unroll
+        for (int j = 0; j < ND; ++j) {
+            real *st = stale0 + 3 * j * BS;
+            if ((MASK >> j) & 1u) {       // joint_jacobian!, algorithm.jl:65-81
+                real cx, cy, cz;
+                jac_col(jfr[j], ((KREV >> j) & 1u) != 0, px, py, pz, cx, cy, cz);
+                if (KSTALE) { st[0] = cx; st[BS] = cy; st[2 * BS] = cz; }
+                __stcs(&Gp[(size_t)j * es], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));   // transpose(grad) * jac
+            } else if (KSTALE) {          // column left over from an earlier sphere (collision.jl:76,90)
+                const real cx = st[0], cy = st[BS], cz = st[2 * BS];
+                __stcs(&Gp[(size_t)j * es], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));
+            } else {
+                __stcs(&Gp[(size_t)j * es], real(0));      // a zero column (clean scratch): transpose(grad) * 0
             }
         }
     }
@@ -171,6 +174,19 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
     const real trunc = (real)A.truncation_dist, voff = (real)A.vals_offset;
 #endif
     const size_t es = KTILED ? size_t(32) : (size_t)A.ld;
+#if KES32 && !KTILED
+    // the component stride as a 32-bit value: address = base + es32 * (8 k) is ONE 32 x 32 -> 64-bit multiply-add per
+    // store (IMAD.WIDE.U32 with the immediate 8 k) instead of a 64-bit multiply
+    const unsigned es32 = (unsigned)A.ld;
+    #define KOFF(k) ((unsigned long long)es32 * (unsigned)(k))
+#else
+    #define KOFF(k) ((size_t)(k) * es)
+#endif
+#if KSYNC_ON
+    #define KSYNC() __syncthreads()
+#else
+    #define KSYNC()
+#endif
     const long long n_tiles = (A.n + BS - 1) / BS;
     auto q_ptr = [&](long long tile_) {
         const long long n_ = min(tile_ * BS + tid, (long long)A.n - 1);
@@ -233,13 +249,13 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
             #define KREC_BASE(rec) (KTILED ? (n >> 5) * ((long long)(rec) * 32) + (n & 31) : n)
 #if KWANT_T
             real *Tn = reinterpret_cast<real *>(A.T_out) + KREC_BASE(12 * KNFK);
-            #define KST_T(k, v) __stcs(Tn + (size_t)(k) * es, (v))
+            #define KST_T(k, v) __stcs(Tn + KOFF(k), (v))
 #else
             #define KST_T(k, v)
 #endif
 #if KWANT_J
             real *Jn = reinterpret_cast<real *>(A.J_out) + KREC_BASE(KROWS * KND * KNJAC);
-            #define KST_J(k, v) __stcs(Jn + (size_t)(k) * es, (v))
+            #define KST_J(k, v) __stcs(Jn + KOFF(k), (v))
 #else
             #define KST_J(k, v)
 #endif
@@ -259,7 +275,8 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
                 real *Vp0 = reinterpret_cast<real *>(A.vals_out) + KREC_BASE(KS);
                 real *Gp0 = reinterpret_cast<real *>(A.grads_out) + KREC_BASE((long long)KND * KS);
                 int32_t *Ap0 = KARGMIN ? A.argmin_out + KREC_BASE(KS) : nullptr;
-                #define KP2ARGS tb, n_box, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, es
+                #define KP2AARGS tb, n_box, cent0, hand
+                #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, es
 #include "kin_gen_phase2.inc"
 #endif
             }

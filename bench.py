@@ -546,10 +546,16 @@ def main():
         q0 = torch.tensor([0.2, 0, 0, 0, 0.5, 0, 0.5, 0], device=dev, dtype=torch.float64).repeat(Nik, 1)
         K.set_joint_angles(m, joints, q0)
         ms_it, _ = ev_time(lambda: K.pose_constraint(m, gl, joints, tg, True), 5)
-        K.inverse_kinematics_batch(m, gl, joints, tg[:4096], q0[:4096], with_rot=True, iters=40)      # warm-up
+        K.inverse_kinematics_batch(m, gl, joints, tg[:4096], q0[:4096], with_rot=True, iters=40, restarts=2)      # warm-up (builds the kernel)
         barrier()
         t0 = time.perf_counter()
         qsol, fsol = K.inverse_kinematics_batch(m, gl, joints, tg, q0, with_rot=True, iters=40)
+        torch.cuda.synchronize(dev)
+        t_single = max_over_ranks(time.perf_counter() - t0)
+        ok_single = float((fsol < 1e-6).double().mean())
+        barrier()
+        t0 = time.perf_counter()
+        qsol, fsol = K.inverse_kinematics_batch(m, gl, joints, tg, q0, with_rot=True, iters=40, restarts=2)
         torch.cuda.synchronize(dev)
         t_solve = max_over_ranks(time.perf_counter() - t0)
         K.set_joint_angles(m, joints, qsol)
@@ -557,7 +563,10 @@ def main():
         vv[:, 3:] = torch.remainder(vv[:, 3:] + np.pi, 2 * np.pi) - np.pi
         ok = float((vv.abs().amax(dim=1) < 1e-3).double().mean())
         row4 = {"residual_and_jacobian_evals_per_s": world * Nik / (ms_it * 1e-3), "ms_per_evaluation": ms_it,
-                "solve_seconds_40_lm_iterations": t_solve, "targets_per_s": world * Nik / t_solve,
+                "solver": "kin_ik_solve: device-resident Levenberg-Marquardt, 40 iterations per solve, one kernel launch per solve; "
+                          "problems above the tolerance are re-seeded twice",
+                "solve_seconds_one_solve": t_single, "fraction_f_below_1e-6_one_solve": ok_single,
+                "solve_seconds_with_2_restarts": t_solve, "targets_per_s": world * Nik / t_solve,
                 "solve_over_40_evaluations": t_solve / (40 * ms_it * 1e-3), "fraction_within_1e-3": ok, "n_gpus": world}
         if not args.no_e2e:
             tgh = torch.empty(tg.shape, dtype=torch.float64).pin_memory()
@@ -566,7 +575,7 @@ def main():
             barrier()
             t0 = time.perf_counter()
             tgd = tgh.to(dev, non_blocking=True)
-            q_e, _ = K.inverse_kinematics_batch(m, gl, joints, tgd, q0, with_rot=True, iters=40)
+            q_e, _ = K.inverse_kinematics_batch(m, gl, joints, tgd, q0, with_rot=True, iters=40, restarts=2)
             qh_.copy_(q_e, non_blocking=True)
             torch.cuda.synchronize(dev)
             dt4 = max_over_ranks(time.perf_counter() - t0)

@@ -67,7 +67,8 @@ typedef enum {
     KIN_ERR_CUDA = -2,
     KIN_ERR_LIMIT = -3,       /* model exceeds a compiled-in limit (KIN_MAX_*) */
     KIN_ERR_NO_DEVICE = -4,
-    KIN_ERR_ALLOC = -5
+    KIN_ERR_ALLOC = -5,
+    KIN_ERR_UNAVAILABLE = -6  /* the operation needs the run-time compiler (NVRTC) and it is not available */
 } KinStatus;
 
 typedef enum { KIN_F64 = 0, KIN_F32 = 1 } KinPrecision;
@@ -255,6 +256,33 @@ KIN_API int kin_lm_step(int64_t n, int32_t n_dof, int32_t dim, const double *q, 
 KIN_API int kin_lm_accept(int64_t n, int32_t n_dof, int32_t dim, const double *q_try, const double *e_try,
                           const double *J_try, const double *f_try, double *q, double *e, double *J, double *f,
                           double *lambda, void *stream);
+
+/* The whole batched IK solve of config 4 in ONE kernel launch (device-resident loop; no host round trip per
+ * iteration).  One thread per problem runs up to `iters` Levenberg-Marquardt iterations on the reference's objective
+ * f = |[p - p_t; rpy - rpy_t]|^2 (inverse_kinematics.jl:38-50; angle residuals wrapped to (-pi, pi]) with the joint
+ * limits as bounds (inverse_kinematics.jl:52-63: active set + clamping) and stops on its own when f < ftol.  The
+ * kernel is generated for this model / link (straight-line FK + Euler-rate Jacobian, csrc/kin_codegen.cpp) and
+ * compiled with NVRTC on first use; without NVRTC the call returns KIN_ERR_UNAVAILABLE and the caller falls back to
+ * kin_pose_residual + kin_lm_step + kin_lm_accept.  FP64, per-problem contiguous arrays (AoS), DEVICE pointers:
+ * targets[n][6] = x y z roll pitch yaw, q0 / q_out [n][n_dof], f_out[n], iters_out[n] (nullable); lower / upper are
+ * HOST [n_dof] (+-inf allowed, NULL = unbounded).  n_dof <= 12. */
+typedef struct {
+    int64_t n;
+    int32_t link_id;           /* 1-based id of the link to place */
+    int32_t with_rot;          /* 6 residual rows (position + rpy) or 3 */
+    int32_t iters;             /* maximum number of iterations */
+    double ftol;               /* a problem stops when f < ftol */
+    double lambda0;            /* initial damping (<= 0: 1e-2) */
+    const void *targets;
+    const void *q0;
+    const double *lower;
+    const double *upper;
+    void *q_out;
+    void *f_out;
+    int32_t *iters_out;
+    void *stream;
+} KinIkCall;
+KIN_API int kin_ik_solve(KinModel *model, const KinIkCall *call);
 
 /* Diagnostics for bench.py / tests: kernel launches issued by this library since load, and the
  * static resources of the kernel a call would use (registers / thread, dynamic shared memory bytes /

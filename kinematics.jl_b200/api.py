@@ -13,7 +13,7 @@ from .sdf import BoxSDF, UnionSDF
 from .collision import (SweptSphereCollisionChecker, add_coll_links, compute_coll_dists,
                         compute_coll_dists_and_grads)
 
-from .inverse_kinematics import ik_objective, inverse_kinematics, inverse_kinematics_batch
+from .inverse_kinematics import ik_objective, ik_solve_device, inverse_kinematics, inverse_kinematics_batch
 from .planning import (ConfigurationConstraint, EqConst, IneqConst, Objective, PoseConstraint, construct_problem,
                        create_straight_trajectory, gather_packed, gather_stacked, nloptize, plan_trajectory, pose_constraint, scipynize,
                        shard_range, smoothness_objective)

@@ -396,8 +396,13 @@ size_t jit_smem(const kin::GenOptions &o, const kin::ProgHeader &h, const JitKer
 
 // Returns the compiled kernel for this call's option set (compiling it on first use), or null when specialisation
 // is unavailable for it (NVRTC missing, compile error, does not fit): the caller then uses the interpreting kernels.
+std::shared_ptr<JitKernel> get_jit_with(KinModel *m, DeviceProgram *dp, const kin::GenOptions &o, const char *kernel_name);
+
 std::shared_ptr<JitKernel> get_jit(KinModel *m, const KinCall *c, DeviceProgram *dp) {
-    const kin::GenOptions o = gen_options(m, c, dp);
+    return get_jit_with(m, dp, gen_options(m, c, dp), "kin_gen_kernel");
+}
+
+std::shared_ptr<JitKernel> get_jit_with(KinModel *m, DeviceProgram *dp, const kin::GenOptions &o, const char *kernel_name) {
     const std::string key = o.key();
     std::lock_guard<std::mutex> lock(dp->jit_mu);
     auto it = dp->jit.find(key);
@@ -418,7 +423,7 @@ std::shared_ptr<JitKernel> get_jit(KinModel *m, const KinCall *c, DeviceProgram 
     k->from_cache = cached;
     (cached ? g_jit_cache_hits : g_jit_compiles).fetch_add(1);
     cudaError_t e = cudaLibraryLoadData(&k->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kern, k->lib, "kin_gen_kernel");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kern, k->lib, kernel_name);
     cudaFuncAttributes fa;
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, (const void *)k->kern);
     if (e != cudaSuccess) {
@@ -593,7 +598,10 @@ int kin_codegen_dump(const KinModelDesc *d, const KinCall *c, int32_t compile, c
     DeviceProgram dp;
     std::string err;
     if (!kin::compile_program(hm, fk, jac, want_coll, want_stale, kin::JF_REGS, dp.prog, err)) return fail(KIN_ERR_INVALID_ARGUMENT, err);
-    const kin::GenOptions o = gen_options(nullptr, c, &dp);
+    kin::GenOptions o = gen_options(nullptr, c, &dp);
+    if (std::getenv("KIN_DUMP_IK")) {          // development aid: the batched-IK kernel of this link instead
+        o.ik = 1; o.rpy_jac = o.with_rot; o.qbatch = 0; o.ksync = 0; o.coll = false; o.block = 128; o.min_blocks = 1;
+    }
     kin::GenSource g;
     if (!kin::generate_source(dp.prog, o, g, err)) return fail(KIN_ERR_INVALID_ARGUMENT, "codegen: " + err);
     const std::string dir(out_dir);
@@ -967,6 +975,47 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
                       void *jac_out, void *stream_) {
     return kin_pose_residual_multi(m, precision, layout, q, n, 1, &link_id, &with_rot, target, target_per_config, mode,
                                    val_out, jac_out, stream_);
+}
+
+int kin_ik_solve(KinModel *m, const KinIkCall *c) {
+    if (!m || !c) return fail(KIN_ERR_INVALID_ARGUMENT, "null model or call");
+    if (c->n < 0 || (c->n > 0 && (!c->targets || !c->q0 || !c->q_out || !c->f_out))) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
+    if (c->iters < 0) return fail(KIN_ERR_INVALID_ARGUMENT, "negative iteration count");
+    const int nd = m->hm.n_dof();
+    if (nd < 1 || nd > 12) return fail(KIN_ERR_LIMIT, "kin_ik_solve: 1..12 configuration columns (use kin_lm_step / kin_lm_accept beyond)");
+    if (c->link_id < 1 || c->link_id > m->hm.n_links) return fail(KIN_ERR_INVALID_ARGUMENT, "link id out of range");
+    if (c->n == 0) return KIN_OK;
+    if (std::getenv("KIN_DISABLE_JIT")) return fail(KIN_ERR_UNAVAILABLE, "kin_ik_solve needs the run-time compiler (KIN_DISABLE_JIT is set)");
+    DeviceGuard guard(m->device);
+    // the program of (this link's transform + its Euler-rate Jacobian)
+    KinCall pc;
+    std::memset(&pc, 0, sizeof pc);
+    pc.precision = KIN_F64; pc.layout = KIN_LAYOUT_SOA; pc.n = c->n; pc.q = c->q0;
+    pc.n_fk_links = 1; pc.fk_links = &c->link_id; pc.T_out = (void *)c->q_out;
+    pc.n_jac_links = 1; pc.jac_links = &c->link_id; pc.J_out = (void *)c->q_out; pc.with_rot = c->with_rot ? 1 : 0; pc.rpy_jac = 1;
+    pc.truncation_dist = INFINITY;
+    std::shared_ptr<DeviceProgram> dp;
+    int rc = get_program(m, &pc, dp);
+    if (rc != KIN_OK) return rc;
+    kin::GenOptions o;
+    o.precision = 0; o.layout = 0; o.want_T = true; o.want_J = true; o.with_rot = pc.with_rot; o.rpy_jac = 1;
+    o.ik = 1; o.block = (int)env_ll("KIN_IK_BLOCK", 128); o.min_blocks = (int)env_ll("KIN_IK_MINB", 1);
+    std::shared_ptr<JitKernel> k = get_jit_with(m, dp.get(), o, "kin_ik_kernel");
+    if (!k) return fail(KIN_ERR_UNAVAILABLE, std::string("kin_ik_solve: the specialised kernel could not be built: ") + kin::jit_status());
+    kin::IkArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.targets = c->targets; a.q0 = c->q0; a.q_out = c->q_out; a.f_out = c->f_out; a.iters_out = c->iters_out;
+    a.n = c->n; a.iters = c->iters; a.ftol = c->ftol; a.lambda0 = c->lambda0 > 0 ? c->lambda0 : 1e-2;
+    for (int j = 0; j < nd; ++j) {
+        a.lo[j] = c->lower ? c->lower[j] : -INFINITY;
+        a.hi[j] = c->upper ? c->upper[j] : INFINITY;
+    }
+    void *args[] = {&a};
+    const long long grid = (c->n + k->block - 1) / k->block;
+    CUDA_TRY(cudaLaunchKernel((const void *)k->kern, dim3((unsigned)grid), dim3((unsigned)k->block), args, 0, (cudaStream_t)c->stream));
+    g_launches.fetch_add(1);
+    g_jit_launches.fetch_add(1);
+    return KIN_OK;
 }
 
 int kin_lm_step(int64_t n, int32_t n_dof, int32_t dim, const double *q, const double *e, const double *J,

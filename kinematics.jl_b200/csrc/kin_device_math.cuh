@@ -319,6 +319,19 @@ struct GenArgs {
     double truncation_dist, vals_offset;
 };
 
+// Kernel parameter of the generated batched-IK kernel (kin_gen_skeleton.cuh: kin_ik_kernel).
+struct IkArgs {
+    const void *targets;         // [n][6]: x y z roll pitch yaw
+    const void *q0;              // [n][n_dof]
+    void *q_out;                 // [n][n_dof]
+    void *f_out;                 // [n] pose objective at q_out
+    int32_t *iters_out;          // [n] iterations used, or null
+    long long n;
+    int iters;
+    double ftol, lambda0;
+    double lo[32], hi[32];       // joint limits per column (+-inf allowed)
+};
+
 // Explicitly rounded single operations (never contracted into an FMA by the compiler): the generated kernels emit
 // every multiplication / addition through these, so that their results are bit-for-bit the ones of the hand-written
 // kernels, where the same operations appear as arguments of fma() (which are never contracted either).

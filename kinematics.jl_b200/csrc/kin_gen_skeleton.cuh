@@ -124,7 +124,155 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
 // sees one read burst per batch (about every 100 us) instead of 4 reads per microsecond.  The probe recovers 5.93 TB/s
 // that way.  The grid is launched cooperatively (all CTAs resident), the barrier words live in A.sync.
 // =====================================================================================================================
-#if !KWS
+#if KIK
+// =====================================================================================================================
+// Batched inverse kinematics (config 4 of BASELINE.json): ONE kernel launch runs the whole damped least-squares solve,
+// one thread per problem.  Per iteration the generated straight-line phase 1 gives the link transform and its
+// Euler-rate Jacobian (the evaluations of f_objective, inverse_kinematics.jl:38-50: e = [p - p_t; rpy - rpy_t],
+// rpy of RotZYX, transform.jl:45-48); the rest is the Levenberg-Marquardt update the host-side driver used to issue as
+// separate launches (kin_lm_step / kin_lm_accept): normal equations H = J'J, g = J'e in registers, joints that sit on
+// a limit and are pushed outward frozen, Cholesky of H + lambda (I + diag H), trial point clamped to the limits
+// (inverse_kinematics.jl:52-63), accept / reject with the damping scaled by 0.3 / 4.  Angle residuals are wrapped to
+// (-pi, pi].  A problem stops on its own when f < ftol.  The reference drives the same evaluations with NLopt SLSQP
+// (third party); this replaces the per-iteration host round trips of a solver callback by a device-resident loop.
+// =====================================================================================================================
+extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_ik_kernel(const __grid_constant__ kin::IkArgs A) {
+    using namespace kin;
+    constexpr int BS = KBS, ND = KND, ROWS = KROWS;
+    const long long n = (long long)blockIdx.x * BS + threadIdx.x;
+    if (n >= A.n) return;
+    const real PI = real(3.14159265358979323846);
+    real q[ND], qt[ND], g[ND], tg[6], H[ND][ND];
+    {
+        const real *q0 = reinterpret_cast<const real *>(A.q0) + n * ND;
+        const real *tp = reinterpret_cast<const real *>(A.targets) + n * 6;
+        #pragma unroll
+        for (int c = 0; c < ND; ++c) { q[c] = q0[c]; qt[c] = q0[c]; g[c] = real(0); }
+        #pragma unroll
+        for (int i = 0; i < 6; ++i) tg[i] = tp[i];
+        #pragma unroll
+        for (int a = 0; a < ND; ++a)
+            #pragma unroll
+            for (int b = 0; b <= a; ++b) H[a][b] = real(0);
+    }
+    real f = CUDART_INF, lam = (real)A.lambda0;
+    int it = 0;
+    #pragma unroll 1
+    for (;; ++it) {
+        // ---- evaluate at qt: link transform Tl (3x4 column-major) and Euler-rate Jacobian Jm[j * ROWS + r] ----
+        real Tl[12], Jm[ROWS * ND];
+        #pragma unroll
+        for (int k = 0; k < ROWS * ND; ++k) Jm[k] = real(0);
+        {
+            #define KQ(c) qt[c]
+            #define KST_T(k, v) Tl[k] = (v)
+            #define KST_J(k, v) Jm[k] = (v)
+            #define KCEN_SET(s, i, v)
+            #define KJF_OUT(j, i, v)
+            #define KSYNC()
+#include "kin_gen_phase1.inc"
+        }
+        real e[ROWS];
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) e[i] = Tl[9 + i] - tg[i];
+        if (ROWS == 6) {   // rpy(T), transform.jl:45-48 (RotZYX): R[r][c] = Tl[c*3 + r]
+            const real yaw = atan2_(Tl[1], Tl[0]);
+            real s1, c1;
+            sincos_(yaw, &s1, &c1);
+            const real pitch = atan2_(-Tl[2], sqrt_(fma_(Tl[5], Tl[5], Tl[8] * Tl[8])));
+            const real roll = atan2_(fma_(Tl[6], s1, -(Tl[7] * c1)), fma_(Tl[4], c1, -(Tl[3] * s1)));
+            const real ang[3] = {roll - tg[3], pitch - tg[4], yaw - tg[5]};
+            #pragma unroll
+            for (int i = 0; i < 3; ++i) {            // wrap to (-pi, pi]
+                real a = ang[i];
+                a = a - real(2) * PI * floor((a + PI) / (real(2) * PI));
+                e[3 + i] = a;
+            }
+        }
+        real ft = real(0);
+        #pragma unroll
+        for (int r = 0; r < ROWS; ++r) ft = fma_(e[r], e[r], ft);
+        const bool ok = ft < f;
+        if (it > 0) {
+            lam *= ok ? real(0.3) : real(4.0);
+            lam = lam < real(1e-9) ? real(1e-9) : (lam > real(1e4) ? real(1e4) : lam);
+        }
+        if (ok) {
+            f = ft;
+            #pragma unroll
+            for (int a = 0; a < ND; ++a) {
+                q[a] = qt[a];
+                real ga = real(0);
+                #pragma unroll
+                for (int r = 0; r < ROWS; ++r) ga = fma_(Jm[a * ROWS + r], e[r], ga);
+                g[a] = ga;
+                #pragma unroll
+                for (int b = 0; b <= a; ++b) {
+                    real hab = real(0);
+                    #pragma unroll
+                    for (int r = 0; r < ROWS; ++r) hab = fma_(Jm[a * ROWS + r], Jm[b * ROWS + r], hab);
+                    H[a][b] = hab;
+                }
+            }
+        }
+        if (f < (real)A.ftol || it >= A.iters) break;
+        // ---- step: active set on the limits, Cholesky of H + lam (I + diag H), qt = clamp(q - x) ----
+        bool fr[ND];
+        real L[ND][ND], x[ND];
+        #pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            const real lo = (real)A.lo[a], hi = (real)A.hi[a];
+            fr[a] = !(((q[a] <= lo + real(1e-12)) && (g[a] > real(0))) || ((q[a] >= hi - real(1e-12)) && (g[a] < real(0))));
+        }
+        #pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            #pragma unroll
+            for (int b = 0; b < a; ++b) L[a][b] = (fr[a] && fr[b]) ? H[a][b] : real(0);
+            L[a][a] = fr[a] ? fma_(lam, real(1) + H[a][a], H[a][a]) : real(1);
+            x[a] = fr[a] ? g[a] : real(0);
+        }
+        #pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            #pragma unroll
+            for (int b = 0; b <= a; ++b) {
+                real sum = L[a][b];
+                #pragma unroll
+                for (int k = 0; k < b; ++k) sum = fma_(-L[a][k], L[b][k], sum);
+                if (a == b) L[a][a] = sqrt_(sum > real(1e-300) ? sum : real(1e-300));
+                else L[a][b] = sum / L[b][b];
+            }
+        }
+        #pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            real sum = x[a];
+            #pragma unroll
+            for (int k = 0; k < a; ++k) sum = fma_(-L[a][k], x[k], sum);
+            x[a] = sum / L[a][a];
+        }
+        #pragma unroll
+        for (int a = ND - 1; a >= 0; --a) {
+            real sum = x[a];
+            #pragma unroll
+            for (int k = a + 1; k < ND; ++k) sum = fma_(-L[k][a], x[k], sum);
+            x[a] = sum / L[a][a];
+        }
+        #pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            const real lo = (real)A.lo[a], hi = (real)A.hi[a];
+            real v = q[a] - x[a];
+            v = v < lo ? lo : (v > hi ? hi : v);
+            qt[a] = v;
+        }
+    }
+    real *qo = reinterpret_cast<real *>(A.q_out) + n * ND;
+    #pragma unroll
+    for (int c = 0; c < ND; ++c) qo[c] = q[c];
+    reinterpret_cast<real *>(A.f_out)[n] = f;
+    if (A.iters_out) A.iters_out[n] = it;
+}
+#endif
+
+#if !KWS && !KIK
 #if KQB > 0
 __device__ __forceinline__ void kin_grid_barrier(unsigned *sync, unsigned n_cta) {
     __syncthreads();

@@ -211,4 +211,4 @@ def test_codegen_and_nvrtc_compile_without_a_gpu(tmp_path):
         assert (out / "kin_gen.cubin").stat().st_size > 10000
         if fused:
             p2 = (out / "kin_gen_phase2.inc").read_text()
-            assert p2.count("phase2_run<") == 4            # wrist / torso / upperarm / elbow: four relevance masks
+            assert p2.count("phase2b_group<") == 4 and p2.count("phase2a_group<") == 1   # four relevance masks, one shared box search

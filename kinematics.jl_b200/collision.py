@@ -20,13 +20,27 @@ class SweptSphereCollisionChecker:         # collision.jl:32-37
         self._parents, self._centers = [], []
 
 
-def add_coll_links(sscc: SweptSphereCollisionChecker, coll_link: Link, centers=None, radii=None):
-    """collision.jl:39-49.  The reference obtains (centers, radius) from scikit-robot's swept-sphere fit
-    of the link's collision mesh (collision.jl:16-30); meshes are not available offline, so the table is
-    passed in (``centers`` (k, 3) in the link frame, ``radii`` scalar or (k,))."""
+def add_coll_links(sscc: SweptSphereCollisionChecker, coll_link: Link, centers=None, radii=None, vertices=None, mesh_dirs=(),
+                   n_sphere=None, tol=0.1):
+    """collision.jl:39-49.  The reference obtains (centers, radius) from scikit-robot's swept-sphere fit of the
+    link's collision mesh (collision.jl:16-30).  Here, in order of precedence:
+      * ``centers`` (k, 3) in the link frame + ``radii`` (scalar or (k,)): an explicit sphere table;
+      * ``vertices`` (n, 3): the fit of swept_sphere.compute_swept_sphere (mesh-free restatement of the algorithm);
+      * otherwise the link's own collision geometry: a box / cylinder / sphere primitive is sampled, a mesh is read
+        from an STL under ``mesh_dirs``; a link without usable geometry adds no spheres, as in the reference
+        (collision.jl:18) -- except that a mesh that cannot be found raises (the meshes of data/fetch.urdf do not
+        ship with the reference)."""
     if centers is None:
-        raise _lib.KinError("add_coll_links: swept-sphere generation from meshes is out of scope (SURVEY 8f-4); "
-                            "pass centers= and radii=")
+        from . import swept_sphere as SS
+        from .mechanism import MeshMetaData
+        if vertices is None:
+            vertices = SS.link_vertices(coll_link, mesh_dirs)
+            if vertices is None:
+                if isinstance(coll_link.geometric_meta_data, MeshMetaData):
+                    raise _lib.KinError("add_coll_links: collision mesh %r of link %r not found (searched %r); pass centers= / radii= "
+                                        "or vertices=" % (coll_link.geometric_meta_data.file_path, coll_link.name, list(mesh_dirs)))
+                return
+        centers, radii = SS.compute_swept_sphere(vertices, n_sphere=n_sphere, tol=tol)
     centers = np.asarray(centers, dtype=np.float64).reshape(-1, 3)
     radii = np.broadcast_to(np.asarray(radii, dtype=np.float64), (len(centers),))
     for c, r in zip(centers, radii):

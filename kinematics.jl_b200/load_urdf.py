@@ -8,7 +8,8 @@ import xml.etree.ElementTree as ET
 
 import numpy as np
 
-from .mechanism import (FIXED, PRISMATIC, REVOLUTE, BoxMetaData, Joint, Link, Mechanism, MeshMetaData)
+from .mechanism import (FIXED, PRISMATIC, REVOLUTE, BoxMetaData, CylinderMetaData, Joint, Link, Mechanism, MeshMetaData,
+                        SphereMetaData)
 from .transform import Transform
 
 
@@ -42,7 +43,16 @@ def _geometry_meta(link_node):             # load_urdf.jl:1-18
     mesh = geom.find("mesh")
     if mesh is not None:
         return MeshMetaData(mesh.get("filename"), _origin(col))
-    return None                            # "primitive type other than box is not supported yet" (:14)
+    # "primitive type other than box is not supported yet" (load_urdf.jl:14): the reference keeps no meta data for
+    # these, so they never become SDFs (sdf.py only takes BoxMetaData); they are kept here only as a vertex source
+    # for the swept-sphere fit (swept_sphere.py)
+    cyl = geom.find("cylinder")
+    if cyl is not None:
+        return CylinderMetaData(float(cyl.get("radius")), float(cyl.get("length")), _origin(col))
+    sph = geom.find("sphere")
+    if sph is not None:
+        return SphereMetaData(float(sph.get("radius")), _origin(col))
+    return None
 
 
 def parse_urdf(urdf_path, with_base=False, robot_type="basic") -> Mechanism:

@@ -20,6 +20,11 @@ class SphereMetaData:                      # mechanism.jl:8-11
         self.radius, self.origin = float(radius), origin
 
 
+class CylinderMetaData:                    # extension: URDF <cylinder> collision primitive (the reference skips it,
+    def __init__(self, radius, length, origin: Transform):     # load_urdf.jl:13-15); only used to fit swept spheres
+        self.radius, self.length, self.origin = float(radius), float(length), origin
+
+
 class MeshMetaData:                        # mechanism.jl:13-16
     def __init__(self, file_path, origin: Transform):
         self.file_path, self.origin = file_path, origin

@@ -82,13 +82,13 @@ def ik_solve_device(m: Mechanism, link, joints, targets, q0, with_rot=True, iter
     ``q0`` (N, n_dof) CUDA tensors -> (q (N, n_dof), f (N,), iterations (N,) int32).  Raises ``KinError`` with code
     ``ERR_UNAVAILABLE`` in the message when the run-time compiler is not available."""
     import torch
-    _check_joints(m, joints)
+    q0 = torch.as_tensor(q0, dtype=torch.float64, device="cuda").contiguous()
+    set_joint_angles(m, joints, q0)            # defines the configuration columns (and the device model) as every caller does
     dm = device_model(m)
     nb = 3 if m.with_base else 0
     lo = np.ascontiguousarray([j.lower_limit for j in joints] + [-np.inf] * nb, dtype=np.float64)
     hi = np.ascontiguousarray([j.upper_limit for j in joints] + [np.inf] * nb, dtype=np.float64)
     tg = torch.as_tensor(targets, dtype=torch.float64, device="cuda").contiguous()
-    q0 = torch.as_tensor(q0, dtype=torch.float64, device="cuda").contiguous()
     N, nd = q0.shape
     assert tg.shape == (N, 6) and nd == dm.n_dof
     q = torch.empty_like(q0)

@@ -445,6 +445,8 @@ def main():
     #      iteration, n_wp = 10..64 per planning iteration): latency of one fused kin_eval, launch to completion ----
     small = {}
     if not args.no_variants:
+        small["note"] = "fused kin_eval (FK all links + gripper Jacobian + collision cost / gradient) of n configurations; after a few small " \
+                        "calls the library switches to its one-warp-per-configuration specialised kernel (negative block size)"
         ld_s = 1024
         Qs_ = Q[:, :ld_s].contiguous()
         Ts_ = torch.empty((N_LINKS * 12, ld_s), dtype=torch.float64, device=dev)
@@ -472,8 +474,9 @@ def main():
                 L.check(lib.kin_eval(dm.h, C.byref(cs)))
                 torch.cuda.synchronize(dev)
             t_sync = (time.perf_counter() - t0) / 50
-            small[str(n_s)] = {"device_us_per_call_back_to_back": 1e3 * a.elapsed_time(b) / reps,
-                               "host_issue_us_per_call": 1e6 * t_issue / reps, "call_plus_sync_us": 1e6 * t_sync}
+            small["n=%d" % n_s] = {"device_us_per_call_back_to_back": 1e3 * a.elapsed_time(b) / reps,
+                               "host_issue_us_per_call": 1e6 * t_issue / reps, "call_plus_sync_us": 1e6 * t_sync,
+                               "launch": launch_info(cs)}
         del Vs, Gs, Qs_, Ts_, Js_
 
     # ---- configs 4 and 5 of BASELINE.json (caller-side rows of SURVEY 8f), through the host mirror ----

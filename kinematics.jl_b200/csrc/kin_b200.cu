@@ -59,6 +59,7 @@ struct DeviceProgram {
     kin::Program prog;
     std::mutex jit_mu;
     std::map<std::string, std::shared_ptr<JitKernel>> jit;
+    std::atomic<int> small_calls{0};     // small-batch launches of this program so far (see jit_wanted)
     int32_t *d_int = nullptr;
     double *d_r64 = nullptr;
     float *d_r32 = nullptr;
@@ -302,7 +303,9 @@ int validate_call(const KinModel *m, const KinCall *c) {
 }
 
 // ---- model-specialised kernels (kin_codegen.hpp / kin_jit.hpp) ----
-constexpr long long kJitMinBatch = 32 * 1024;      // below this the compile is not worth it: interpreting kernels
+constexpr long long kJitMinBatch = 32 * 1024;      // below this the compile is not worth it: interpreting kernels ...
+constexpr long long kWarpMaxBatch = 2048;          // ... except for SMALL batches that keep coming (a solver loop): after
+constexpr int kSmallCallsBeforeJit = 4;            // this many calls the one-warp-per-configuration kernel is built
 
 long long env_ll(const char *name, long long dflt) {
     const char *e = std::getenv(name);
@@ -331,6 +334,13 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
     //   collision, tiled: 256 threads x 1 CTA/SM, no barriers: 3.11
     //   FK / Jacobian only: 128 threads x 1 CTA/SM + input batching (below)
     const bool tiled = c->layout == KIN_LAYOUT_TILED32;
+    // small batches: one warp per configuration (kin_gen_skeleton.cuh, KWARP)
+    o.warp = (c->n <= env_ll("KIN_JIT_WARP_MAX", kWarpMaxBatch) && (!o.coll || h.n_sph <= 32)) ? 1 : 0;
+    if (o.warp) {
+        o.block = 128; o.min_blocks = 1; o.qbatch = 0; o.ksync = 0; o.es32 = 0; o.fd_cold = 0;
+        o.grad_mode = o.want_grads ? c->grad_mode : -1;
+        return o;
+    }
     o.block = (int)env_ll("KIN_JIT_BLOCK", (o.coll && tiled) ? 256 : 128);
     o.min_blocks = (int)env_ll("KIN_JIT_MINB", o.coll ? (tiled ? 1 : 2) : 1);
     o.grad_mode = o.want_grads ? c->grad_mode : -1;
@@ -355,12 +365,18 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
     return o;
 }
 
-bool jit_wanted(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
+bool jit_wanted(const KinModel *m, const KinCall *c, const DeviceProgram *dp, bool count = true) {
     (void)m;
     if (std::getenv("KIN_DISABLE_JIT")) return false;
     if (c->layout != KIN_LAYOUT_SOA && c->layout != KIN_LAYOUT_TILED32) return false;
     if (c->vals_out && dp->prog.h.n_sph > 0 && dp->prog.h.n_dof > 16) return false;     // frames would not fit in registers
-    if (c->n < env_ll("KIN_JIT_MIN_BATCH", kJitMinBatch) && !std::getenv("KIN_FORCE_JIT")) return false;
+    if (c->n < env_ll("KIN_JIT_MIN_BATCH", kJitMinBatch) && !std::getenv("KIN_FORCE_JIT")) {
+        // a small batch: worth a specialised (one warp per configuration) kernel once the same program keeps being
+        // called, as a solver callback does
+        if (c->n > env_ll("KIN_JIT_WARP_MAX", kWarpMaxBatch) || std::getenv("KIN_JIT_NO_SMALL")) return false;
+        std::atomic<int> &calls = const_cast<DeviceProgram *>(dp)->small_calls;
+        return (count ? calls.fetch_add(1) + 1 : calls.load()) >= kSmallCallsBeforeJit;
+    }
     return true;
 }
 
@@ -389,6 +405,7 @@ int jit_slots(const kin::GenOptions &o, const kin::ProgHeader &h) {
 size_t jit_smem(const kin::GenOptions &o, const kin::ProgHeader &h, const JitKernel &k) {
     const size_t rs = o.precision ? sizeof(float) : sizeof(double);
     size_t reals = 0;
+    if (o.warp) return 0;                  // the one-warp-per-configuration kernel keeps everything in registers
     if (o.coll) reals += (((size_t)h.n_box * kin::BOX_REALS + h.n_sph + 1) & ~size_t(1)) + (size_t)k.slots * k.block;
     if (o.qbatch > 0) reals += (size_t)2 * o.qbatch * h.n_dof * k.block;
     return rs * reals;
@@ -466,6 +483,7 @@ int launch_jit(KinModel *m, const KinCall *c, DeviceProgram *dp, JitKernel &k, c
     const long long tiles = (c->n + k.block - 1) / k.block;
     long long grid = (long long)k.occ * m->n_sm;
     if (grid > tiles) grid = tiles;
+    if (o.warp) grid = (c->n + k.block / 32 - 1) / (k.block / 32);        // one warp per configuration, not persistent
     if (grid < 1) return KIN_OK;
     void *args[] = {&a};
     if (k.cooperative) {
@@ -751,12 +769,13 @@ int kin_query_launch(KinModel *m, const KinCall *c, int32_t *regs, int32_t *smem
     if (rc != KIN_OK) return rc;
     DeviceProgram *dp = dp_.get();
     const int pi = c->precision == KIN_F32 ? 1 : 0, li = c->layout;
-    if (jit_wanted(m, c, dp)) {
+    if (jit_wanted(m, c, dp, /*count=*/false)) {
         std::shared_ptr<JitKernel> jk = get_jit(m, c, dp);
         if (jk) {
             const long long tiles = (c->n + jk->block - 1) / jk->block;
             long long g = (long long)jk->occ * m->n_sm;
             if (g > tiles) g = tiles;
+            if (gen_options(m, c, dp).warp) g = (c->n + jk->block / 32 - 1) / (jk->block / 32);
             if (regs) *regs = jk->regs;
             if (smem_bytes) *smem_bytes = (int32_t)jit_smem(gen_options(m, c, dp), dp->prog.h, *jk);
             if (block) *block = -jk->block;          // negative block size: the model-specialised (NVRTC) kernel

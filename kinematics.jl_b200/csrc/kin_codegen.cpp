@@ -10,9 +10,9 @@ namespace kin {
 
 std::string GenOptions::key() const {
     char b[160];
-    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d I%d", precision, layout, (int)want_T, (int)want_J,
+    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d I%d W%d", precision, layout, (int)want_T, (int)want_J,
                   (int)coll, with_rot, rpy_jac, keep_irrelevant, (int)want_grads, (int)want_argmin, (int)stale, (int)ws, block, min_blocks, qbatch,
-                  ksync, es32, grad_mode, fd_cold, ik);
+                  ksync, es32, grad_mode, fd_cold, ik, warp);
     return b;
 }
 
@@ -343,7 +343,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
             for (unsigned mk : masks) seen |= mk == r.mask;
             if (!seen) masks.push_back(r.mask);
         }
-        p2 << "#pragma unroll 1\nfor (int s0 = 0; s0 < KS;) {\n    int se, mi;\n";
+        p2 << "#if !KWARP\n#pragma unroll 1\nfor (int s0 = 0; s0 < KS;) {\n    int se, mi;\n";
         for (size_t r = 0; r < runs.size(); ++r) {
             size_t mi = 0;
             while (masks[mi] != runs[r].mask) ++mi;
@@ -353,7 +353,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
         p2 << "    const int ge = min(s0 + SPH_GROUP, se);\n    phase2a_group<real>(s0, ge, KP2AARGS);\n    switch (mi) {\n";
         for (size_t mi = 0; mi < masks.size(); ++mi)
             p2 << "        case " << mi << ": phase2b_group<real, KND, 0x" << std::hex << masks[mi] << std::dec << "u>(s0, ge, KP2BARGS); break;\n";
-        p2 << "        default: break;\n    }\n    s0 = ge;\n}\n";
+        p2 << "        default: break;\n    }\n    s0 = ge;\n}\n#endif\n";
     }
     out.phase2 = p2.str();
 
@@ -363,7 +363,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
     if (o.fd_cold) c << "#define KIN_FD_COLD 1\n";
     c << "#define KWANT_T " << (o.want_T ? 1 : 0) << "\n#define KWANT_J " << (o.want_J ? 1 : 0) << "\n#define KCOLL " << (o.coll ? 1 : 0)
       << "\n#define KTILED " << (o.layout == 2 ? 1 : 0) << "\n#define KWS " << (o.ws ? 1 : 0) << "\n";
-    c << "#define KBS " << o.block << "\n#define KMINB " << o.min_blocks << "\n#define KIK " << o.ik << "\n#define KQB " << o.qbatch << "\n#define KSYNC_ON "
+    c << "#define KBS " << o.block << "\n#define KMINB " << o.min_blocks << "\n#define KWARP " << o.warp << "\n#define KIK " << o.ik << "\n#define KQB " << o.qbatch << "\n#define KSYNC_ON "
       << o.ksync << "\n#define KES32 " << o.es32 << "\n";
     c << "namespace kin {\n";
     c << "constexpr int KND = " << ND << ", KDC = " << DC << ", KS = " << S << ", KNFK = " << (o.want_T ? h.n_fk : 0) << ", KNJAC = "
@@ -380,6 +380,9 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
             std::snprintf(b, sizeof b, "%a", r);
             c << (s ? ", " : "") << "KREAL(" << b << ")";
         }
+        c << "};\n";
+        c << "__device__ const unsigned KSPHMASK[KS] = {";
+        for (int s = 0; s < S; ++s) c << (s ? ", " : "") << "0x" << std::hex << (unsigned)I[h.io_sph_mask + s] << std::dec << "u";
         c << "};\n";
     }
     c << "}  // namespace kin\n";

@@ -31,6 +31,7 @@ struct GenOptions {
     bool ws = false;            // warp-specialised skeleton (producer = phase 1, consumers = phase 2)
     int block = 128, min_blocks = 1;
     int qbatch = 0;             // > 0: tiles per input batch (cp.async into shared memory behind a grid-wide barrier)
+    int warp = 0;               // 1: small-batch kernel, one WARP per configuration (lane = sphere in phase 2)
     int ik = 0;                 // 1: the batched Levenberg-Marquardt IK kernel around phase 1 (one link: T + rpy-Jacobian)
     int grad_mode = -1;         // >= 0: the gradient mode as a compile-time constant (only that code path is compiled in)
     int fd_cold = 0;            // 1: the rare direct-FD fallback of the series gradient is an out-of-line call

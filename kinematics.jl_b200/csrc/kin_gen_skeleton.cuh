@@ -272,7 +272,119 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_ik_kernel(const __g
 }
 #endif
 
-#if !KWS && !KIK
+#if KWARP
+// =====================================================================================================================
+// Small-batch kernel: one WARP per configuration.  The reference's real callers evaluate ONE configuration per solver
+// iteration (IK, inverse_kinematics.jl:38-50) or n_wp = 10 .. 64 per iteration (planning.jl:59-67); with one thread per
+// configuration such a call is a single thread walking ~19k dependent instructions (37 us).  Here every lane of the
+// warp walks the chain (phase 1 is straight-line, a few microseconds; its stores are spread over the lanes), and in
+// phase 2 lane s owns sphere s: its union-SDF search, truncation, gradient and chain rule run side by side.  The one
+// thing that couples the spheres -- the shared Jacobian scratch of collision.jl:76,90, through which a sphere inherits
+// the columns of joints that do not move it from the last non-truncated sphere before it -- becomes a warp ballot
+// ("which earlier lanes wrote column j") and a shuffle from the last of them.  Same helpers, same operation order per
+// sphere: results are bit-identical to the other kernels.  KS <= 32.
+// =====================================================================================================================
+extern "C" __global__ void __launch_bounds__(KBS, 1) kin_gen_kernel(const __grid_constant__ kin::GenArgs A) {
+    using namespace kin;
+    const int lane = threadIdx.x & 31;
+    const long long n = (long long)blockIdx.x * (KBS / 32) + (threadIdx.x >> 5);       // this warp's configuration
+    if (n >= A.n) return;
+    const size_t es = KTILED ? size_t(32) : (size_t)A.ld;
+    #define KREC_BASE(rec) (KTILED ? (n >> 5) * ((long long)(rec) * 32) + (n & 31) : n)
+    const real *qn = reinterpret_cast<const real *>(A.q) + KREC_BASE(KND);
+    #define KQ(c) __ldg(qn + (size_t)(c) * es)
+    // output component k is stored by lane k mod 32 (every lane holds every value)
+#if KWANT_T
+    real *Tn = reinterpret_cast<real *>(A.T_out) + KREC_BASE(12 * KNFK);
+    #define KST_T(k, v) do { if (lane == ((k) & 31)) Tn[(size_t)(k) * es] = (v); } while (0)
+#else
+    #define KST_T(k, v)
+#endif
+#if KWANT_J
+    real *Jn = reinterpret_cast<real *>(A.J_out) + KREC_BASE(KROWS * KND * KNJAC);
+    #define KST_J(k, v) do { if (lane == ((k) & 31)) Jn[(size_t)(k) * es] = (v); } while (0)
+#else
+    #define KST_J(k, v)
+#endif
+#if KCOLL
+    real px = real(0), py = real(0), pz = real(0);            // the centre of THIS lane's sphere
+    #define KCEN_SET(s, i, v) do { if (lane == (s)) { if ((i) == 0) px = (v); else if ((i) == 1) py = (v); else pz = (v); } } while (0)
+#else
+    #define KCEN_SET(s, i, v)
+#endif
+    #define KJF_OUT(j, i, v)
+    #define KSYNC()
+    {
+#include "kin_gen_phase1.inc"
+#if KCOLL
+#include "kin_gen_phase2.inc"
+        const bool has = lane < KS;
+        const int s = has ? lane : KS - 1;
+        const real *tb = reinterpret_cast<const real *>(A.boxes);
+        const int n_box = A.n_box;
+        const real trunc = (real)A.truncation_dist, voff = (real)A.vals_offset;
+        // ---- 2a: union SDF of this lane's sphere (sdf.jl:108-114) ----
+        real kmin = CUDART_INF;
+        int kidx = 0;
+        #pragma unroll 1
+        for (int b = 0; b < n_box; ++b) {
+            BoxRow<real> row;
+            #pragma unroll
+            for (int i = 0; i < 9; ++i) row.r[i] = __ldg(tb + b * BOX_REALS + i);
+            #pragma unroll
+            for (int i = 0; i < 3; ++i) { row.t[i] = __ldg(tb + b * BOX_REALS + 9 + i); row.h[i] = __ldg(tb + b * BOX_REALS + 12 + i); }
+            const real key = box_key(row, px, py, pz);
+            if (key < kmin) { kmin = key; kidx = b; }
+        }
+        const real dmin = key_to_dist(kmin);
+        const real dist0 = dmin - KRADIUS[s];
+        const bool truncated = dist0 > trunc;
+        if (has) {
+            reinterpret_cast<real *>(A.vals_out)[KREC_BASE(KS) + (size_t)s * es] = (truncated ? trunc : dist0) - voff;
+            if (KARGMIN) A.argmin_out[KREC_BASE(KS) + (size_t)s * es] = kidx + 1;
+        }
+        if (KGRADS) {
+            // ---- 2b: gradient of the argmin box, chain rule through the sphere's Jacobian (collision.jl:78-93) ----
+            real grad[3] = {real(0), real(0), real(0)};
+            if (has && !truncated) {
+                BoxRow<real> row;
+                #pragma unroll
+                for (int i = 0; i < 9; ++i) row.r[i] = __ldg(tb + kidx * BOX_REALS + i);
+                #pragma unroll
+                for (int i = 0; i < 3; ++i) { row.t[i] = __ldg(tb + kidx * BOX_REALS + 9 + i); row.h[i] = __ldg(tb + kidx * BOX_REALS + 12 + i); }
+                box_gradient(row, KGRADMODE >= 0 ? KGRADMODE : A.grad_mode, px, py, pz, dmin, grad);
+            }
+            const unsigned mask = KSPHMASK[s];
+            real *Gp = reinterpret_cast<real *>(A.grads_out) + KREC_BASE((long long)KND * KS) + (size_t)s * KND * es;
+            const unsigned below = (1u << lane) - 1u;
+            #pragma unroll
+            for (int j = 0; j < KND; ++j) {
+                const bool mine = has && !truncated && ((mask >> j) & 1u);
+                real cx = real(0), cy = real(0), cz = real(0);
+                if (mine) jac_col(jfr[j], ((KREV >> j) & 1u) != 0, px, py, pz, cx, cy, cz);
+                if (KSTALE) {
+                    // the scratch column j as sphere s sees it: written by the last non-truncated sphere before it
+                    // that is moved by joint j (collision.jl:76,90), zero if there is none
+                    const unsigned writers = __ballot_sync(0xffffffffu, mine);
+                    const unsigned prev = writers & below;
+                    const int src = prev ? 31 - __clz(prev) : lane;
+                    const real sx = __shfl_sync(0xffffffffu, cx, src), sy = __shfl_sync(0xffffffffu, cy, src),
+                               sz = __shfl_sync(0xffffffffu, cz, src);
+                    if (!mine && prev) { cx = sx; cy = sy; cz = sz; }
+                }
+                if (has) {
+                    real gj = real(0);
+                    if (!truncated && (mine || KSTALE)) gj = fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz));
+                    Gp[(size_t)j * es] = gj;
+                }
+            }
+        }
+#endif
+    }
+}
+#endif
+
+#if !KWS && !KIK && !KWARP
 #if KQB > 0
 __device__ __forceinline__ void kin_grid_barrier(unsigned *sync, unsigned n_cta) {
     __syncthreads();

@@ -530,6 +530,37 @@ def test_specialised_kernel_is_bitwise_identical(layout, n, with_base, monkeypat
     assert failures.value == 0 and launches.value > 0
 
 
+def test_small_batches_switch_to_the_warp_per_configuration_kernel(monkeypatch):
+    """A solver callback evaluates one configuration (IK) or n_wp of them (planning) over and over: after a few small
+    calls of the same program the library builds the one-warp-per-configuration kernel for it; results stay bit-identical
+    across the switch and match the oracle."""
+    monkeypatch.delenv("KIN_DISABLE_JIT", raising=False)
+    monkeypatch.delenv("KIN_FORCE_JIT", raising=False)
+    from kinematics_jl_b200.device import current_q, evaluate
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
+    q = scenes.random_configs(jo, 10, False, seed=37)
+    K.set_joint_angles(m, joints, dev(q))
+    K.compute_coll_dists(sscc, joints, sdf)
+    dm = device_model(m)
+    Qc, ql, N = current_q(m)
+    outs, blocks = [], []
+    for _ in range(8):
+        o = evaluate(dm, Qc, ql, N, fk_links=list(range(1, 26)), jac_links=[K.find_link(m, "gripper_link").id], collision=True,
+                     want_argmin=True, launch_info=True)
+        torch.cuda.synchronize()
+        outs.append({k: o[k].clone() for k in ("T", "J", "vals", "grads", "argmin")})
+        blocks.append(o["launch"]["block"])
+    assert blocks[0] > 0 and blocks[-1] < 0, blocks                   # interpreting kernel first, specialised kernel later
+    for o in outs[1:]:
+        for k in o:
+            assert torch.equal(o[k], outs[0][k]), k
+    v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, q)
+    np.testing.assert_allclose(host(outs[-1]["vals"]), v_ref, rtol=RTOL, atol=ATOL)
+    assert np.array_equal(outs[-1]["argmin"].cpu().numpy(), am_ref)
+    np.testing.assert_allclose(host(outs[-1]["grads"]), g_ref.transpose(0, 2, 1), rtol=0, atol=1e-7)
+    np.testing.assert_allclose(host(outs[-1]["T"]), R.batch_fk(mo, jo, q, mo.links[:25])[:, :, :3, :], rtol=RTOL, atol=ATOL)
+
+
 def test_specialised_kernel_fp32_and_general_models(monkeypatch):
     """FP32 instantiation of the specialised kernel (same folding in float) and models that exercise the general
     paths of the generator: a branching tree with general axes / rpy origins / frozen joints, and the PR2 chain."""

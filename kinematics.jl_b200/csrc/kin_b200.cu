@@ -368,7 +368,8 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
 bool jit_wanted(const KinModel *m, const KinCall *c, const DeviceProgram *dp, bool count = true) {
     (void)m;
     if (std::getenv("KIN_DISABLE_JIT")) return false;
-    if (c->layout != KIN_LAYOUT_SOA && c->layout != KIN_LAYOUT_TILED32) return false;
+    const bool small = c->n <= env_ll("KIN_JIT_WARP_MAX", kWarpMaxBatch) && (!c->vals_out || dp->prog.h.n_sph <= 32);
+    if (c->layout == KIN_LAYOUT_AOS && !small) return false;       // AoS: only the small-batch kernel is specialised
     if (c->vals_out && dp->prog.h.n_sph > 0 && dp->prog.h.n_dof > 16) return false;     // frames would not fit in registers
     if (c->n < env_ll("KIN_JIT_MIN_BATCH", kJitMinBatch) && !std::getenv("KIN_FORCE_JIT")) {
         // a small batch: worth a specialised (one warp per configuration) kernel once the same program keeps being

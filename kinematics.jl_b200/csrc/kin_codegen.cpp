@@ -135,7 +135,10 @@ struct Frame {
 
 bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std::string &err) {
     const ProgHeader &h = p.h;
-    if (o.layout != 0 && o.layout != 2) { err = "only the SoA and tiled layouts are specialised"; return false; }
+    if (o.layout != 0 && o.layout != 2 && !(o.layout == 1 && o.warp)) {
+        err = "only the SoA and tiled layouts are specialised (AoS: small batches only)";
+        return false;
+    }
     if (h.n_dof > 32) { err = "too many columns"; return false; }
     const bool f32 = o.precision == 1;
     Emitter E(f32);
@@ -362,7 +365,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
     c << "#define KREAL " << (f32 ? "float" : "double") << "\n";
     if (o.fd_cold) c << "#define KIN_FD_COLD 1\n";
     c << "#define KWANT_T " << (o.want_T ? 1 : 0) << "\n#define KWANT_J " << (o.want_J ? 1 : 0) << "\n#define KCOLL " << (o.coll ? 1 : 0)
-      << "\n#define KTILED " << (o.layout == 2 ? 1 : 0) << "\n#define KWS " << (o.ws ? 1 : 0) << "\n";
+      << "\n#define KTILED " << (o.layout == 2 ? 1 : 0) << "\n#define KAOS " << (o.layout == 1 ? 1 : 0) << "\n#define KWS " << (o.ws ? 1 : 0) << "\n";
     c << "#define KBS " << o.block << "\n#define KMINB " << o.min_blocks << "\n#define KWARP " << o.warp << "\n#define KIK " << o.ik << "\n#define KQB " << o.qbatch << "\n#define KSYNC_ON "
       << o.ksync << "\n#define KES32 " << o.es32 << "\n";
     c << "namespace kin {\n";

@@ -289,8 +289,10 @@ extern "C" __global__ void __launch_bounds__(KBS, 1) kin_gen_kernel(const __grid
     const int lane = threadIdx.x & 31;
     const long long n = (long long)blockIdx.x * (KBS / 32) + (threadIdx.x >> 5);       // this warp's configuration
     if (n >= A.n) return;
-    const size_t es = KTILED ? size_t(32) : (size_t)A.ld;
-    #define KREC_BASE(rec) (KTILED ? (n >> 5) * ((long long)(rec) * 32) + (n & 31) : n)
+    // all three layouts: SoA, tiled, and AoS (one contiguous record per configuration -- the reference-native layout,
+    // which is what a solver callback hands over)
+    const size_t es = KAOS ? size_t(1) : KTILED ? size_t(32) : (size_t)A.ld;
+    #define KREC_BASE(rec) (KAOS ? n * (long long)(rec) : KTILED ? (n >> 5) * ((long long)(rec) * 32) + (n & 31) : n)
     const real *qn = reinterpret_cast<const real *>(A.q) + KREC_BASE(KND);
     #define KQ(c) __ldg(qn + (size_t)(c) * es)
     // output component k is stored by lane k mod 32 (every lane holds every value)

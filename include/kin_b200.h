@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define KIN_B200_ABI_VERSION 2
+#define KIN_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define KIN_API __attribute__((visibility("default")))
@@ -242,28 +242,14 @@ KIN_API int kin_pose_residual_multi(KinModel *model, int32_t precision, int32_t 
                                     int32_t n_links, const int32_t *link_ids, const int32_t *with_rots, const void *target,
                                     int32_t target_per_config, int32_t mode, void *val_out, void *jac_out, void *stream);
 
-/* Batched Levenberg-Marquardt iteration of the IK driver built on kin_pose_residual / kin_eval (config 4;
- * the reference drives the same evaluations with NLopt SLSQP, inverse_kinematics.jl:1-30, which is third
- * party).  One thread per problem, everything per-problem contiguous (AoS), FP64, DEVICE pointers:
- *   q[n][n_dof], e[n][dim] residual, J[n][dim][n_dof] = d e / d q, lambda[n], f[n] = |e|^2,
- *   lo / hi [n_dof] joint limits (+-inf allowed).
- * kin_lm_step:   q_try = clamp(q - (J'J + lambda (I + diag J'J))^-1 J'e) with the joints that sit on a limit
- *                and are pushed outward frozen (active set); Cholesky in registers / local memory.
- * kin_lm_accept: where f_try < f the trial point (q, e, J, f) replaces the current one and lambda *= 0.3,
- *                elsewhere lambda *= 4 (clamped to [1e-9, 1e4]). */
-KIN_API int kin_lm_step(int64_t n, int32_t n_dof, int32_t dim, const double *q, const double *e, const double *J,
-                        const double *lambda, const double *lo, const double *hi, double *q_try, void *stream);
-KIN_API int kin_lm_accept(int64_t n, int32_t n_dof, int32_t dim, const double *q_try, const double *e_try,
-                          const double *J_try, const double *f_try, double *q, double *e, double *J, double *f,
-                          double *lambda, void *stream);
-
 /* The whole batched IK solve of config 4 in ONE kernel launch (device-resident loop; no host round trip per
  * iteration).  One thread per problem runs up to `iters` Levenberg-Marquardt iterations on the reference's objective
  * f = |[p - p_t; rpy - rpy_t]|^2 (inverse_kinematics.jl:38-50; angle residuals wrapped to (-pi, pi]) with the joint
  * limits as bounds (inverse_kinematics.jl:52-63: active set + clamping) and stops on its own when f < ftol.  The
  * kernel is generated for this model / link (straight-line FK + Euler-rate Jacobian, csrc/kin_codegen.cpp) and
- * compiled with NVRTC on first use; without NVRTC the call returns KIN_ERR_UNAVAILABLE and the caller falls back to
- * kin_pose_residual + kin_lm_step + kin_lm_accept.  FP64, per-problem contiguous arrays (AoS), DEVICE pointers:
+ * compiled with NVRTC on first use; without NVRTC the same method runs as one kin_eval + one step kernel per
+ * iteration (the loop of the collision-constrained solve below, without spheres).  FP64, per-problem contiguous
+ * arrays (AoS), DEVICE pointers:
  * targets[n][6] = x y z roll pitch yaw, q0 / q_out [n][n_dof], f_out[n], iters_out[n] (nullable); lower / upper are
  * HOST [n_dof] (+-inf allowed, NULL = unbounded).  n_dof <= 12. */
 typedef struct {
@@ -281,6 +267,22 @@ typedef struct {
     void *f_out;
     int32_t *iters_out;
     void *stream;
+    /* ---- collision-constrained solve (ABI version 3) ----
+     * collision != 0: the reference's two-stage problem (inverse_kinematics.jl:8-19): the pose objective subject to
+     * dists(q) - margin >= 0 for every sphere of the model's sphere table against the model's boxes (IneqConst with
+     * margin 0.02 in the reference), q0 being the warm start (normally the result of a collision == 0 solve).  The
+     * constraint is enforced by an augmented-Lagrangian Levenberg-Marquardt iteration (csrc/kin_ik_coll.cuh): per
+     * iteration ONE kin_eval over the batch (link transform + Euler-rate Jacobian + sphere distances and gradients,
+     * truncated at margin + 0.05 as planning.jl:56, forward-difference SDF gradient, clean Jacobian scratch) and ONE
+     * step kernel (accept / multiplier update / normal equations / Cholesky), no host synchronisation, `iters`
+     * iterations at most.  A problem stops when f < ftol and every dist >= margin - ctol.  Works without NVRTC (the
+     * interpreting kernels evaluate).  ~ (30 + 21 n_dof + 2 S + S n_dof) * 8 bytes of stream-ordered scratch per problem. */
+    int32_t collision;
+    int32_t reserved_;
+    double margin;             /* the reference uses 0.02 */
+    double coll_weight;        /* penalty parameter mu of the augmented Lagrangian (<= 0: 100) */
+    double ctol;               /* constraint tolerance (<= 0: 1e-6) */
+    void *dmin_out;            /* DEVICE [n], nullable: min over spheres of the UNtruncated signed distance at q_out */
 } KinIkCall;
 KIN_API int kin_ik_solve(KinModel *model, const KinIkCall *call);
 

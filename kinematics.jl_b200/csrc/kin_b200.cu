@@ -17,6 +17,7 @@
 #include "../../include/kin_b200.h"
 #include "kin_kernels.cuh"
 #include "kin_kernels_ws.cuh"
+#include "kin_ik_coll.cuh"
 #include "kin_model.hpp"
 #include "kin_codegen.hpp"
 #include "kin_jit.hpp"
@@ -997,15 +998,112 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
                                    val_out, jac_out, stream_);
 }
 
+}  // extern "C"
+namespace {
+
+template <int ND>
+void launch_ik_coll_step(const kin::IkCollArgs &a, bool rot, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((a.n + 127) / 128);
+    if (rot) kin::ik_coll_step_kernel<ND, true><<<grid, 128, 0, stream>>>(a);
+    else kin::ik_coll_step_kernel<ND, false><<<grid, 128, 0, stream>>>(a);
+}
+
+// The collision-constrained solve of kin_ik_solve (csrc/kin_ik_coll.cuh): a loop of (kin_eval, step kernel) pairs on the
+// caller's stream over a stream-ordered workspace; nothing is read back.
+// With c->collision == 0 (the pose-only problem when the run-time compiler is unavailable) no sphere is evaluated.
+int ik_solve_coll(KinModel *m, const KinIkCall *c) {
+    const int nd = m->hm.n_dof(), S = c->collision ? m->hm.n_sph : 0, rows = c->with_rot ? 6 : 3;
+    if (c->collision && (S < 1 || m->hm.n_box < 1))
+        return fail(KIN_ERR_INVALID_ARGUMENT, "kin_ik_solve: collision requested but the model has no spheres / no boxes");
+    if (c->collision && !(c->margin == c->margin)) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_ik_solve: margin is NaN");
+    DeviceGuard guard(m->device);
+    cudaStream_t stream = (cudaStream_t)c->stream;
+    const long long n = c->n, ld = (n + 31) / 32 * 32;
+    // workspace (doubles per problem): q_try, T, J, V, G | q, H, g, phi, fpose, damp, viol, mult | Vfin ; then int32 status, its
+    const long long nh = (long long)nd * (nd + 1) / 2;
+    const long long per = nd + 12 + (long long)rows * nd + S + (long long)S * nd + nd + nh + nd + 4 + S + S;
+    double *ws = nullptr;
+    CUDA_TRY(cudaMallocFromPoolAsync((void **)&ws, sizeof(double) * (size_t)(per * ld) + 2 * sizeof(int32_t) * (size_t)ld, m->pool, stream));
+    kin::IkCollArgs a;
+    std::memset(&a, 0, sizeof a);
+    double *p = ws;
+    auto take = [&](long long k) { double *r = p; p += k * ld; return r; };
+    a.n = n; a.ld = ld; a.n_sph = S;
+    a.q_try = take(nd);
+    double *T = take(12), *J = take((long long)rows * nd), *V = take(S), *G = take((long long)S * nd);
+    a.T = T; a.J = J; a.V = V; a.G = G;
+    a.q = take(nd); a.H = take(nh); a.g = take(nd);
+    a.phi = take(1); a.fpose = take(1); a.damp = take(1); a.viol = take(1); a.mult = take(S);
+    double *Vfin = take(S);
+    a.status = (int32_t *)p; a.its = a.status + ld;
+    a.margin = c->margin; a.mu = c->coll_weight > 0 ? c->coll_weight : 100.0; a.ftol = c->ftol;
+    a.ctol = c->ctol > 0 ? c->ctol : 1e-6; a.lambda0 = c->lambda0 > 0 ? c->lambda0 : 1e-2;
+    a.trunc = c->margin + 0.05;                                  // planning.jl:56
+    a.targets = (const double *)c->targets;
+    for (int j = 0; j < nd; ++j) {
+        a.lo[j] = c->lower ? c->lower[j] : -INFINITY;
+        a.hi[j] = c->upper ? c->upper[j] : INFINITY;
+    }
+    int rc = KIN_OK;
+    kin::ik_coll_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, (const double *)c->q0, nd);
+    g_launches.fetch_add(1);
+    KinCall ec;
+    std::memset(&ec, 0, sizeof ec);
+    ec.precision = KIN_F64; ec.layout = KIN_LAYOUT_SOA; ec.n = n; ec.batch_stride = ld; ec.q = a.q_try;
+    ec.n_fk_links = 1; ec.fk_links = &c->link_id; ec.T_out = T;
+    ec.n_jac_links = 1; ec.jac_links = &c->link_id; ec.with_rot = c->with_rot ? 1 : 0; ec.rpy_jac = 1; ec.J_out = J;
+    ec.truncation_dist = a.trunc; ec.grad_mode = KIN_GRAD_FD; ec.scratch_mode = KIN_SCRATCH_CLEAN;
+    if (S > 0) { ec.vals_out = V; ec.grads_out = G; }
+    ec.stream = c->stream;
+    for (int it = 0; it <= c->iters && rc == KIN_OK; ++it) {
+        rc = kin_eval(m, &ec);
+        if (rc != KIN_OK) break;
+        a.it = it;
+        switch (nd) {
+#define KIN_IKC_CASE(N_) case N_: launch_ik_coll_step<N_>(a, rows == 6, stream); break;
+            KIN_IKC_CASE(1) KIN_IKC_CASE(2) KIN_IKC_CASE(3) KIN_IKC_CASE(4) KIN_IKC_CASE(5) KIN_IKC_CASE(6)
+            KIN_IKC_CASE(7) KIN_IKC_CASE(8) KIN_IKC_CASE(9) KIN_IKC_CASE(10) KIN_IKC_CASE(11) KIN_IKC_CASE(12)
+#undef KIN_IKC_CASE
+            default: break;
+        }
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) { rc = fail_cuda(le, "launching ik_coll_step_kernel"); break; }
+        g_launches.fetch_add(1);
+    }
+    if (rc == KIN_OK) {
+        // the UNtruncated distances of the final configurations (for dmin_out)
+        if (c->dmin_out && S > 0) {
+            KinCall fc;
+            std::memset(&fc, 0, sizeof fc);
+            fc.precision = KIN_F64; fc.layout = KIN_LAYOUT_SOA; fc.n = n; fc.batch_stride = ld; fc.q = a.q;
+            fc.truncation_dist = INFINITY; fc.vals_out = Vfin; fc.stream = c->stream;
+            rc = kin_eval(m, &fc);
+        }
+        if (rc == KIN_OK) {
+            kin::ik_coll_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, Vfin, nd, (double *)c->q_out, (double *)c->f_out,
+                                                                                     c->iters_out, S > 0 ? (double *)c->dmin_out : nullptr);
+            cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) rc = fail_cuda(le, "launching ik_coll_finish_kernel");
+            g_launches.fetch_add(1);
+        }
+    }
+    cudaFreeAsync(ws, stream);
+    return rc;
+}
+
+}  // namespace
+extern "C" {
+
 int kin_ik_solve(KinModel *m, const KinIkCall *c) {
     if (!m || !c) return fail(KIN_ERR_INVALID_ARGUMENT, "null model or call");
     if (c->n < 0 || (c->n > 0 && (!c->targets || !c->q0 || !c->q_out || !c->f_out))) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
     if (c->iters < 0) return fail(KIN_ERR_INVALID_ARGUMENT, "negative iteration count");
     const int nd = m->hm.n_dof();
-    if (nd < 1 || nd > 12) return fail(KIN_ERR_LIMIT, "kin_ik_solve: 1..12 configuration columns (use kin_lm_step / kin_lm_accept beyond)");
+    if (nd < 1 || nd > 12) return fail(KIN_ERR_LIMIT, "kin_ik_solve: 1..12 configuration columns");
     if (c->link_id < 1 || c->link_id > m->hm.n_links) return fail(KIN_ERR_INVALID_ARGUMENT, "link id out of range");
     if (c->n == 0) return KIN_OK;
-    if (std::getenv("KIN_DISABLE_JIT")) return fail(KIN_ERR_UNAVAILABLE, "kin_ik_solve needs the run-time compiler (KIN_DISABLE_JIT is set)");
+    if (c->collision) return ik_solve_coll(m, c);
+    if (std::getenv("KIN_DISABLE_JIT")) return ik_solve_coll(m, c);      // no run-time compiler: (kin_eval, step kernel) pairs
     DeviceGuard guard(m->device);
     // the program of (this link's transform + its Euler-rate Jacobian)
     KinCall pc;
@@ -1021,7 +1119,7 @@ int kin_ik_solve(KinModel *m, const KinIkCall *c) {
     o.precision = 0; o.layout = 0; o.want_T = true; o.want_J = true; o.with_rot = pc.with_rot; o.rpy_jac = 1;
     o.ik = 1; o.block = (int)env_ll("KIN_IK_BLOCK", 128); o.min_blocks = (int)env_ll("KIN_IK_MINB", 1);
     std::shared_ptr<JitKernel> k = get_jit_with(m, dp.get(), o, "kin_ik_kernel");
-    if (!k) return fail(KIN_ERR_UNAVAILABLE, std::string("kin_ik_solve: the specialised kernel could not be built: ") + kin::jit_status());
+    if (!k) return ik_solve_coll(m, c);
     kin::IkArgs a;
     std::memset(&a, 0, sizeof a);
     a.targets = c->targets; a.q0 = c->q0; a.q_out = c->q_out; a.f_out = c->f_out; a.iters_out = c->iters_out;
@@ -1035,28 +1133,6 @@ int kin_ik_solve(KinModel *m, const KinIkCall *c) {
     CUDA_TRY(cudaLaunchKernel((const void *)k->kern, dim3((unsigned)grid), dim3((unsigned)k->block), args, 0, (cudaStream_t)c->stream));
     g_launches.fetch_add(1);
     g_jit_launches.fetch_add(1);
-    return KIN_OK;
-}
-
-int kin_lm_step(int64_t n, int32_t n_dof, int32_t dim, const double *q, const double *e, const double *J,
-                const double *lambda, const double *lo, const double *hi, double *q_try, void *stream) {
-    if (n < 0 || n_dof < 1 || n_dof > kin::LM_MAX_DOF || dim < 1) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_lm_step: bad sizes (n_dof <= 16)");
-    if (n > 0 && (!q || !e || !J || !lambda || !lo || !hi || !q_try)) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
-    if (n == 0) return KIN_OK;
-    kin::lm_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, n_dof, dim, q, e, J, lambda, lo, hi, q_try);
-    CUDA_TRY(cudaGetLastError());
-    g_launches.fetch_add(1);
-    return KIN_OK;
-}
-
-int kin_lm_accept(int64_t n, int32_t n_dof, int32_t dim, const double *q_try, const double *e_try, const double *J_try,
-                  const double *f_try, double *q, double *e, double *J, double *f, double *lambda, void *stream) {
-    if (n < 0 || n_dof < 1 || dim < 1) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_lm_accept: bad sizes");
-    if (n > 0 && (!q_try || !e_try || !J_try || !f_try || !q || !e || !J || !f || !lambda)) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
-    if (n == 0) return KIN_OK;
-    kin::lm_accept_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, n_dof, dim, q_try, e_try, J_try, f_try, q, e, J, f, lambda);
-    CUDA_TRY(cudaGetLastError());
-    g_launches.fetch_add(1);
     return KIN_OK;
 }
 

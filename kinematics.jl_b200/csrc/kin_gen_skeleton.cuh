@@ -129,8 +129,8 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
 // Batched inverse kinematics (config 4 of BASELINE.json): ONE kernel launch runs the whole damped least-squares solve,
 // one thread per problem.  Per iteration the generated straight-line phase 1 gives the link transform and its
 // Euler-rate Jacobian (the evaluations of f_objective, inverse_kinematics.jl:38-50: e = [p - p_t; rpy - rpy_t],
-// rpy of RotZYX, transform.jl:45-48); the rest is the Levenberg-Marquardt update the host-side driver used to issue as
-// separate launches (kin_lm_step / kin_lm_accept): normal equations H = J'J, g = J'e in registers, joints that sit on
+// rpy of RotZYX, transform.jl:45-48); the rest is the Levenberg-Marquardt update (the same one ik_coll_step_kernel of
+// kin_ik_coll.cuh performs as a separate launch): normal equations H = J'J, g = J'e in registers, joints that sit on
 // a limit and are pushed outward frozen, Cholesky of H + lambda (I + diag H), trial point clamped to the limits
 // (inverse_kinematics.jl:52-63), accept / reject with the damping scaled by 0.3 / 4.  Angle residuals are wrapped to
 // (-pi, pi].  A problem stops on its own when f < ftol.  The reference drives the same evaluations with NLopt SLSQP

@@ -1,0 +1,241 @@
+// kin_ik_coll.cuh -- the collision-CONSTRAINED batched IK of config 4 (BASELINE.json: "1M independent gripper pose
+// targets solved in parallel, Jacobian + SDF per iteration"), device resident.
+//
+// The reference solves   min |[p - p_t; rpy - rpy_t]|^2   s.t.  dists(q) - margin >= 0,  lo <= q <= hi
+// (inverse_kinematics.jl:1-30: f_objective :38-50, IneqConst(sscc, joints, sdf, 1, 0.02) with tolerance 1e-8 :14-19,
+// bounds :52-63) one problem at a time with NLopt SLSQP (third party).  Here every problem of the batch runs an
+// augmented-Lagrangian Levenberg-Marquardt iteration on the same functions:
+//     merit  phi(q) = |e(q)|^2 + mu * sum_s psi_s^2,   psi_s = max(0, margin - d_s(q) + lambda_s / mu)
+// Per iteration the host issues TWO launches on the caller's stream, with no host synchronisation in between:
+//   1. kin_eval (the fused hot-path kernel) at the trial points: link transform, Euler-rate Jacobian, sphere distances
+//      and their gradients (truncated at margin + 0.05 like planning.jl:56), SoA;
+//   2. ik_coll_step_kernel (this file), one thread per problem: residuals, accept / reject against the merit, first-order
+//      multiplier update lambda_s <- mu * psi_s at every accepted point, Gauss-Newton normal equations
+//      H = J'J + mu * sum_{psi_s > 0} g_s g_s',  g = J'e - mu * sum psi_s g_s  in registers, joints on a limit that are
+//      pushed outward frozen, Cholesky of H + damping (I + diag H), next trial point clamped to the limits.
+// A problem stops when |e|^2 < ftol and every constraint holds to ctol; stopped problems keep their trial point (their
+// evaluation is repeated, results ignored).  All state is SoA in a stream-ordered workspace.
+#pragma once
+
+#include <cstdint>
+
+namespace kin {
+
+constexpr int IKC_MAX_DOF = 12;
+
+struct IkCollArgs {
+    long long n, ld;                 // problems, SoA stride of every array below
+    int n_sph, it;
+    double margin, mu, ftol, ctol, lambda0, trunc;
+    const double *targets;           // [n][6] AoS (caller's)
+    const double *T, *J, *V, *G;     // kin_eval outputs at the trial points (SoA)
+    double *q_try;                   // [ND][ld]  trial points = input of the next kin_eval
+    double *q, *H, *g;               // current point, its normal equations (lower triangle, row-major packed) and gradient
+    double *phi, *fpose, *damp, *viol, *mult;      // merit, |e|^2, LM damping, max_s (margin - d_s), multipliers [S][ld]
+    int32_t *status;                 // 0 running, 1 stopped (converged)
+    int32_t *its;                    // iterations used
+    double lo[IKC_MAX_DOF], hi[IKC_MAX_DOF];
+};
+
+// q0 (AoS, caller's) -> q_try and q (SoA); merit +inf so that the first evaluation is accepted
+__global__ void __launch_bounds__(256) ik_coll_init_kernel(const IkCollArgs A, const double *__restrict__ q0, int nd) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= A.n) return;
+    for (int a = 0; a < nd; ++a) {
+        const double v = fmin(fmax(q0[n * nd + a], A.lo[a]), A.hi[a]);
+        A.q_try[a * A.ld + n] = v;
+        A.q[a * A.ld + n] = v;
+        A.g[a * A.ld + n] = 0.0;
+    }
+    for (int k = 0; k < nd * (nd + 1) / 2; ++k) A.H[k * A.ld + n] = 0.0;
+    for (int s = 0; s < A.n_sph; ++s) A.mult[s * A.ld + n] = 0.0;
+    A.phi[n] = CUDART_INF;
+    A.fpose[n] = CUDART_INF;
+    A.viol[n] = CUDART_INF;
+    A.damp[n] = A.lambda0;
+    A.status[n] = 0;
+    A.its[n] = 0;
+}
+
+template <int ND, bool ROT>
+__global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= A.n) return;
+    if (A.status[n]) return;
+    constexpr int ROWS = ROT ? 6 : 3;
+    const long long ld = A.ld;
+    const double PI = 3.14159265358979323846;
+    const double mu = A.mu, margin = A.margin;
+    const int S = A.n_sph;
+
+    // ---- residual at the trial point: e = [p - p_t; rpy - rpy_t] (planning.jl:114-138 sign), angles wrapped ----
+    double e[ROWS];
+    {
+        const double *Tn = A.T + n, *tg = A.targets + n * 6;
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) e[i] = Tn[(9 + i) * ld] - tg[i];
+        if (ROT) {        // rpy(T), transform.jl:45-48 (RotZYX): R[r][c] = T[c*3 + r]
+            const double r00 = Tn[0], r10 = Tn[ld], r20 = Tn[2 * ld], r01 = Tn[3 * ld], r11 = Tn[4 * ld], r21 = Tn[5 * ld],
+                         r02 = Tn[6 * ld], r12 = Tn[7 * ld], r22 = Tn[8 * ld];
+            const double yaw = atan2(r10, r00);
+            double s1, c1;
+            sincos(yaw, &s1, &c1);
+            const double pitch = atan2(-r20, sqrt(fma(r21, r21, r22 * r22)));
+            const double roll = atan2(fma(r02, s1, -(r12 * c1)), fma(r11, c1, -(r01 * s1)));
+            const double ang[3] = {roll - tg[3], pitch - tg[4], yaw - tg[5]};
+            #pragma unroll
+            for (int i = 0; i < 3; ++i) e[3 + i] = ang[i] - 2.0 * PI * floor((ang[i] + PI) / (2.0 * PI));
+        }
+    }
+    double ft = 0.0;
+    #pragma unroll
+    for (int r = 0; r < ROWS; ++r) ft = fma(e[r], e[r], ft);
+
+    // ---- merit under the CURRENT multipliers ----
+    double phi_t = ft;
+    for (int s = 0; s < S; ++s) {
+        const double d = A.V[s * ld + n];
+        const double psi = d >= A.trunc ? 0.0 : fmax(0.0, margin - d + A.mult[s * ld + n] / mu);
+        phi_t = fma(mu * psi, psi, phi_t);
+    }
+    const bool ok = phi_t < A.phi[n];
+    double damp = A.damp[n];
+    if (A.it > 0) {
+        damp *= ok ? 0.3 : 4.0;
+        damp = fmin(fmax(damp, 1e-9), 1e4);
+        A.damp[n] = damp;
+    }
+
+    double q[ND], g[ND], H[ND][ND];
+    if (ok) {
+        // ---- accepted: multipliers, merit and normal equations at this point ----
+        #pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            q[a] = A.q_try[a * ld + n];
+            g[a] = 0.0;
+            #pragma unroll
+            for (int b = 0; b <= a; ++b) H[a][b] = 0.0;
+        }
+        #pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            double jr[ND];
+            #pragma unroll
+            for (int a = 0; a < ND; ++a) jr[a] = A.J[(long long)(a * ROWS + r) * ld + n];
+            #pragma unroll
+            for (int a = 0; a < ND; ++a) {
+                g[a] = fma(jr[a], e[r], g[a]);
+                #pragma unroll
+                for (int b = 0; b <= a; ++b) H[a][b] = fma(jr[a], jr[b], H[a][b]);
+            }
+        }
+        double phi_n = ft, viol = -CUDART_INF;
+        #pragma unroll 1
+        for (int s = 0; s < S; ++s) {
+            const double d = A.V[s * ld + n];
+            double lam = 0.0, psi = 0.0;
+            if (d < A.trunc) {
+                viol = fmax(viol, margin - d);
+                lam = mu * fmax(0.0, margin - d + A.mult[s * ld + n] / mu);    // first-order multiplier update
+                psi = fmax(0.0, margin - d + lam / mu);
+            }
+            A.mult[s * ld + n] = lam;
+            if (psi > 0.0) {
+                double gs[ND];
+                #pragma unroll
+                for (int a = 0; a < ND; ++a) gs[a] = A.G[(long long)(s * ND + a) * ld + n];
+                const double w = mu * psi;
+                #pragma unroll
+                for (int a = 0; a < ND; ++a) {
+                    g[a] = fma(-w, gs[a], g[a]);
+                    const double ma = mu * gs[a];
+                    #pragma unroll
+                    for (int b = 0; b <= a; ++b) H[a][b] = fma(ma, gs[b], H[a][b]);
+                }
+                phi_n = fma(w, psi, phi_n);
+            }
+        }
+        #pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            A.q[a * ld + n] = q[a];
+            A.g[a * ld + n] = g[a];
+            #pragma unroll
+            for (int b = 0; b <= a; ++b) A.H[(long long)(a * (a + 1) / 2 + b) * ld + n] = H[a][b];
+        }
+        A.phi[n] = phi_n;
+        A.fpose[n] = ft;
+        A.viol[n] = viol;
+        A.its[n] = A.it;
+        if (ft < A.ftol && viol <= A.ctol) {       // q_try == q already
+            A.status[n] = 1;
+            return;
+        }
+    } else {
+        #pragma unroll
+        for (int a = 0; a < ND; ++a) {
+            q[a] = A.q[a * ld + n];
+            g[a] = A.g[a * ld + n];
+            #pragma unroll
+            for (int b = 0; b <= a; ++b) H[a][b] = A.H[(long long)(a * (a + 1) / 2 + b) * ld + n];
+        }
+    }
+
+    // ---- step: active set on the limits, Cholesky of H + damp (I + diag H), q_try = clamp(q - x) ----
+    bool fr[ND];
+    double x[ND];
+    #pragma unroll
+    for (int a = 0; a < ND; ++a)
+        fr[a] = !(((q[a] <= A.lo[a] + 1e-12) && (g[a] > 0.0)) || ((q[a] >= A.hi[a] - 1e-12) && (g[a] < 0.0)));
+    #pragma unroll
+    for (int a = 0; a < ND; ++a) {
+        #pragma unroll
+        for (int b = 0; b < a; ++b) H[a][b] = (fr[a] && fr[b]) ? H[a][b] : 0.0;
+        H[a][a] = fr[a] ? fma(damp, 1.0 + H[a][a], H[a][a]) : 1.0;
+        x[a] = fr[a] ? g[a] : 0.0;
+    }
+    #pragma unroll
+    for (int a = 0; a < ND; ++a) {
+        #pragma unroll
+        for (int b = 0; b <= a; ++b) {
+            double sum = H[a][b];
+            #pragma unroll
+            for (int k = 0; k < b; ++k) sum = fma(-H[a][k], H[b][k], sum);
+            if (a == b) H[a][a] = sqrt(sum > 1e-300 ? sum : 1e-300);
+            else H[a][b] = sum / H[b][b];
+        }
+    }
+    #pragma unroll
+    for (int a = 0; a < ND; ++a) {
+        double sum = x[a];
+        #pragma unroll
+        for (int k = 0; k < a; ++k) sum = fma(-H[a][k], x[k], sum);
+        x[a] = sum / H[a][a];
+    }
+    #pragma unroll
+    for (int a = ND - 1; a >= 0; --a) {
+        double sum = x[a];
+        #pragma unroll
+        for (int k = a + 1; k < ND; ++k) sum = fma(-H[k][a], x[k], sum);
+        x[a] = sum / H[a][a];
+    }
+    #pragma unroll
+    for (int a = 0; a < ND; ++a) A.q_try[a * ld + n] = fmin(fmax(q[a] - x[a], A.lo[a]), A.hi[a]);
+}
+
+// q (SoA) -> q_out (AoS, caller's), |e|^2, iterations, and the smallest signed distance of the final configuration
+// (from a final UNtruncated distance evaluation Vfin at q)
+__global__ void __launch_bounds__(256) ik_coll_finish_kernel(const IkCollArgs A, const double *__restrict__ Vfin, int nd,
+                                                             double *__restrict__ q_out, double *__restrict__ f_out,
+                                                             int32_t *__restrict__ iters_out, double *__restrict__ dmin_out) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= A.n) return;
+    for (int a = 0; a < nd; ++a) q_out[n * nd + a] = A.q[a * A.ld + n];
+    f_out[n] = A.fpose[n];
+    if (iters_out) iters_out[n] = A.its[n];
+    if (dmin_out) {
+        double dm = CUDART_INF;
+        for (int s = 0; s < A.n_sph; ++s) dm = fmin(dm, Vfin[s * A.ld + n]);
+        dmin_out[n] = dm;
+    }
+}
+
+}  // namespace kin

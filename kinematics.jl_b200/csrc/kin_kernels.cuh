@@ -20,10 +20,6 @@
 #include "kin_program.h"
 #include "kin_device_math.cuh"
 
-#ifndef KIN_LM_MAX_DOF
-#define KIN_LM_MAX_DOF 16
-#endif
-
 // Debug build (-DKIN_DEBUG, kinematics.jl_b200/lib.py: build(debug=True) -> libkin_b200_debug.so): every table
 // index and scratch-slot index the kernels derive from the program tables is range-checked; a violation prints
 // the condition and traps.  This is the analogue of the reference's @debugassert (Kinematics.jl:25-30, cache.jl:24,35,
@@ -594,79 +590,5 @@ pose_residual_kernel(const real *__restrict__ T, const real *__restrict__ J, con
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Batched Levenberg-Marquardt step / accept (config 4).  One thread per problem.
-// ---------------------------------------------------------------------------------------------------
-constexpr int LM_MAX_DOF = KIN_LM_MAX_DOF;
-
-__global__ void __launch_bounds__(128)
-lm_step_kernel(long long n, int nd, int dim, const double *__restrict__ q, const double *__restrict__ e,
-               const double *__restrict__ J, const double *__restrict__ lambda, const double *__restrict__ lo,
-               const double *__restrict__ hi, double *__restrict__ q_try) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double H[LM_MAX_DOF * LM_MAX_DOF], g[LM_MAX_DOF], x[LM_MAX_DOF];
-    bool fr[LM_MAX_DOF];
-    const double *Ji = J + i * (long long)dim * nd, *ei = e + i * (long long)dim, *qi = q + i * (long long)nd;
-    for (int a = 0; a < nd; ++a) {
-        g[a] = 0.0;
-        for (int b = 0; b < nd; ++b) H[a * nd + b] = 0.0;
-    }
-    for (int r = 0; r < dim; ++r) {            // H = J'J, g = J'e
-        const double er = ei[r];
-        for (int a = 0; a < nd; ++a) {
-            const double ja = Ji[r * nd + a];
-            g[a] = fma(ja, er, g[a]);
-            for (int b = 0; b <= a; ++b) H[a * nd + b] = fma(ja, Ji[r * nd + b], H[a * nd + b]);
-        }
-    }
-    const double lam = lambda[i];
-    for (int a = 0; a < nd; ++a) {
-        const double qa = qi[a];
-        // a joint sitting on a limit whose gradient pushes outward is frozen
-        fr[a] = !(((qa <= lo[a] + 1e-12) && (g[a] > 0.0)) || ((qa >= hi[a] - 1e-12) && (g[a] < 0.0)));
-    }
-    for (int a = 0; a < nd; ++a) {
-        for (int b = 0; b < a; ++b) H[a * nd + b] = (fr[a] && fr[b]) ? H[a * nd + b] : 0.0;
-        H[a * nd + a] = fr[a] ? fma(lam, 1.0 + H[a * nd + a], H[a * nd + a]) : 1.0;
-        x[a] = fr[a] ? g[a] : 0.0;
-    }
-    // Cholesky H = L L' (lower triangle in place), then two triangular solves
-    for (int a = 0; a < nd; ++a) {
-        for (int b = 0; b <= a; ++b) {
-            double sum = H[a * nd + b];
-            for (int k = 0; k < b; ++k) sum = fma(-H[a * nd + k], H[b * nd + k], sum);
-            H[a * nd + b] = (a == b) ? sqrt(fmax(sum, 1e-300)) : sum / H[b * nd + b];
-        }
-    }
-    for (int a = 0; a < nd; ++a) {
-        double sum = x[a];
-        for (int k = 0; k < a; ++k) sum = fma(-H[a * nd + k], x[k], sum);
-        x[a] = sum / H[a * nd + a];
-    }
-    for (int a = nd - 1; a >= 0; --a) {
-        double sum = x[a];
-        for (int k = a + 1; k < nd; ++k) sum = fma(-H[k * nd + a], x[k], sum);
-        x[a] = sum / H[a * nd + a];
-    }
-    for (int a = 0; a < nd; ++a) q_try[i * (long long)nd + a] = fmin(fmax(qi[a] - x[a], lo[a]), hi[a]);
-}
-
-__global__ void __launch_bounds__(128)
-lm_accept_kernel(long long n, int nd, int dim, const double *__restrict__ q_try, const double *__restrict__ e_try,
-                 const double *__restrict__ J_try, const double *__restrict__ f_try, double *__restrict__ q,
-                 double *__restrict__ e, double *__restrict__ J, double *__restrict__ f, double *__restrict__ lambda) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const bool ok = f_try[i] < f[i];
-    double lam = lambda[i] * (ok ? 0.3 : 4.0);
-    lambda[i] = fmin(fmax(lam, 1e-9), 1e4);
-    if (!ok) return;
-    f[i] = f_try[i];
-    for (int a = 0; a < nd; ++a) q[i * (long long)nd + a] = q_try[i * (long long)nd + a];
-    for (int r = 0; r < dim; ++r) e[i * (long long)dim + r] = e_try[i * (long long)dim + r];
-    const long long jn = (long long)dim * nd;
-    for (long long k = 0; k < jn; ++k) J[i * jn + k] = J_try[i * jn + k];
-}
 
 }  // namespace kin

@@ -1,6 +1,7 @@
-"""The per-iteration evaluation of the reference's IK driver (inverse_kinematics.jl:38-50) on the B200
-backend, batched over independent problems, plus a batched damped-least-squares driver that uses it.
-The SLSQP solver itself (NLopt) is third-party and out of scope."""
+"""The per-iteration evaluations of the reference's IK driver (inverse_kinematics.jl:38-50) on the B200 backend,
+batched over independent problems; the device-resident batched solvers built on them (pose only: one kernel launch;
+collision constrained: one fused evaluation + one step kernel per iteration); and the reference's own single-problem
+driver with SLSQP (scipy's, the reference's SCIPY back-end; NLopt is third party and not installed)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -76,15 +77,27 @@ def ik_objective(m: Mechanism, link, joints, target_pose, with_rot=True):
     return f, g
 
 
-def ik_solve_device(m: Mechanism, link, joints, targets, q0, with_rot=True, iters=100, ftol=1e-10, lambda0=1e-2):
-    """The whole pose-only solve in ONE kernel launch (``kin_ik_solve``: device-resident Levenberg-Marquardt loop around
-    the generated FK + Euler-rate Jacobian of ``link``; no host round trip per iteration).  ``targets`` (N, 6),
-    ``q0`` (N, n_dof) CUDA tensors -> (q (N, n_dof), f (N,), iterations (N,) int32).  Raises ``KinError`` with code
-    ``ERR_UNAVAILABLE`` in the message when the run-time compiler is not available."""
+def ik_solve_device(m: Mechanism, link, joints, targets, q0, with_rot=True, iters=100, ftol=1e-10, lambda0=1e-2,
+                    sscc=None, sdf=None, margin=0.02, coll_weight=100.0, ctol=1e-6):
+    """The device-resident batched solve (``kin_ik_solve``).  ``targets`` (N, 6), ``q0`` (N, n_dof) CUDA tensors.
+
+    Without ``sscc`` / ``sdf``: the whole pose-only Levenberg-Marquardt solve in ONE kernel launch around the generated
+    FK + Euler-rate Jacobian of ``link`` -> (q (N, n_dof), f (N,), iterations (N,) int32); without the run-time
+    compiler the same method runs as one ``kin_eval`` + one step kernel per iteration.
+
+    With ``sscc`` and ``sdf``: the reference's constrained problem (inverse_kinematics.jl:14-19: the same objective
+    subject to ``dists - margin >= 0``) from the warm start ``q0``, by an augmented-Lagrangian Levenberg-Marquardt
+    iteration that issues one fused ``kin_eval`` and one step kernel per iteration with no host round trip
+    (csrc/kin_ik_coll.cuh) -> (q, f, iterations, dmin) with dmin (N,) the smallest signed sphere distance at q."""
     import torch
+    collide = sscc is not None and sdf is not None
     q0 = torch.as_tensor(q0, dtype=torch.float64, device="cuda").contiguous()
     set_joint_angles(m, joints, q0)            # defines the configuration columns (and the device model) as every caller does
-    dm = device_model(m)
+    if collide:
+        from .collision import _prepare
+        _, dm = _prepare(sscc, joints, sdf)
+    else:
+        dm = device_model(m)
     nb = 3 if m.with_base else 0
     lo = np.ascontiguousarray([j.lower_limit for j in joints] + [-np.inf] * nb, dtype=np.float64)
     hi = np.ascontiguousarray([j.upper_limit for j in joints] + [np.inf] * nb, dtype=np.float64)
@@ -100,109 +113,83 @@ def ik_solve_device(m: Mechanism, link, joints, targets, q0, with_rot=True, iter
     c.lower, c.upper = lo.ctypes.data_as(C.POINTER(C.c_double)), hi.ctypes.data_as(C.POINTER(C.c_double))
     c.q_out, c.f_out, c.iters_out = q.data_ptr(), f.data_ptr(), its.data_ptr()
     c.stream = torch.cuda.current_stream().cuda_stream
+    if collide:
+        dmin = torch.empty(N, dtype=torch.float64, device="cuda")
+        c.collision, c.margin, c.coll_weight, c.ctol, c.dmin_out = 1, float(margin), float(coll_weight), float(ctol), dmin.data_ptr()
     _lib.check(_lib.lib().kin_ik_solve(dm.h, C.byref(c)))
-    return q, f, its
+    return (q, f, its, dmin) if collide else (q, f, its)
+
+
+def _seed_limits(m, joints):
+    import torch
+    nb = 3 if m.with_base else 0
+    lo = torch.tensor([j.lower_limit if np.isfinite(j.lower_limit) else -np.pi for j in joints] + [-1.0, -1.0, -np.pi][:nb],
+                      device="cuda", dtype=torch.float64)
+    hi = torch.tensor([j.upper_limit if np.isfinite(j.upper_limit) else np.pi for j in joints] + [1.0, 1.0, np.pi][:nb],
+                      device="cuda", dtype=torch.float64)
+    return lo, hi
 
 
 def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=True, iters=100, ftol=1e-10,
-                             sscc=None, sdf=None, margin=0.02, coll_weight=100.0, use_bistage=True, restarts=0, tol=1e-3, seed=0):
-    """Batched IK for N independent pose targets (config 4 of BASELINE.json): Levenberg-Marquardt with
-    per-problem adaptive damping and an active set for the joint limits on the reference's objective
-    f = |[p - p_t; rpy - rpy_t]|^2 (inverse_kinematics.jl:38-50), iterates clamped to the joint limits
-    (:52-63).
+                             sscc=None, sdf=None, margin=0.02, coll_weight=100.0, use_bistage=True, restarts=0, tol=1e-3, seed=0,
+                             coll_iters=60, ctol=1e-6, return_dmin=False):
+    """Batched IK for N independent pose targets (config 4 of BASELINE.json) on the reference's objective
+    f = |[p - p_t; rpy - rpy_t]|^2 (inverse_kinematics.jl:38-50), iterates clamped to the joint limits (:52-63).
 
     Without ``sscc`` / ``sdf`` the whole solve is one kernel launch (``ik_solve_device``); ``restarts`` > 0 re-solves
     the problems that did not reach ``tol`` (max |pose error|, as test/test_inverse_kinematics.jl:22-23 measures it)
     from random in-limit seeds, that many times -- a local method started from one seed leaves a few per cent of the
     reachable targets in a local minimum at a joint limit.
 
-    With ``sscc`` and ``sdf`` the reference's collision constraint ``dists - margin >= 0`` of the
-    two-stage driver (inverse_kinematics.jl:1-21, IneqConst with margin 0.02) enters as a quadratic penalty
-    coll_weight * sum(max(0, margin - d_s)^2): its residual rows and Jacobian rows come from
-    compute_coll_dists_and_grads (truncation margin + 0.05, as planning.jl:56); every evaluation of the
-    residuals and Jacobians is a libkin_b200 call over the whole batch, and so are the LM step (normal
-    equations + Cholesky per problem, kin_lm_step) and the accept / damping update (kin_lm_accept).  (The HARD
-    constraint is what ``inverse_kinematics`` below enforces with SLSQP, one problem at a time.)
-    Angle residuals are wrapped to (-pi, pi] for stepping.
-    ``targets`` (N, 6) [x y z roll pitch yaw], ``q0`` (N, n_dof).  Returns (q, f) with f the pose objective."""
+    With ``sscc`` and ``sdf`` the reference's two-stage driver (inverse_kinematics.jl:1-21) runs on the device for the
+    whole batch: the collision-free warm start (``use_bistage``, :8-13) and then the solve under the HARD constraint
+    ``dists - margin >= 0`` (IneqConst with margin 0.02, :14-19), an augmented-Lagrangian Levenberg-Marquardt loop of
+    at most ``coll_iters`` (fused evaluation, step kernel) launch pairs without a host round trip.  ``restarts``
+    re-seeds the problems that end with pose error > ``tol`` or a distance below ``margin - ctol`` (a local method can
+    end pressed against the obstacle on the wrong side of it).
+    ``targets`` (N, 6) [x y z roll pitch yaw], ``q0`` (N, n_dof).  Returns (q, f) with f the pose objective
+    (and the smallest signed sphere distance per problem with ``return_dmin``)."""
     import torch
-    from .collision import compute_coll_dists_and_grads
-    from .planning import pose_constraint
     collide = sscc is not None and sdf is not None
     targets = torch.as_tensor(targets, dtype=torch.float64, device="cuda")
-    if not collide or use_bistage:
-        # pose-only solve (the whole of it, or the warm start of inverse_kinematics.jl:8-13)
-        try:
-            q, f, _ = ik_solve_device(m, link, joints, targets, q0, with_rot=with_rot, iters=iters, ftol=ftol)
-            if restarts > 0:
-                nb = 3 if m.with_base else 0
-                lo = torch.tensor([j.lower_limit if np.isfinite(j.lower_limit) else -np.pi for j in joints] + [-1.0, -1.0, -np.pi][:nb],
-                                  device="cuda", dtype=torch.float64)
-                hi = torch.tensor([j.upper_limit if np.isfinite(j.upper_limit) else np.pi for j in joints] + [1.0, 1.0, np.pi][:nb],
-                                  device="cuda", dtype=torch.float64)
-                gen = torch.Generator(device="cuda").manual_seed(seed)
-                for _ in range(restarts):
-                    # f = sum of squared residuals: max |e| <= tol is implied by f <= tol^2, and f > rows * tol^2 rules it out
-                    bad = torch.nonzero(f > tol * tol, as_tuple=False).squeeze(1)
-                    if bad.numel() == 0:
-                        break
-                    qs = lo + (hi - lo) * torch.rand((bad.numel(), q.shape[1]), generator=gen, device="cuda", dtype=torch.float64)
-                    q2, f2, _ = ik_solve_device(m, link, joints, targets[bad], qs, with_rot=with_rot, iters=iters, ftol=ftol)
-                    better = f2 < f[bad]
-                    q[bad[better]] = q2[better]
-                    f[bad[better]] = f2[better]
-            if not collide:
-                set_joint_angles(m, joints, q)
-                return q, f
-            q0 = q
-        except _lib.KinError as err:
-            if "error %d" % _lib.ERR_UNAVAILABLE not in str(err):
-                raise
-            if collide:      # no run-time compiler: the warm start runs on the multi-kernel path below
-                q0, _ = inverse_kinematics_batch(m, link, joints, targets, q0, with_rot=with_rot, iters=iters, ftol=ftol,
-                                                 restarts=0, use_bistage=False)
-    nb = 3 if m.with_base else 0
-    lo = torch.tensor([j.lower_limit for j in joints] + [-np.inf] * nb, device="cuda", dtype=torch.float64)
-    hi = torch.tensor([j.upper_limit for j in joints] + [np.inf] * nb, device="cuda", dtype=torch.float64)
-    q = torch.as_tensor(q0, dtype=torch.float64, device="cuda").contiguous().clone()
-    N, nd = q.shape
-    sw = float(np.sqrt(coll_weight))
-    L_ = _lib.lib()
-    stream = torch.cuda.current_stream().cuda_stream
+    q0 = torch.as_tensor(q0, dtype=torch.float64, device="cuda")
 
-    def evaluate(qq):
-        """-> e (N, dim), J (N, dim, n_dof) = d e / d q (both contiguous), f = |e|^2, f_pose"""
-        set_joint_angles(m, joints, qq)
-        e, JT = pose_constraint(m, link, joints, targets, with_rot)     # e (N, rows) = now - target, JT (N, nd, rows) view
-        J = JT.permute(0, 2, 1)                                          # the AoS storage itself: (N, rows, nd)
-        if with_rot:
-            e[:, 3:] = torch.remainder(e[:, 3:] + np.pi, 2 * np.pi) - np.pi
-        f_pose = (e * e).sum(dim=1)
+    def pose_only(tg, qs):
+        return ik_solve_device(m, link, joints, tg, qs, with_rot=with_rot, iters=iters, ftol=ftol)[:2]
+
+    def solve(tg, qs):
+        """-> q, f, good (N,) bool"""
         if not collide:
-            return e, J.contiguous(), f_pose, f_pose
-        # penalty rows r_s = sw * max(0, margin - d_s); d r_s / d q = -sw * grads[:, s] where active
-        d, g = compute_coll_dists_and_grads(sscc, joints, sdf, truncation_dist=margin + 0.05)
-        act = (d < margin).to(q.dtype)
-        e = torch.cat([e, sw * (margin - d) * act], dim=1)
-        J = torch.cat([J, (-sw * g * act[:, None, :]).permute(0, 2, 1)], dim=1).contiguous()
-        return e, J, (e * e).sum(dim=1), f_pose
+            q, f = pose_only(tg, qs)
+            return q, f, None, f <= tol * tol
+        if use_bistage:
+            qs, _ = pose_only(tg, qs)
+        q, f, _, dmin = ik_solve_device(m, link, joints, tg, qs, with_rot=with_rot, iters=coll_iters, ftol=ftol, sscc=sscc, sdf=sdf,
+                                        margin=margin, coll_weight=coll_weight, ctol=ctol)
+        # f = sum of squared residuals: max |e| <= tol is implied by f <= tol^2
+        return q, f, dmin, (f <= tol * tol) & (dmin >= margin - 10 * ctol)
 
-    e, J, f, f_pose = evaluate(q)
-    e, J = e.contiguous(), J.contiguous()
-    dim = e.shape[1]
-    lam = torch.full((N,), 1e-2, dtype=torch.float64, device="cuda")
-    q_try = torch.empty_like(q)
-    for it in range(iters):
-        _lib.check(L_.kin_lm_step(N, nd, dim, q.data_ptr(), e.data_ptr(), J.data_ptr(), lam.data_ptr(), lo.data_ptr(),
-                                  hi.data_ptr(), q_try.data_ptr(), stream))
-        e_t, J_t, f_t, fp_t = evaluate(q_try)
-        f_pose = torch.where(f_t < f, fp_t, f_pose)
-        _lib.check(L_.kin_lm_accept(N, nd, dim, q_try.data_ptr(), e_t.contiguous().data_ptr(), J_t.data_ptr(), f_t.data_ptr(),
-                                    q.data_ptr(), e.data_ptr(), J.data_ptr(), f.data_ptr(), lam.data_ptr(), stream))
-        if it % 8 == 7 and float(f.max()) < ftol:      # the convergence flag is read back every 8th iteration only
-            break
+    q, f, dmin, good = solve(targets, q0)
+    if restarts > 0:
+        lo, hi = _seed_limits(m, joints)
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        for _ in range(restarts):
+            bad = torch.nonzero(~good, as_tuple=False).squeeze(1)
+            if bad.numel() == 0:
+                break
+            qs = lo + (hi - lo) * torch.rand((bad.numel(), q.shape[1]), generator=gen, device="cuda", dtype=torch.float64)
+            q2, f2, d2, g2 = solve(targets[bad], qs)
+            # a restart replaces a failed problem when it succeeds, or (pose only) when it is closer
+            better = g2 if collide else (f2 < f[bad])
+            q[bad[better]] = q2[better]
+            f[bad[better]] = f2[better]
+            if collide:
+                dmin[bad[better]] = d2[better]
+            good[bad[better]] = g2[better]
     set_joint_angles(m, joints, q)
-    return q, f_pose
+    if collide and return_dmin:
+        return q, f, dmin
+    return q, f
 
 
 def inverse_kinematics(m: Mechanism, link, joints, target_pose, sscc=None, sdf=None, use_bistage=True, ftol=1e-5,

@@ -53,7 +53,9 @@ class KinCall(C.Structure):
 class KinIkCall(C.Structure):
     _fields_ = [("n", C.c_int64), ("link_id", C.c_int32), ("with_rot", C.c_int32), ("iters", C.c_int32), ("ftol", C.c_double),
                 ("lambda0", C.c_double), ("targets", C.c_void_p), ("q0", C.c_void_p), ("lower", _dp), ("upper", _dp),
-                ("q_out", C.c_void_p), ("f_out", C.c_void_p), ("iters_out", C.c_void_p), ("stream", C.c_void_p)]
+                ("q_out", C.c_void_p), ("f_out", C.c_void_p), ("iters_out", C.c_void_p), ("stream", C.c_void_p),
+                ("collision", C.c_int32), ("reserved_", C.c_int32), ("margin", C.c_double), ("coll_weight", C.c_double),
+                ("ctol", C.c_double), ("dmin_out", C.c_void_p)]
 
 
 ERR_UNAVAILABLE = -6
@@ -61,7 +63,7 @@ ERR_UNAVAILABLE = -6
 EXPORTS = ["kin_last_error", "kin_abi_version", "kin_build_id", "kin_debug_build", "kin_model_create", "kin_model_destroy", "kin_model_set_spheres",
            "kin_model_set_boxes", "kin_model_n_dof", "kin_model_n_spheres", "kin_model_n_boxes", "kin_eval",
            "kin_eval_host", "kin_fk_links", "kin_fk_jacobian", "kin_collision", "kin_launch_count",
-           "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual", "kin_pose_residual_multi", "kin_lm_step", "kin_lm_accept", "kin_probe_fp64",
+           "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual", "kin_pose_residual_multi", "kin_probe_fp64",
            "kin_jit_status", "kin_jit_stats", "kin_codegen_dump", "kin_ik_solve"]
 
 
@@ -202,8 +204,6 @@ def lib():
                                         C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kin_pose_residual_multi.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, _ip, _ip,
                                               C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.kin_lm_step.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 8
-        L.kin_lm_accept.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 10
         L.kin_probe_fp64.argtypes = [_dp, _dp, _dp]
         L.kin_ik_solve.argtypes = [C.c_void_p, C.POINTER(KinIkCall)]
         L.kin_jit_status.restype = C.c_char_p

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L.EXPORTS)
     for name in declared:
         assert hasattr(L.lib(), name), name
-    assert L.lib().kin_abi_version() == 2
+    assert L.lib().kin_abi_version() == 3
     assert L.lib().kin_build_id().decode() == L.source_id()        # the loaded binary is the one built from these sources
 
 

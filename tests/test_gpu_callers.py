@@ -129,40 +129,102 @@ def test_batched_ik_reaches_reachable_targets():
     assert np.all(qn >= lo - 1e-12) and np.all(qn <= hi + 1e-12)
 
 
-def test_batched_collision_aware_ik():
-    """Config 4 with the collision constraint of the reference's two-stage IK (inverse_kinematics.jl:1-21,
-    margin 0.02) against the thin box of test/test_planning.jl:23-25: about a quarter of the unconstrained
-    solutions run an arm sphere through the box; the penalised solve clears all of them.  (A penalty
-    trades pose error for clearance where the margin is active, so somewhat fewer targets end within 1e-3
-    than with SLSQP's hard constraint; the solver itself is out of scope, the evaluations are what is tested.)"""
-    m, joints, sscc = scenes.product_fetch(False)
-    link = K.find_link(m, "gripper_link")
+def _thin_box():
     pose = np.eye(4)
     pose[:3, 3] = [0.4, -0.25, 0.8]
-    box = K.BoxSDF(K.Transform(pose), [0.05, 0.05, 0.5])
+    return pose, [0.05, 0.05, 0.5]                         # the pillar of test/test_planning.jl:23-25
+
+
+def test_batched_collision_aware_ik():
+    """Config 4 with the reference's HARD collision constraint (inverse_kinematics.jl:14-19: dists - 0.02 >= 0 after the
+    collision-free warm start) solved on the device for the whole batch (kin_ik_solve with collision = 1).
+
+    Targets are feasible by construction: gripper poses of random configurations that clear the pillar of
+    test/test_planning.jl:23-25 by 0.03, with the gripper behind / beside the pillar.  The pose-only solutions from the
+    common seed violate the margin for part of them (the scenario does exercise the constraint); the constrained
+    solve must end within 1e-3 of the pose (test_inverse_kinematics.jl:22-23) AND with every sphere at >= margin,
+    for >= 90 % of the targets from the one seed and >= 97 % with three re-seeded restarts.  The reported objective
+    and smallest distance are checked against the oracle at the returned configurations."""
+    m, joints, sscc = scenes.product_fetch(False)
+    mo, jo, so = scenes.oracle_fetch(False)
+    link, link_o = K.find_link(m, "gripper_link"), R.find_link(mo, "gripper_link")
+    pose, width = _thin_box()
+    box, box_o = K.BoxSDF(K.Transform(pose), width), R.BoxSDF(pose, width)
+    margin, N = 0.02, 1024
+    qc = scenes.random_configs(jo, 60 * N, False, seed=3)
+    K.set_joint_angles(m, joints, dev(qc))
+    d = K.compute_coll_dists(sscc, joints, box).amin(dim=1).cpu().numpy()
+    p = K.get_transform(m, link)[:, :, 3].cpu().numpy()
+    keep = (d > 0.03) & (p[:, 0] > 0.5) & (np.abs(p[:, 1] + 0.25) < 0.3) & (p[:, 2] > 0.5) & (p[:, 2] < 1.1)
+    idx = np.nonzero(keep)[0][:N]
+    assert idx.size == N
+    tg = _pose_targets(m, joints, link, qc[idx])
+    q0 = np.tile(np.array([0.2, 0, 0, 0, 0.5, 0, 0.5, 0]), (N, 1))
+
+    def outcome(q):
+        err = _pose_err(m, joints, link, q, tg)
+        K.set_joint_angles(m, joints, q)
+        dm = K.compute_coll_dists(sscc, joints, box).amin(dim=1)
+        return (err < 1e-3).cpu().numpy(), (dm >= margin - 1e-5).cpu().numpy(), dm.cpu().numpy()
+
+    q_free, _ = K.inverse_kinematics_batch(m, link, joints, dev(tg), dev(q0), with_rot=True, iters=40)
+    r0, c0, _ = outcome(q_free)
+    lib = K.load_library()
+    n0 = lib.kin_launch_count()
+    q1, f1, its, dmin1 = K.ik_solve_device(m, link, joints, dev(tg), q_free, with_rot=True, iters=60, sscc=sscc, sdf=box, margin=margin)
+    torch.cuda.synchronize()
+    # init + 61 x (kin_eval, step) + the final distance evaluation + finish: no other launches, nothing read back
+    assert lib.kin_launch_count() - n0 == 1 + 61 * 2 + 2
+    r1, c1, dm1 = outcome(q1)
+    np.testing.assert_allclose(dmin1.cpu().numpy(), dm1, rtol=1e-12, atol=1e-12)
+    q2, f2, dmin2 = K.inverse_kinematics_batch(m, link, joints, dev(tg), dev(q0), with_rot=True, iters=40, sscc=sscc, sdf=box, margin=margin,
+                                               restarts=3, return_dmin=True)
+    r2, c2, dm2 = outcome(q2)
+    pc = lambda t: 100 * float(np.mean(t))
+    print("IK vs thin box (feasible targets): pose-only reached %.1f %% / margin kept %.1f %% / both %.1f %%; constrained, one seed: "
+          "%.1f / %.1f / %.1f %% (mean %.1f iterations); with 3 restarts: %.1f / %.1f / %.1f %%"
+          % (pc(r0), pc(c0), pc(r0 & c0), pc(r1), pc(c1), pc(r1 & c1), float(its.double().mean()), pc(r2), pc(c2), pc(r2 & c2)))
+    assert pc(c0) < 97.0                     # the scenario does exercise the constraint
+    assert pc(c1) > 99.0 and pc(r1 & c1) >= 90.0
+    assert pc(r2 & c2) >= 97.0
+    lo = np.array([j.lower_limit for j in joints])
+    hi = np.array([j.upper_limit for j in joints])
+    qn = q2.cpu().numpy()
+    assert np.all(qn >= lo - 1e-12) and np.all(qn <= hi + 1e-12)
+    # the oracle at the returned configurations: objective, distances, constraint
+    d_o, _, _ = R.batch_collision(so, jo, box_o, qn, with_grads=False)
+    np.testing.assert_allclose(dmin2.cpu().numpy(), d_o.min(axis=1), rtol=1e-12, atol=1e-12)
+    good = r2 & c2
+    assert np.all(d_o.min(axis=1)[good] >= margin - 1e-5)
+    fn = f2.cpu().numpy()
+    for n in range(0, N, 97):
+        fo, _ = R.ik_objective(mo, link_o, jo, qn[n], target_T(tg[n, :3], tg[n, 3:]), True)
+        if fn[n] < 1e-2:
+            np.testing.assert_allclose(fn[n], fo, rtol=1e-9, atol=1e-18)
+
+
+def test_batched_collision_aware_ik_arbitrary_targets():
+    """The same solve on targets drawn without regard to feasibility (a box of positions behind the pillar, identity
+    rotation; about 30 % of them cannot be reached with every sphere 0.02 clear -- repeated re-seeding of the
+    prototype profiles/proto_ik_coll.py saturates at 70 %): an infeasible problem must still end with the constraint
+    satisfied (the pose error is what gives), and the reached-and-clear share must be near that ceiling."""
+    m, joints, sscc = scenes.product_fetch(False)
+    link = K.find_link(m, "gripper_link")
+    pose, width = _thin_box()
+    box = K.BoxSDF(K.Transform(pose), width)
     N = 1024
     rng = np.random.default_rng(5)
     tg = np.zeros((N, 6))
     tg[:, 0], tg[:, 1], tg[:, 2] = rng.uniform(0.55, 0.8, N), rng.uniform(-0.3, 0.3, N), rng.uniform(0.7, 1.1, N)
     q0 = np.tile(np.array([0.2, 0, 0, 0, 0.5, 0, 0.5, 0]), (N, 1))
-
-    def outcome(q):
-        K.set_joint_angles(m, joints, q)
-        d = K.compute_coll_dists(sscc, joints, box)
-        v, _ = K.pose_constraint(m, link, joints, dev(tg), True)
-        v[:, 3:] = torch.remainder(v[:, 3:] + np.pi, 2 * np.pi) - np.pi
-        return v.abs().amax(dim=1) < 1e-3, d.amin(dim=1) > -1e-3
-
-    q_free, _ = K.inverse_kinematics_batch(m, link, joints, dev(tg), dev(q0), with_rot=True, iters=80)
-    r0, c0 = outcome(q_free)
-    q, _ = K.inverse_kinematics_batch(m, link, joints, dev(tg), dev(q0), with_rot=True, iters=80, sscc=sscc, sdf=box, margin=0.02)
-    r1, c1 = outcome(q)
-    f = lambda t: 100 * float(t.double().mean())
-    print("IK vs thin box: unconstrained reached %.1f %% / clear %.1f %% / both %.1f %%; constrained reached %.1f %% / clear %.1f %% / both %.1f %%"
-          % (f(r0), f(c0), f(r0 & c0), f(r1), f(c1), f(r1 & c1)))
-    assert f(c0) < 90.0                      # the scenario does exercise the constraint
-    assert f(c1) > 99.0
-    assert f(r1 & c1) > 55.0
+    q, f, dmin = K.inverse_kinematics_batch(m, link, joints, dev(tg), dev(q0), with_rot=True, iters=40, sscc=sscc, sdf=box, margin=0.02,
+                                            restarts=2, return_dmin=True)
+    reached = (_pose_err(m, joints, link, q, tg) < 1e-3).cpu().numpy()
+    clear = (dmin >= 0.02 - 1e-3).cpu().numpy()
+    print("IK vs thin box (arbitrary targets): reached %.1f %% / clear %.1f %% / both %.1f %%"
+          % (100 * reached.mean(), 100 * clear.mean(), 100 * (reached & clear).mean()))
+    assert clear.mean() > 0.97
+    assert (reached & clear).mean() > 0.62
 
 
 # ------------------------------------------------------------------------------------------------
@@ -450,7 +512,7 @@ def test_device_resident_ik_solve(with_base, monkeypatch):
     print("device IK (with_base=%s): %.2f %% within 1e-3 after one solve, %.2f %% with two restarts, mean iterations %.1f"
           % (with_base, 100 * ok1, 100 * (err2 < 1e-3).mean(), float(its.double().mean())))
     assert (err2 < 1e-3).mean() >= 0.99
-    # the multi-kernel path (kin_pose_residual + kin_lm_step + kin_lm_accept) it replaces: same method, same quality
+    # without the run-time compiler the same method runs as (kin_eval, step kernel) pairs: same quality
     monkeypatch.setenv("KIN_DISABLE_JIT", "1")
     q3, _ = K.inverse_kinematics_batch(m, link, joints, dev(tg[:1024]), dev(q0[:1024]), with_rot=True, iters=40)
     monkeypatch.delenv("KIN_DISABLE_JIT")

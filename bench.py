@@ -594,7 +594,7 @@ def main():
         feas = torch.nonzero(K.compute_coll_dists(sscc, joints, sdf).amin(dim=1) > 0.03).squeeze(1)
         tgc, q0c = tg[feas].contiguous(), q0[feas].contiguous()
         Nc = int(feas.numel())
-        K.inverse_kinematics_batch(m, gl, joints, tgc[:65536], q0c[:65536], with_rot=True, iters=40, sscc=sscc, sdf=sdf, coll_iters=2)   # warm-up (builds the large-batch kernels)
+        K.inverse_kinematics_batch(m, gl, joints, tgc, q0c, with_rot=True, iters=40, sscc=sscc, sdf=sdf, coll_iters=2)   # warm-up (builds the large-batch kernels, grows the workspace pool)
         torch.cuda.synchronize(dev)
         barrier()
         t0 = time.perf_counter()

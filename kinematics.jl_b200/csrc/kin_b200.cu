@@ -348,13 +348,15 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
     o.fd_cold = (int)env_ll("KIN_JIT_FD_COLD", 0);
     o.ksync = (int)env_ll("KIN_JIT_KSYNC", (o.coll && !tiled) ? 1 : 0);
     o.es32 = (o.layout == KIN_LAYOUT_SOA && (c->batch_stride ? c->batch_stride : c->n) < (1ll << 32)) ? (int)env_ll("KIN_JIT_ES32", 1) : 0;
+    if (o.layout == KIN_LAYOUT_AOS) o.keep_irrelevant = 0;     // (calls with keep_irrelevant never get here: jit_wanted)
     o.qbatch = 0;
     // input batching (kin_gen_skeleton.cuh): the FK / Jacobian-only kernels are bound by the DRAM write path and use
     // no other shared memory, so the configurations of as many tiles as fit twice in ~200 KB are fetched per batch
     // behind a grid-wide barrier (one CTA per SM, cooperative launch)
     if (h.n_dof > 0 && !std::getenv("KIN_JIT_NO_QBATCH")) {
         const size_t rs = o.precision ? sizeof(float) : sizeof(double);
-        const size_t budget = std::min<size_t>((size_t)(m ? m->dev_smem : 227 * 1024), 200 * 1024);
+        size_t budget = std::min<size_t>((size_t)(m ? m->dev_smem : 227 * 1024), 200 * 1024);
+        if (o.layout == KIN_LAYOUT_AOS) budget -= std::min<size_t>(budget, 24 * 1024);     // room for the output stages
         // measured (profiles/sweep_jit.py, 2^24 configurations): 128 threads x 12 tiles per batch, one CTA per SM:
         // 8.72 -> 7.78 ms (0.84 -> 0.94 of the HBM peak); the collision kernels need their shared memory for the
         // per-configuration scratch and are not write-bound: no batching there unless asked for (KIN_JIT_QBATCH_COLL)
@@ -370,7 +372,9 @@ bool jit_wanted(const KinModel *m, const KinCall *c, const DeviceProgram *dp, bo
     (void)m;
     if (std::getenv("KIN_DISABLE_JIT")) return false;
     const bool small = c->n <= env_ll("KIN_JIT_WARP_MAX", kWarpMaxBatch) && (!c->vals_out || dp->prog.h.n_sph <= 32);
-    if (c->layout == KIN_LAYOUT_AOS && !small) return false;       // AoS: only the small-batch kernel is specialised
+    // large AoS batches: outputs staged through shared memory (kin_gen_skeleton.cuh: aos_flush); get_jacobian!
+    // semantics (columns left untouched) cannot be staged and stay with the interpreting kernel
+    if (c->layout == KIN_LAYOUT_AOS && !small && c->J_out && c->keep_irrelevant) return false;
     if (c->vals_out && dp->prog.h.n_sph > 0 && dp->prog.h.n_dof > 16) return false;     // frames would not fit in registers
     if (c->n < env_ll("KIN_JIT_MIN_BATCH", kJitMinBatch) && !std::getenv("KIN_FORCE_JIT")) {
         // a small batch: worth a specialised (one warp per configuration) kernel once the same program keeps being
@@ -409,6 +413,8 @@ size_t jit_smem(const kin::GenOptions &o, const kin::ProgHeader &h, const JitKer
     size_t reals = 0;
     if (o.warp) return 0;                  // the one-warp-per-configuration kernel keeps everything in registers
     if (o.coll) reals += (((size_t)h.n_box * kin::BOX_REALS + h.n_sph + 1) & ~size_t(1)) + (size_t)k.slots * k.block;
+    if (o.layout == KIN_LAYOUT_AOS)      // the warps' output stages (AOS_STAGE_ROWS x 33 per warp)
+        reals += (size_t)(k.block / 32) * 33 * (std::max(12, (int)h.n_dof) + (o.coll ? 2 * kin::SPH_GROUP : 0));
     if (o.qbatch > 0) reals += (size_t)2 * o.qbatch * h.n_dof * k.block;
     return rs * reals;
 }

@@ -135,10 +135,15 @@ struct Frame {
 
 bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std::string &err) {
     const ProgHeader &h = p.h;
-    if (o.layout != 0 && o.layout != 2 && !(o.layout == 1 && o.warp)) {
-        err = "only the SoA and tiled layouts are specialised (AoS: small batches only)";
+    // AoS, one thread per configuration: the outputs of a warp are staged through shared memory in chunks of at most
+    // AOS_CHUNK values per record (KPUT into a stage row, KFLUSH_* writes 32 records x chunk with the lanes running
+    // along the records: whole sectors); get_jacobian! semantics (columns left untouched) cannot be staged
+    const bool aos = o.layout == 1 && !o.warp && !o.ik;
+    if (aos && o.want_J && o.keep_irrelevant) {
+        err = "AoS with keep_irrelevant is not specialised";
         return false;
     }
+    constexpr int AOS_CHUNK = 12;
     if (h.n_dof > 32) { err = "too many columns"; return false; }
     const bool f32 = o.precision == 1;
     Emitter E(f32);
@@ -247,9 +252,16 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
             const TfV Tl = tf_mul_const(E, T, ar, ai[1] & AF_R_IDENTITY);
             if (do_T) {                        // get_transform, as 3x4 column-major
                 const int base = 12 * ai[0];
-                for (int c = 0; c < 3; ++c)
-                    for (int r = 0; r < 3; ++r) E.os << "KST_T(" << base + c * 3 + r << ", " << E.str(Tl.r[r * 3 + c]) << ");\n";
-                for (int r = 0; r < 3; ++r) E.os << "KST_T(" << base + 9 + r << ", " << E.str(Tl.p[r]) << ");\n";
+                if (aos) {
+                    for (int c = 0; c < 3; ++c)
+                        for (int r = 0; r < 3; ++r) E.os << "KPUT(" << c * 3 + r << ", " << E.str(Tl.r[r * 3 + c]) << ");\n";
+                    for (int r = 0; r < 3; ++r) E.os << "KPUT(" << 9 + r << ", " << E.str(Tl.p[r]) << ");\n";
+                    E.os << "KFLUSH_T(" << base << ", 12);\n";
+                } else {
+                    for (int c = 0; c < 3; ++c)
+                        for (int r = 0; r < 3; ++r) E.os << "KST_T(" << base + c * 3 + r << ", " << E.str(Tl.r[r * 3 + c]) << ");\n";
+                    for (int r = 0; r < 3; ++r) E.os << "KST_T(" << base + 9 + r << ", " << E.str(Tl.p[r]) << ");\n";
+                }
             }
             if (do_J) {                        // get_jacobian, algorithm.jl:83-114
                 const int kbase = ai[2] * rows * ND;
@@ -261,8 +273,16 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
                     for (int i = 0; i < 9; ++i) E.os << "TL.r[" << i << "] = " << E.str(Tl.r[i]) << "; ";
                     E.os << "\nTL.p[0] = TL.p[1] = TL.p[2] = real(0);\nrpy_rate_coeffs(TL, " << kk << "); }\n";
                 }
+                // AoS: chunks of whole columns, at most AOS_CHUNK values, flushed after their last column
+                const int cols_per_chunk = AOS_CHUNK / rows;
+                int chunk_k0 = kbase;
+                auto stj = [&](int k, const std::string &v) -> std::string {
+                    if (aos) return "KPUT(" + std::to_string(k - chunk_k0) + ", " + v + ");";
+                    return "KST_J(" + std::to_string(k) + ", " + v + ");";
+                };
                 for (int j = 0; j < ND; ++j) {
                     const int kc = kbase + j * rows;
+                    if (aos && j % cols_per_chunk == 0) chunk_k0 = kc;
                     if ((mask >> j) & 1u) {
                         const Frame &f = frames[j];
                         if (!f.set) { err = "Jacobian column of a joint that has not been visited"; return false; }
@@ -274,29 +294,30 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
                             cy = E.fma(f.a[2], dx, E.neg(E.mul(f.a[0], dz)));
                             cz = E.fma(f.a[0], dy, E.neg(E.mul(f.a[1], dx)));
                         } else { cx = f.a[0]; cy = f.a[1]; cz = f.a[2]; }
-                        E.os << "KST_J(" << kc << ", " << E.str(cx) << "); KST_J(" << kc + 1 << ", " << E.str(cy) << "); KST_J(" << kc + 2
-                             << ", " << E.str(cz) << ");\n";
+                        E.os << stj(kc, E.str(cx)) << " " << stj(kc + 1, E.str(cy)) << " " << stj(kc + 2, E.str(cz)) << "\n";
                         if (o.with_rot) {
                             if (rev) {
                                 if (o.rpy_jac) {
                                     E.os << "{ real o3, o4, o5; rpy_rows(" << kk << ", " << E.str(f.a[0]) << ", " << E.str(f.a[1]) << ", "
-                                         << E.str(f.a[2]) << ", o3, o4, o5); KST_J(" << kc + 3 << ", o3); KST_J(" << kc + 4 << ", o4); KST_J("
-                                         << kc + 5 << ", o5); }\n";
+                                         << E.str(f.a[2]) << ", o3, o4, o5); " << stj(kc + 3, "o3") << " " << stj(kc + 4, "o4") << " "
+                                         << stj(kc + 5, "o5") << " }\n";
                                 } else {
-                                    for (int r = 0; r < 3; ++r) E.os << "KST_J(" << kc + 3 + r << ", " << E.str(f.a[r]) << "); ";
+                                    for (int r = 0; r < 3; ++r) E.os << stj(kc + 3 + r, E.str(f.a[r])) << " ";
                                     E.os << "\n";
                                 }
                             } else if (!o.keep_irrelevant || j >= DC) {
                                 // prismatic: rows 4:6 untouched by the reference (algorithm.jl:78-81), except in the base
                                 // block, which it always writes (algorithm.jl:102-104)
-                                for (int r = 3; r < 6; ++r) E.os << "KST_J(" << kc + r << ", real(0)); ";
+                                for (int r = 3; r < 6; ++r) E.os << stj(kc + r, "real(0)") << " ";
                                 E.os << "\n";
                             }
                         }
                     } else if (!o.keep_irrelevant) {
-                        for (int r = 0; r < rows; ++r) E.os << "KST_J(" << kc + r << ", real(0)); ";
+                        for (int r = 0; r < rows; ++r) E.os << stj(kc + r, "real(0)") << " ";
                         E.os << "\n";
                     }
+                    if (aos && ((j + 1) % cols_per_chunk == 0 || j + 1 == ND))
+                        E.os << "KFLUSH_J(" << chunk_k0 << ", " << (kc + rows - chunk_k0) << ");\n";
                 }
             }
         }

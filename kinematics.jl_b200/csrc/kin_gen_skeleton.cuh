@@ -57,14 +57,70 @@ __device__ __forceinline__ void phase2a_group(const int s0, const int ge, const 
     }
 }
 
+#if KAOS && !KWARP && !KIK
+// ---- AoS outputs of the one-thread-per-configuration kernel.  A thread owns a record, so a plain store would scatter
+//      8 bytes per lane over 32 records.  Instead every lane PUTs its values into rows of a warp-private stage in
+//      shared memory (row = component, 33 reals per row: conflict free) and the warp writes the 32 records of the
+//      chunk with the lanes running ALONG the records: CNT lanes per record, 32 / CNT records per store instruction,
+//      whole sectors.  REC (values per record) and CNT are compile-time, so lane -> (record, component) is computed
+//      once and every load / store of the loop has an immediate offset. ----
+constexpr int AOS_STAGE_G = KND > 12 ? KND : 12;                          // rows for link transforms / Jacobian chunks / gradients
+constexpr int AOS_STAGE_ROWS = AOS_STAGE_G + (KCOLL ? 2 * SPH_GROUP : 0);  // + distances and argmins of one sphere group
+constexpr int AOS_STAGE_LD = 33;
+
+template <typename T, int CNT, int REC, typename real_>
+__device__ __forceinline__ void aos_flush(const real_ *stw, const int row0, T *dst, const int nvalid, const int lane) {
+    constexpr int RPI = 32 / CNT;                      // records per store instruction
+    constexpr int ITERS = (32 + RPI - 1) / RPI;
+    const int rl = lane / CNT, c = lane - rl * CNT;
+    const real_ *src = stw + (row0 + c) * AOS_STAGE_LD + rl;
+    T *d = dst + (long long)rl * REC + c;
+    __syncwarp();
+    if (lane < RPI * CNT) {
+        #pragma unroll
+        for (int i = 0; i < ITERS; ++i)
+            if (i * RPI + rl < nvalid) __stcs(d + (long long)i * RPI * REC, *reinterpret_cast<const T *>(src + i * RPI));
+    }
+    __syncwarp();
+}
+template <typename T, int REC, typename real_>
+__device__ __forceinline__ void aos_flush_group(const real_ *stw, const int row0, T *dst, const int cnt, const int nvalid, const int lane) {
+    switch (cnt) {            // a sphere group holds 1 .. SPH_GROUP spheres
+        case 1: aos_flush<T, 1, REC>(stw, row0, dst, nvalid, lane); break;
+        case 2: aos_flush<T, 2, REC>(stw, row0, dst, nvalid, lane); break;
+        case 3: aos_flush<T, 3, REC>(stw, row0, dst, nvalid, lane); break;
+        default: aos_flush<T, 4, REC>(stw, row0, dst, nvalid, lane); break;
+    }
+}
+static_assert(SPH_GROUP <= 4, "aos_flush_group covers groups of up to 4 spheres");
+#endif
+
 // per sphere, IN sphere order (the shared scratch of collision.jl:76,90 makes the order observable)
+// AoS: Vp0 / Gp0 / Ap0 point at the FIRST record of the warp, es = lane, stw = the warp's stage, nvalid = records of the
+// warp inside the batch; the control flow below is warp-uniform except for the truncation branch, which re-converges
+// before each flush.
 template <typename real_, int ND, unsigned MASK>
 __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const real_ *__restrict__ tb,
                                               const real_ *__restrict__ rad, const real_ *cent0, real_ *stale0, const real_ *hand,
                                               const JFrame<real_> (&jfr)[ND > 0 ? ND : 1], const int grad_mode, const real_ trunc,
-                                              const real_ voff, real_ *Vp0, real_ *Gp0, int32_t *Ap0, const size_t es) {
+                                              const real_ voff, real_ *Vp0, real_ *Gp0, int32_t *Ap0, const size_t es
+#if KAOS && !KWARP && !KIK
+                                              , real_ *stw, const int nvalid
+#endif
+                                              ) {
     typedef real_ real;
     constexpr int BS = KBS;
+#if KAOS && !KWARP && !KIK
+    const int lane = (int)es;
+    real *stg = stw + lane;
+    #define KP2_V(s_, g_, v_) stg[(AOS_STAGE_G + (g_)) * AOS_STAGE_LD] = (v_)
+    #define KP2_A(s_, g_, v_) reinterpret_cast<int *>(&stg[(AOS_STAGE_G + SPH_GROUP + (g_)) * AOS_STAGE_LD])[0] = (v_)
+    #define KP2_G(j_, v_) stg[(j_) * AOS_STAGE_LD] = (v_)
+#else
+    #define KP2_V(s_, g_, v_) __stcs(Vp0 + (size_t)(s_) * es, (v_))
+    #define KP2_A(s_, g_, v_) __stcs(Ap0 + (size_t)(s_) * es, (v_))
+    #define KP2_G(j_, v_) __stcs(&Gp[(size_t)(j_) * es], (v_))
+#endif
     #pragma unroll 1
     for (int s = s0; s < ge; ++s) {
         const int g = s - s0;
@@ -72,39 +128,51 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
         const int kmin = reinterpret_cast<const int *>(&hand[(SPH_GROUP + g) * BS])[0];
         const real dist0 = dmin - rad[s];
         const bool truncated = dist0 > trunc;
-        __stcs(Vp0 + (size_t)s * es, (truncated ? trunc : dist0) - voff);
-        if (KARGMIN) __stcs(Ap0 + (size_t)s * es, kmin + 1);
+        KP2_V(s, g, (truncated ? trunc : dist0) - voff);
+        if (KARGMIN) KP2_A(s, g, kmin + 1);
         if (!KGRADS) continue;
+#if !(KAOS && !KWARP && !KIK)
         real *Gp = Gp0 + (size_t)s * ND * es;
+#endif
         if (truncated) {            // collision.jl:84-86
             #pragma unroll
-            for (int j = 0; j < ND; ++j) __stcs(&Gp[(size_t)j * es], real(0));
-            continue;
-        }
-        const real *cs = cent0 + 3 * s * BS;
-        const real px = cs[0], py = cs[BS], pz = cs[2 * BS];
-        real grad[3];
-        {
-            BoxRow<real> row;
-            load_box(tb + kmin * BOX_REALS, row);
-            box_gradient(row, KGRADMODE >= 0 ? KGRADMODE : grad_mode, px, py, pz, dmin, grad);
-        }
-        #pragma unroll
-        for (int j = 0; j < ND; ++j) {
-            real *st = stale0 + 3 * j * BS;
-            if ((MASK >> j) & 1u) {       // joint_jacobian!, algorithm.jl:65-81
-                real cx, cy, cz;
-                jac_col(jfr[j], ((KREV >> j) & 1u) != 0, px, py, pz, cx, cy, cz);
-                if (KSTALE) { st[0] = cx; st[BS] = cy; st[2 * BS] = cz; }
-                __stcs(&Gp[(size_t)j * es], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));   // transpose(grad) * jac
-            } else if (KSTALE) {          // column left over from an earlier sphere (collision.jl:76,90)
-                const real cx = st[0], cy = st[BS], cz = st[2 * BS];
-                __stcs(&Gp[(size_t)j * es], fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));
-            } else {
-                __stcs(&Gp[(size_t)j * es], real(0));      // a zero column (clean scratch): transpose(grad) * 0
+            for (int j = 0; j < ND; ++j) KP2_G(j, real(0));
+        } else {
+            const real *cs = cent0 + 3 * s * BS;
+            const real px = cs[0], py = cs[BS], pz = cs[2 * BS];
+            real grad[3];
+            {
+                BoxRow<real> row;
+                load_box(tb + kmin * BOX_REALS, row);
+                box_gradient(row, KGRADMODE >= 0 ? KGRADMODE : grad_mode, px, py, pz, dmin, grad);
+            }
+            #pragma unroll
+            for (int j = 0; j < ND; ++j) {
+                real *st = stale0 + 3 * j * BS;
+                if ((MASK >> j) & 1u) {       // joint_jacobian!, algorithm.jl:65-81
+                    real cx, cy, cz;
+                    jac_col(jfr[j], ((KREV >> j) & 1u) != 0, px, py, pz, cx, cy, cz);
+                    if (KSTALE) { st[0] = cx; st[BS] = cy; st[2 * BS] = cz; }
+                    KP2_G(j, fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));   // transpose(grad) * jac
+                } else if (KSTALE) {          // column left over from an earlier sphere (collision.jl:76,90)
+                    const real cx = st[0], cy = st[BS], cz = st[2 * BS];
+                    KP2_G(j, fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));
+                } else {
+                    KP2_G(j, real(0));      // a zero column (clean scratch): transpose(grad) * 0
+                }
             }
         }
+#if KAOS && !KWARP && !KIK
+        aos_flush<real, ND, ND * KS>(stw, 0, Gp0 + (size_t)s * ND, nvalid, lane);
+#endif
     }
+#if KAOS && !KWARP && !KIK
+    aos_flush_group<real, KS>(stw, AOS_STAGE_G, Vp0 + s0, ge - s0, nvalid, lane);
+    if (KARGMIN) aos_flush_group<int32_t, KS>(stw, AOS_STAGE_G + SPH_GROUP, Ap0 + s0, ge - s0, nvalid, lane);
+#endif
+    #undef KP2_V
+    #undef KP2_A
+    #undef KP2_G
 }
 
 }  // namespace kin
@@ -435,8 +503,14 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
     __syncthreads();
     const real trunc = (real)A.truncation_dist, voff = (real)A.vals_offset;
 #endif
-    const size_t es = KTILED ? size_t(32) : (size_t)A.ld;
-#if KES32 && !KTILED
+    const size_t es = KAOS ? size_t(1) : KTILED ? size_t(32) : (size_t)A.ld;
+#if KAOS
+    const int lane = tid & 31;
+    real *stw = smem_next + (tid >> 5) * (AOS_STAGE_ROWS * AOS_STAGE_LD);   // this warp's output stage
+    real *stg = stw + lane;
+    smem_next += (BS / 32) * (AOS_STAGE_ROWS * AOS_STAGE_LD);
+#endif
+#if KES32 && !KTILED && !KAOS
     // the component stride as a 32-bit value: address = base + es32 * (8 k) is ONE 32 x 32 -> 64-bit multiply-add per
     // store (IMAD.WIDE.U32 with the immediate 8 k) instead of a 64-bit multiply
     const unsigned es32 = (unsigned)A.ld;
@@ -452,7 +526,7 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
     const long long n_tiles = (A.n + BS - 1) / BS;
     auto q_ptr = [&](long long tile_) {
         const long long n_ = min(tile_ * BS + tid, (long long)A.n - 1);
-        return reinterpret_cast<const real *>(A.q) + (KTILED ? (n_ >> 5) * ((long long)KND * 32) + (n_ & 31) : n_);
+        return reinterpret_cast<const real *>(A.q) + (KAOS ? n_ * KND : KTILED ? (n_ >> 5) * ((long long)KND * 32) + (n_ & 31) : n_);
     };
 #if KQB > 0
     real *sq = smem_next;                                     // [2][KQB][KND][BS]
@@ -492,7 +566,7 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
     if ((long long)blockIdx.x < n_tiles) {
         const real *qp = q_ptr(blockIdx.x);
         #pragma unroll
-        for (int c = 0; c < KND; ++c) qcur[c] = __ldcs(qp + (size_t)c * es);
+        for (int c = 0; c < KND; ++c) qcur[c] = KAOS ? __ldg(qp + c) : __ldcs(qp + (size_t)c * es);
     }
     {
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -501,13 +575,28 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
                 const long long tn = tile + gridDim.x < n_tiles ? tile + gridDim.x : tile;
                 const real *qp = q_ptr(tn);
                 #pragma unroll
-                for (int c = 0; c < KND; ++c) qnxt[c] = __ldcs(qp + (size_t)c * es);
+                for (int c = 0; c < KND; ++c) qnxt[c] = KAOS ? __ldg(qp + c) : __ldcs(qp + (size_t)c * es);
             }
             #define KQ(c) qcur[c]
 #endif
             // ---------------- one tile: threads past the end of the batch redo the last configuration (identical
             //                  values, benign duplicate stores) ----------------
             const long long n = min(tile * BS + tid, (long long)A.n - 1);
+#if KAOS
+            // AoS: the warp's 32 records are written together from the stage (aos_flush); n_w0 = its first record
+            const long long n_w0 = tile * BS + (tid & ~31);
+            const int nvalid = (int)max(0ll, min(32ll, (long long)A.n - n_w0));
+            #define KREC_BASE(rec) (n_w0 * (long long)(rec))
+            #define KPUT(i, v) stg[(i) * AOS_STAGE_LD] = (v)
+#if KWANT_T
+            real *Tw = reinterpret_cast<real *>(A.T_out) + KREC_BASE(12 * KNFK);
+            #define KFLUSH_T(off, cnt) aos_flush<real, cnt, 12 * KNFK>(stw, 0, Tw + (off), nvalid, lane)
+#endif
+#if KWANT_J
+            real *Jw = reinterpret_cast<real *>(A.J_out) + KREC_BASE(KROWS * KND * KNJAC);
+            #define KFLUSH_J(off, cnt) aos_flush<real, cnt, KROWS * KND * KNJAC>(stw, 0, Jw + (off), nvalid, lane)
+#endif
+#else
             #define KREC_BASE(rec) (KTILED ? (n >> 5) * ((long long)(rec) * 32) + (n & 31) : n)
 #if KWANT_T
             real *Tn = reinterpret_cast<real *>(A.T_out) + KREC_BASE(12 * KNFK);
@@ -520,6 +609,7 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
             #define KST_J(k, v) __stcs(Jn + KOFF(k), (v))
 #else
             #define KST_J(k, v)
+#endif
 #endif
 #if KCOLL
             #define KCEN_SET(s, i, v) cent0[(3 * (s) + (i)) * BS] = (v)
@@ -538,7 +628,11 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
                 real *Gp0 = reinterpret_cast<real *>(A.grads_out) + KREC_BASE((long long)KND * KS);
                 int32_t *Ap0 = KARGMIN ? A.argmin_out + KREC_BASE(KS) : nullptr;
                 #define KP2AARGS tb, n_box, cent0, hand
+#if KAOS
+                #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, (size_t)lane, stw, nvalid
+#else
                 #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, es
+#endif
 #include "kin_gen_phase2.inc"
 #endif
             }

@@ -495,8 +495,8 @@ def _eval_all(m, joints, sscc, sdf, Q, layout, jit, monkeypatch, **kw):
 
 
 @pytest.mark.parametrize("with_base", [False, True])
-@pytest.mark.parametrize("layout", [L.SOA, L.TILED32])
-@pytest.mark.parametrize("n", [1, 77, 40000])
+@pytest.mark.parametrize("layout", [L.SOA, L.TILED32, L.AOS])
+@pytest.mark.parametrize("n", [1, 77, 40013])
 def test_specialised_kernel_is_bitwise_identical(layout, n, with_base, monkeypatch):
     """The NVRTC-compiled, model-specialised kernel (straight-line phase 1 with the model's constants folded in,
     phase 2 instantiated per relevance mask) against the interpreting ahead-of-time kernel on the same inputs: every

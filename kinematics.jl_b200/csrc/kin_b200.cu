@@ -414,7 +414,7 @@ size_t jit_smem(const kin::GenOptions &o, const kin::ProgHeader &h, const JitKer
     if (o.warp) return 0;                  // the one-warp-per-configuration kernel keeps everything in registers
     if (o.coll) reals += (((size_t)h.n_box * kin::BOX_REALS + h.n_sph + 1) & ~size_t(1)) + (size_t)k.slots * k.block;
     if (o.layout == KIN_LAYOUT_AOS)      // the warps' output stages (AOS_STAGE_ROWS x 33 per warp)
-        reals += (size_t)(k.block / 32) * 33 * (std::max(12, (int)h.n_dof) + (o.coll ? 2 * kin::SPH_GROUP : 0));
+        reals += (size_t)(k.block / 32) * (34 * std::max(12, (int)h.n_dof) + (o.coll ? 2 * 36 * kin::SPH_GROUP : 0));   // AOS_STAGE_REALS
     if (o.qbatch > 0) reals += (size_t)2 * o.qbatch * h.n_dof * k.block;
     return rs * reals;
 }

@@ -1,6 +1,7 @@
 // kin_codegen.cpp -- see kin_codegen.hpp.  Load-time only.
 #include "kin_codegen.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <sstream>
@@ -254,8 +255,8 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
                 const int base = 12 * ai[0];
                 if (aos) {
                     for (int c = 0; c < 3; ++c)
-                        for (int r = 0; r < 3; ++r) E.os << "KPUT(" << c * 3 + r << ", " << E.str(Tl.r[r * 3 + c]) << ");\n";
-                    for (int r = 0; r < 3; ++r) E.os << "KPUT(" << 9 + r << ", " << E.str(Tl.p[r]) << ");\n";
+                        for (int r = 0; r < 3; ++r) E.os << "KPUT(12, " << c * 3 + r << ", " << E.str(Tl.r[r * 3 + c]) << ");\n";
+                    for (int r = 0; r < 3; ++r) E.os << "KPUT(12, " << 9 + r << ", " << E.str(Tl.p[r]) << ");\n";
                     E.os << "KFLUSH_T(" << base << ", 12);\n";
                 } else {
                     for (int c = 0; c < 3; ++c)
@@ -275,14 +276,14 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
                 }
                 // AoS: chunks of whole columns, at most AOS_CHUNK values, flushed after their last column
                 const int cols_per_chunk = AOS_CHUNK / rows;
-                int chunk_k0 = kbase;
+                int chunk_k0 = kbase, chunk_cnt = 0;
                 auto stj = [&](int k, const std::string &v) -> std::string {
-                    if (aos) return "KPUT(" + std::to_string(k - chunk_k0) + ", " + v + ");";
+                    if (aos) return "KPUT(" + std::to_string(chunk_cnt) + ", " + std::to_string(k - chunk_k0) + ", " + v + ");";
                     return "KST_J(" + std::to_string(k) + ", " + v + ");";
                 };
                 for (int j = 0; j < ND; ++j) {
                     const int kc = kbase + j * rows;
-                    if (aos && j % cols_per_chunk == 0) chunk_k0 = kc;
+                    if (aos && j % cols_per_chunk == 0) { chunk_k0 = kc; chunk_cnt = std::min(cols_per_chunk, ND - j) * rows; }
                     if ((mask >> j) & 1u) {
                         const Frame &f = frames[j];
                         if (!f.set) { err = "Jacobian column of a joint that has not been visited"; return false; }

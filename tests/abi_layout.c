@@ -1,4 +1,4 @@
-/* Prints the layout gcc gives the two structs of include/kin_b200.h as JSON (tests/test_julia_binding.py compares it
+/* Prints the layout gcc gives the structs of include/kin_b200.h as JSON (tests/test_julia_binding.py compares it
  * with the struct declarations of julia/CUDABackend.jl and with the ctypes structures of kinematics.jl_b200/lib.py). */
 #include <stddef.h>
 #include <stdio.h>
@@ -21,6 +21,12 @@ int main(void) {
     F(KinCall, with_rot); F(KinCall, rpy_jac); F(KinCall, keep_irrelevant); F(KinCall, J_out); F(KinCall, truncation_dist);
     F(KinCall, grad_mode); F(KinCall, scratch_mode); F(KinCall, vals_out); F(KinCall, grads_out); F(KinCall, argmin_out);
     F(KinCall, vals_offset); F(KinCall, stream);
+    first = 1;
+    printf("\n  ]},\n  \"KinIkCall\": {\"size\": %zu, \"fields\": [\n", sizeof(KinIkCall));
+    F(KinIkCall, n); F(KinIkCall, link_id); F(KinIkCall, with_rot); F(KinIkCall, iters); F(KinIkCall, ftol); F(KinIkCall, lambda0);
+    F(KinIkCall, targets); F(KinIkCall, q0); F(KinIkCall, lower); F(KinIkCall, upper); F(KinIkCall, q_out); F(KinIkCall, f_out);
+    F(KinIkCall, iters_out); F(KinIkCall, stream); F(KinIkCall, collision); F(KinIkCall, reserved_); F(KinIkCall, margin);
+    F(KinIkCall, coll_weight); F(KinIkCall, ctol); F(KinIkCall, dmin_out);
     printf("\n  ]}\n}\n");
     return 0;
 }

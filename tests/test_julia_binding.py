@@ -37,7 +37,7 @@ def julia_struct(name):
     return [tuple(x.strip() for x in line.split("::")) for line in body.strip().splitlines()]
 
 
-@pytest.mark.parametrize("name", ["KinModelDesc", "KinCall"])
+@pytest.mark.parametrize("name", ["KinModelDesc", "KinCall", "KinIkCall"])
 def test_julia_struct_matches_c_layout(name, c_layout):
     fields = julia_struct(name)
     ref = c_layout[name]["fields"]
@@ -52,7 +52,7 @@ def test_julia_struct_matches_c_layout(name, c_layout):
     assert (off + max_al - 1) // max_al * max_al == c_layout[name]["size"]
 
 
-@pytest.mark.parametrize("name", ["KinModelDesc", "KinCall"])
+@pytest.mark.parametrize("name", ["KinModelDesc", "KinCall", "KinIkCall"])
 def test_ctypes_struct_matches_c_layout(name, c_layout):
     from kinematics_jl_b200 import lib as L
     S = getattr(L, name)
@@ -101,9 +101,9 @@ def test_every_ccall_matches_the_header():
         assert ret in ("Cint", "Cstring")
     # the operators of the reference's export list (Kinematics.jl:45-70) on this path all have a binding
     assert {"kin_model_create", "kin_model_destroy", "kin_model_set_boxes", "kin_eval", "kin_eval_host", "kin_pose_residual_multi",
-            "kin_sdf_points", "kin_last_error"} <= seen
+            "kin_sdf_points", "kin_last_error", "kin_ik_solve"} <= seen
     for fn in ("get_transform", "get_jacobian", "get_jacobian!", "compute_coll_dists", "compute_coll_dists_and_grads", "ineq_const",
-               "f_objective", "pose_constraint", "sdf_points", "sdf_gradient", "eval_host!", "set_boxes!"):
+               "f_objective", "pose_constraint", "sdf_points", "sdf_gradient", "eval_host!", "set_boxes!", "inverse_kinematics_batch"):
         assert re.search(r"^(function )?%s\(" % re.escape(fn), JL, re.M), fn
 
 

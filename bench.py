@@ -171,22 +171,33 @@ def cpu_arm_trajectory_stack(target_seconds):
             "sample": "%d problems x 64 waypoints (margin 0.03, truncation 0.08, fridge SDF), %.1f s, %d pthreads" % (n_prob, dt, threads)}
 
 
-def cpu_arm_ik(n_targets):
-    """inverse_kinematics! of the reference (SLSQP on f_objective with bounds) on every host core."""
+def cpu_arm_ik(n_targets, collision=False):
+    """inverse_kinematics! of the reference (SLSQP on f_objective with bounds; with ``collision`` the two-stage solve
+    under IneqConst(margin 0.02) against the fridge, inverse_kinematics.jl:1-21) on every host core."""
     R, scenes = _oracle_scene()
     from oracle import callers_cpu as CC
     import scene_fetch
     mo, jo, so = scenes.oracle_fetch(False)
-    q = scenes.random_configs(jo, n_targets, False, seed=77)
+    q = scenes.random_configs(jo, (3 if collision else 1) * n_targets, False, seed=77)
+    kw = {}
+    if collision:      # targets = poses of configurations that clear the fridge by 0.03, as in the GPU row
+        d, _, _ = R.batch_collision(so, jo, scenes.oracle_fridge_sdf(), q, with_grads=False)
+        q = q[d.min(axis=1) > 0.03][:n_targets]
+        kw = dict(sphere_fixture=os.path.join(ROOT, "data", "fetch_spheres.json"), obstacle_urdf=os.path.join(ROOT, "data", "fridge.urdf"),
+                  obstacle_state=scene_fetch.FRIDGE_STATE, margin=0.02)
     Ts = R.batch_fk(mo, jo, q, [R.find_link(mo, "gripper_link")])[:, 0]
     procs = os.cpu_count() or 1
     r = CC.run_ik_baseline(os.path.join(ROOT, "data", "fetch.urdf"), scene_fetch.FETCH_JOINT_NAMES, "gripper_link", Ts,
-                           np.array([0.2, 0, 0, 0, 0.5, 0, 0.5, 0]), with_rot=True, ftol=1e-10, n_procs=procs)
-    return {"value": r["targets_per_s"], "unit": "targets/s", "cores": r["procs"], "kind": "port",
-            "fraction_objective_below_1e-6": r["fraction_objective_below_1e-6"], "mean_objective_evals": r["mean_evals"],
-            "sample": "%d reachable gripper pose targets, scipy SLSQP (= the reference's SCIPY back-end; NLopt absent) driving the "
-                      "oracle's C f_objective through ctypes (Python call overhead included), %d processes, %.1f s"
-                      % (r["n"], r["procs"], r["seconds"])}
+                           np.array([0.2, 0, 0, 0, 0.5, 0, 0.5, 0]), with_rot=True, ftol=1e-10, n_procs=procs, **kw)
+    out = {"value": r["targets_per_s"], "unit": "targets/s", "cores": r["procs"], "kind": "port",
+           "fraction_objective_below_1e-6": r["fraction_objective_below_1e-6"], "mean_objective_evals": r["mean_evals"],
+           "sample": "%d reachable gripper pose targets, scipy SLSQP (= the reference's SCIPY back-end; NLopt absent) driving the "
+                     "oracle's C %s through ctypes (Python call overhead included), %d processes, %.1f s"
+                     % (r["n"], "f_objective and IneqConst (two-stage solve, margin 0.02, fridge)" if collision else "f_objective",
+                        r["procs"], r["seconds"])}
+    if collision:
+        out["fraction_reached_and_margin_kept"] = r["fraction_reached_and_margin_kept"]
+    return out
 
 
 def reference_main(args):
@@ -707,6 +718,7 @@ def main():
             callers["trajectory_stack(4096x64)"]["cpu_baseline"] = c5
             c4 = cpu_arm_ik(64 * (os.cpu_count() or 1))
             callers["batched_ik(2^20 targets)"]["cpu_baseline"] = c4
+            callers["batched_ik_collision_constrained"]["cpu_baseline"] = cpu_arm_ik(16 * (os.cpu_count() or 1), collision=True)
             if e2e is not None:
                 e2e["trajectory_stack_cpu_baseline_value"] = c5["value"]
                 e2e["ik_cpu_baseline_value"] = c4["value"]

@@ -119,29 +119,54 @@ __device__ __forceinline__ real box_key(const BoxRow<real> &b, real px, real py,
 template <typename real>
 __device__ __forceinline__ real key_to_dist(real key) { return key > real(0) ? real(0.5) * sqrt_(key) : key; }
 
-// closed-form gradient of one box, world frame (extension; KIN_GRAD_ANALYTIC)
+// 1 / (2 f) for f > 0: a single-precision MUFU.RCP seed refined by Newton steps (two steps: 2^-23 -> 2^-92, i.e. to the
+// last bits of a double; one step for a float) -- a full IEEE division costs ~4x more and the kernels are issue bound
+__device__ __forceinline__ double half_recip_(double f) {
+    float seed;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"((float)f));
+    double r = (double)seed;
+    r = fma(r, fma(-f, r, 1.0), r);
+    r = fma(r, fma(-f, r, 1.0), r);
+    return 0.5 * r;
+}
+__device__ __forceinline__ float half_recip_(float f) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f));
+    r = fmaf(r, fmaf(-f, r, 1.0f), r);
+    return 0.5f * r;
+}
+__device__ __forceinline__ double copysign_(double x, double s) { return copysign(x, s); }
+__device__ __forceinline__ float copysign_(float x, float s) { return copysignf(x, s); }
+
+// closed-form gradient of one box, world frame (extension; KIN_GRAD_ANALYTIC).  f = the box distance at p (already
+// known from the union search: |max(q, 0)| outside, max q inside).  Outside: grad = R' (m sigma) / f -- the leading
+// term of the forward-difference series below, with one reciprocal and no square root; inside / on the surface: the
+// signed axis of the arg-max face.
 template <typename real>
-__device__ __forceinline__ void box_grad_analytic(const BoxRow<real> &b, real px, real py, real pz, real g[3]) {
-    real l[3], q[3], m[3], gl[3] = {0, 0, 0};
+__device__ __forceinline__ void box_grad_analytic(const BoxRow<real> &b, real px, real py, real pz, real f, real g[3]) {
+    real l[3], q[3];
     l[0] = fma_(b.r[0], px, fma_(b.r[1], py, fma_(b.r[2], pz, b.t[0])));
     l[1] = fma_(b.r[3], px, fma_(b.r[4], py, fma_(b.r[5], pz, b.t[1])));
     l[2] = fma_(b.r[6], px, fma_(b.r[7], py, fma_(b.r[8], pz, b.t[2])));
     #pragma unroll
-    for (int i = 0; i < 3; ++i) { q[i] = abs_(l[i]) - b.h[i]; m[i] = relu_(q[i]); }
-    const real nrm = sqrt_(fma_(m[0], m[0], fma_(m[1], m[1], m[2] * m[2])));
-    if (nrm > real(0)) {
+    for (int i = 0; i < 3; ++i) q[i] = abs_(l[i]) - b.h[i];
+    if (f > real(0)) {
+        const real hf = half_recip_(f);
+        real n2[3];
         #pragma unroll
-        for (int i = 0; i < 3; ++i) gl[i] = (m[i] / nrm) * (l[i] < real(0) ? real(-1) : real(1));
+        for (int i = 0; i < 3; ++i) n2[i] = copysign_(q[i] + abs_(q[i]), l[i]);      // 2 m_k sigma_k (exact clamp)
+        // world = R * g_local, and the table holds inv_R = R' row-major => R[r][c] = b.r[c*3 + r]
+        #pragma unroll
+        for (int r = 0; r < 3; ++r) g[r] = fma_(b.r[0 + r], n2[0], fma_(b.r[3 + r], n2[1], b.r[6 + r] * n2[2])) * hf;
     } else {
         int k = 0;
         if (q[1] > q[k]) k = 1;
         if (q[2] > (k == 1 ? q[1] : q[0])) k = 2;
+        const real lk = k == 0 ? l[0] : (k == 1 ? l[1] : l[2]);
+        const real sg = lk < real(0) ? real(-1) : real(1);
         #pragma unroll
-        for (int i = 0; i < 3; ++i) if (i == k) gl[i] = l[i] < real(0) ? real(-1) : real(1);
+        for (int r = 0; r < 3; ++r) g[r] = sg * (k == 0 ? b.r[r] : (k == 1 ? b.r[3 + r] : b.r[6 + r]));
     }
-    // world = R * g_local, and the table holds inv_R = R' row-major => R[r][c] = b.r[c*3 + r]
-    #pragma unroll
-    for (int r = 0; r < 3; ++r) g[r] = fma_(b.r[0 + r], gl[0], fma_(b.r[3 + r], gl[1], b.r[6 + r] * gl[2]));
 }
 
 // The reference's forward difference  g_i = (f(p + eps e_i) - f(p)) / eps,  eps = 1e-7  (sdf.jl:34-41), evaluated
@@ -240,7 +265,7 @@ __device__ __forceinline__ bool box_gradient_fd_series(const BoxRow<float> &, fl
 // grad_mode 0 = forward difference (series where valid, else direct), 1 = analytic, 2 = forward difference, always direct
 template <typename real>
 __device__ __forceinline__ void box_gradient(const BoxRow<real> &b, int grad_mode, real px, real py, real pz, real dmin, real g[3]) {
-    if (grad_mode == 1) { box_grad_analytic(b, px, py, pz, g); return; }
+    if (grad_mode == 1) { box_grad_analytic(b, px, py, pz, dmin, g); return; }
     if (grad_mode == 0) {
         if (box_gradient_fd_series(b, px, py, pz, dmin, g)) return;
 #ifdef KIN_FD_COLD

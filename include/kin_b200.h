@@ -197,6 +197,14 @@ KIN_API int kin_eval(KinModel *model, const KinCall *call);
  * and returns when every output is in host memory.  `stream` is ignored. */
 KIN_API int kin_eval_host(KinModel *model, const KinCall *call);
 
+/* SoA calls: the rows of T_out / J_out that do not depend on the configuration (links no control joint moves, zero /
+ * unit rotation entries, Jacobian columns of joints that do not move the link -- known to the code generator) are not
+ * copied back over PCIe, which is what bounds this call: up to 4 host threads (KIN_HOST_FILL_THREADS) write them into
+ * the caller's arrays while the device produces the rest.  The values are the ones the kernels write (up to the sign of
+ * a zero).  keep_irrelevant = 1 and KIN_HOST_NO_CONST_FILL=1 opt out.
+ * kin_host_transfer_bytes: bytes kin_eval_host moved host -> device, device -> host, and filled on the host, since load. */
+KIN_API int kin_host_transfer_bytes(int64_t *h2d, int64_t *d2h, int64_t *host_filled);
+
 /* Convenience wrappers with the names of SURVEY 8b; each fills a KinCall and calls kin_eval. */
 /* get_transform, algorithm.jl:1 */
 KIN_API int kin_fk_links(KinModel *model, int32_t precision, int32_t layout, const void *q, int64_t n,

@@ -12,6 +12,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/kin_b200.h"
@@ -23,12 +24,16 @@
 #include "kin_jit.hpp"
 
 #include <chrono>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <fstream>
 
 namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0}, g_jit_compiles{0}, g_jit_cache_hits{0}, g_jit_launches{0}, g_jit_failures{0};
+std::atomic<long long> g_h2d_bytes{0}, g_d2h_bytes{0}, g_host_fill_bytes{0};     // kin_eval_host traffic since load
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -814,6 +819,67 @@ int kin_query_launch(KinModel *m, const KinCall *c, int32_t *regs, int32_t *smem
 
 // Host-buffer variant: chunks of the batch are staged through kStreams device buffers; within a
 // stream the order is H2D(q) -> kernel -> D2H(outputs), and the streams overlap each other.
+}  // extern "C"
+namespace {
+
+// ---- constant output rows of a host-staged SoA call: filled by host threads instead of crossing PCIe ----
+void fill_row(void *dst, size_t n, double v, bool f32) {
+    if (f32) {
+        float *p = (float *)dst;
+        const float x = (float)v;
+        size_t i = 0;
+#if defined(__SSE2__)
+        for (; i < n && ((uintptr_t)(p + i) & 15); ++i) p[i] = x;
+        const __m128 xv = _mm_set1_ps(x);
+        for (; i + 4 <= n; i += 4) _mm_stream_ps(p + i, xv);      // non-temporal: no read-for-ownership of the output
+        _mm_sfence();
+#endif
+        for (; i < n; ++i) p[i] = x;
+    } else {
+        double *p = (double *)dst;
+        size_t i = 0;
+#if defined(__SSE2__)
+        for (; i < n && ((uintptr_t)(p + i) & 15); ++i) p[i] = v;
+        const __m128d xv = _mm_set1_pd(v);
+        for (; i + 2 <= n; i += 2) _mm_stream_pd(p + i, xv);
+        _mm_sfence();
+#endif
+        for (; i < n; ++i) p[i] = v;
+    }
+}
+
+struct RowPlan {                         // of one output array with `comps` component rows
+    std::vector<std::pair<int, int>> runs;                 // [begin, end) runs of rows that depend on the configuration
+    std::vector<std::pair<int, double>> consts;            // (row, value) of the others
+    void build(size_t comps, const std::vector<std::pair<int, double>> &cs) {
+        std::vector<char> is_const(comps, 0);
+        for (const auto &kv : cs)
+            if (kv.first >= 0 && (size_t)kv.first < comps && !is_const[kv.first]) { is_const[kv.first] = 1; consts.push_back(kv); }
+        for (size_t r = 0; r < comps;) {
+            if (is_const[r]) { ++r; continue; }
+            size_t e = r;
+            while (e < comps && !is_const[e]) ++e;
+            runs.emplace_back((int)r, (int)e);
+            r = e;
+        }
+    }
+};
+
+struct FillJobs {                        // joins its threads on every exit path
+    std::vector<std::thread> threads;
+    ~FillJobs() { for (auto &t : threads) if (t.joinable()) t.join(); }
+};
+
+}  // namespace
+extern "C" {
+
+int kin_host_transfer_bytes(int64_t *h2d, int64_t *d2h, int64_t *host_filled) {
+    if (h2d) *h2d = g_h2d_bytes.load();
+    if (d2h) *d2h = g_d2h_bytes.load();
+    if (host_filled) *host_filled = g_host_fill_bytes.load();
+    return KIN_OK;
+}
+
 int kin_eval_host(KinModel *m, const KinCall *c) {
     int rc = validate_call(m, c);
     if (rc != KIN_OK) return rc;
@@ -832,7 +898,8 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
                  cJ = c->J_out ? (size_t)rows * ND * c->n_jac_links : 0, cV = c->vals_out ? S : 0,
                  cG = c->grads_out ? (size_t)ND * S : 0, cA = c->argmin_out ? S : 0;
     const size_t per_cfg = es * (cq + cT + cJ + cV + cG) + 4 * cA;
-    long long chunk = 1 << 16;
+    long long chunk = env_ll("KIN_HOST_CHUNK", 1 << 17);       // measured (profiles/sweep_e2e_host.sh): 2^15 .. 2^18 within 3 %
+    if (chunk < 32) chunk = 32;
     if (chunk > c->n) chunk = c->n;
     // tiled storage holds whole tiles of 32 configurations: size the staging carves for the padded chunk (the
     // kernel addresses, and the copies move, roundup(count, 32) records; host buffers are padded likewise)
@@ -856,6 +923,38 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
     const long long N = c->n, ldh = c->batch_stride ? c->batch_stride : N;
     const bool aos = c->layout != KIN_LAYOUT_SOA;          // AoS and tiled: one contiguous block per chunk
     const bool tiled = c->layout == KIN_LAYOUT_TILED32;
+    // SoA: the rows of T / J that do not depend on the configuration (for Fetch with the 8 arm joints: 175 of the 348:
+    // links no control joint moves, zero / unit rotation entries, Jacobian columns of joints that do not move the
+    // link -- the code generator knows them, kin_codegen.hpp) are NOT copied back over PCIe, which is what bounds this
+    // call: host threads fill them while the device works on the rest.  Same values as the kernels write (up to the
+    // sign of a zero).  get_jacobian! semantics (rows the kernel leaves untouched) and KIN_HOST_NO_CONST_FILL opt out.
+    RowPlan planT, planJ;
+    bool elide = !aos && (cT || cJ) && !(c->J_out && c->keep_irrelevant) && !std::getenv("KIN_HOST_NO_CONST_FILL");
+    if (elide) {
+        kin::GenSource g;
+        std::string err;
+        elide = kin::generate_source(dp->prog, gen_options(m, c, dp), g, err);
+        if (elide) { planT.build(cT, g.const_T); planJ.build(cJ, g.const_J); }
+        if (planT.consts.empty() && planJ.consts.empty()) elide = false;
+    }
+    FillJobs fill;
+    if (elide) {
+        struct Job { unsigned char *row; double v; };
+        auto jobs = std::make_shared<std::vector<Job>>();
+        for (const auto &kv : planT.consts) jobs->push_back({(unsigned char *)c->T_out + es * (size_t)kv.first * ldh, kv.second});
+        for (const auto &kv : planJ.consts) jobs->push_back({(unsigned char *)c->J_out + es * (size_t)kv.first * ldh, kv.second});
+        const unsigned hw = std::thread::hardware_concurrency();
+        // 2 .. 4 threads keep up with the PCIe stream; more only compete with the DMA writes for host memory bandwidth
+        long long nt = env_ll("KIN_HOST_FILL_THREADS", std::min<long long>(4, std::max<long long>(1, hw / 2)));
+        nt = std::max<long long>(1, std::min<long long>(nt, (long long)jobs->size()));
+        const bool f32 = c->precision == KIN_F32;
+        const size_t n_fill = (size_t)N;
+        for (long long t = 0; t < nt; ++t)
+            fill.threads.emplace_back([jobs, t, nt, n_fill, f32] {
+                for (size_t j = (size_t)t; j < jobs->size(); j += (size_t)nt) fill_row((*jobs)[j].row, n_fill, (*jobs)[j].v, f32);
+            });
+        g_host_fill_bytes.fetch_add((long long)(es * jobs->size() * (size_t)N));
+    }
     int k = 0;
     for (long long n0 = 0; n0 < N; n0 += chunk, k = (k + 1) % HostStage::kStreams) {
         const long long mcount = (N - n0 < chunk) ? N - n0 : chunk;
@@ -878,20 +977,41 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
             return to_dev ? cudaMemcpy2DAsync(dev, esz * mcount, (const unsigned char *)host_c + hoff, esz * ldh, width, comps, cudaMemcpyHostToDevice, s)
                           : cudaMemcpy2DAsync((unsigned char *)host_m + hoff, esz * ldh, dev, esz * mcount, width, comps, cudaMemcpyDeviceToHost, s);
         };
+        // device -> host copy of the configuration-dependent rows only (SoA, see above)
+        auto copy_runs = [&](void *dev, void *host_m, const RowPlan &plan) -> cudaError_t {
+            for (const auto &run : plan.runs) {
+                const size_t r0 = (size_t)run.first, nr = (size_t)(run.second - run.first);
+                cudaError_t e = cudaMemcpy2DAsync((unsigned char *)host_m + es * (r0 * ldh + n0), es * ldh,
+                                                  (unsigned char *)dev + es * r0 * mcount, es * mcount, es * mcount, nr,
+                                                  cudaMemcpyDeviceToHost, s);
+                if (e != cudaSuccess) return e;
+                g_d2h_bytes.fetch_add((long long)(es * mcount * nr));
+            }
+            return cudaSuccess;
+        };
         CUDA_TRY(copy(dq, c->q, nullptr, cq, es, true));
+        g_h2d_bytes.fetch_add((long long)(es * cq * mcount));
         KinCall cc = *c;
         cc.n = mcount; cc.batch_stride = 0; cc.q = dq;
         cc.T_out = cT ? dT : nullptr; cc.J_out = cJ ? dJ : nullptr; cc.vals_out = cV ? dV : nullptr;
         cc.grads_out = cG ? dG : nullptr; cc.argmin_out = cA ? (int32_t *)dA : nullptr;
         rc = launch(m, &cc, dp, s);
         if (rc != KIN_OK) return rc;
-        CUDA_TRY(copy(dT, nullptr, c->T_out, cT, es, false));
-        CUDA_TRY(copy(dJ, nullptr, c->J_out, cJ, es, false));
+        if (elide) {
+            if (cT) CUDA_TRY(copy_runs(dT, c->T_out, planT));
+            if (cJ) CUDA_TRY(copy_runs(dJ, c->J_out, planJ));
+        } else {
+            CUDA_TRY(copy(dT, nullptr, c->T_out, cT, es, false));
+            CUDA_TRY(copy(dJ, nullptr, c->J_out, cJ, es, false));
+            g_d2h_bytes.fetch_add((long long)(es * (cT + cJ) * mcount));
+        }
+        g_d2h_bytes.fetch_add((long long)((es * (cV + cG) + 4 * cA) * mcount));
         CUDA_TRY(copy(dV, nullptr, c->vals_out, cV, es, false));
         CUDA_TRY(copy(dG, nullptr, c->grads_out, cG, es, false));
         CUDA_TRY(copy(dA, nullptr, c->argmin_out, cA, 4, false));
     }
     for (int i = 0; i < HostStage::kStreams; ++i) CUDA_TRY(cudaStreamSynchronize(st.stream[i]));
+    for (auto &t : fill.threads) t.join();
     return KIN_OK;
 }
 

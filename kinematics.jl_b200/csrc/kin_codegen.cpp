@@ -147,6 +147,8 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
     constexpr int AOS_CHUNK = 12;
     if (h.n_dof > 32) { err = "too many columns"; return false; }
     const bool f32 = o.precision == 1;
+    out.const_T.clear();
+    out.const_J.clear();
     Emitter E(f32);
     const int ND = h.n_dof, DC = h.n_joints, S = o.coll ? h.n_sph : 0;
     const int rows = o.with_rot ? 6 : 3;
@@ -253,6 +255,11 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
             const TfV Tl = tf_mul_const(E, T, ar, ai[1] & AF_R_IDENTITY);
             if (do_T) {                        // get_transform, as 3x4 column-major
                 const int base = 12 * ai[0];
+                for (int c = 0; c < 3; ++c)
+                    for (int r = 0; r < 3; ++r)
+                        if (Tl.r[r * 3 + c].c) out.const_T.emplace_back(base + c * 3 + r, Tl.r[r * 3 + c].v);
+                for (int r = 0; r < 3; ++r)
+                    if (Tl.p[r].c) out.const_T.emplace_back(base + 9 + r, Tl.p[r].v);
                 if (aos) {
                     for (int c = 0; c < 3; ++c)
                         for (int r = 0; r < 3; ++r) E.os << "KPUT(12, " << c * 3 + r << ", " << E.str(Tl.r[r * 3 + c]) << ");\n";
@@ -277,6 +284,11 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
                 // AoS: chunks of whole columns, at most AOS_CHUNK values, flushed after their last column
                 const int cols_per_chunk = AOS_CHUNK / rows;
                 int chunk_k0 = kbase, chunk_cnt = 0;
+                auto stv = [&](int k, const Val &v) -> std::string {       // a value of the symbolic evaluation
+                    if (v.c) out.const_J.emplace_back(k, v.v);
+                    return E.str(v);
+                };
+                auto stz = [&](int k) -> std::string { out.const_J.emplace_back(k, 0.0); return "real(0)"; };
                 auto stj = [&](int k, const std::string &v) -> std::string {
                     if (aos) return "KPUT(" + std::to_string(chunk_cnt) + ", " + std::to_string(k - chunk_k0) + ", " + v + ");";
                     return "KST_J(" + std::to_string(k) + ", " + v + ");";
@@ -295,7 +307,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
                             cy = E.fma(f.a[2], dx, E.neg(E.mul(f.a[0], dz)));
                             cz = E.fma(f.a[0], dy, E.neg(E.mul(f.a[1], dx)));
                         } else { cx = f.a[0]; cy = f.a[1]; cz = f.a[2]; }
-                        E.os << stj(kc, E.str(cx)) << " " << stj(kc + 1, E.str(cy)) << " " << stj(kc + 2, E.str(cz)) << "\n";
+                        E.os << stj(kc, stv(kc, cx)) << " " << stj(kc + 1, stv(kc + 1, cy)) << " " << stj(kc + 2, stv(kc + 2, cz)) << "\n";
                         if (o.with_rot) {
                             if (rev) {
                                 if (o.rpy_jac) {
@@ -303,18 +315,18 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
                                          << E.str(f.a[2]) << ", o3, o4, o5); " << stj(kc + 3, "o3") << " " << stj(kc + 4, "o4") << " "
                                          << stj(kc + 5, "o5") << " }\n";
                                 } else {
-                                    for (int r = 0; r < 3; ++r) E.os << stj(kc + 3 + r, E.str(f.a[r])) << " ";
+                                    for (int r = 0; r < 3; ++r) E.os << stj(kc + 3 + r, stv(kc + 3 + r, f.a[r])) << " ";
                                     E.os << "\n";
                                 }
                             } else if (!o.keep_irrelevant || j >= DC) {
                                 // prismatic: rows 4:6 untouched by the reference (algorithm.jl:78-81), except in the base
                                 // block, which it always writes (algorithm.jl:102-104)
-                                for (int r = 3; r < 6; ++r) E.os << stj(kc + r, "real(0)") << " ";
+                                for (int r = 3; r < 6; ++r) E.os << stj(kc + r, stz(kc + r)) << " ";
                                 E.os << "\n";
                             }
                         }
                     } else if (!o.keep_irrelevant) {
-                        for (int r = 0; r < rows; ++r) E.os << stj(kc + r, "real(0)") << " ";
+                        for (int r = 0; r < rows; ++r) E.os << stj(kc + r, stz(kc + r)) << " ";
                         E.os << "\n";
                     }
                     if (aos && ((j + 1) % cols_per_chunk == 0 || j + 1 == ND))

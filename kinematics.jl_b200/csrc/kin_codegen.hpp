@@ -17,6 +17,8 @@
 // library).
 #pragma once
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "kin_model.hpp"
 
@@ -24,7 +26,7 @@ namespace kin {
 
 struct GenOptions {
     int precision = 0;          // 0 = f64, 1 = f32
-    int layout = 0;             // 0 = SoA, 2 = tiled (AoS stays on the interpreting kernel)
+    int layout = 0;             // 0 = SoA, 1 = AoS (outputs staged per warp through shared memory), 2 = tiled
     bool want_T = false, want_J = false, coll = false;
     int with_rot = 0, rpy_jac = 0, keep_irrelevant = 0;
     bool want_grads = false, want_argmin = false, stale = false;
@@ -46,6 +48,10 @@ struct GenSource {
     std::string phase1;         // "kin_gen_phase1.inc": straight-line phase 1
     std::string phase2;         // "kin_gen_phase2.inc": the phase-2 run calls
     int n_ops = 0;              // arithmetic operations emitted in phase 1 (diagnostics)
+    // outputs whose value does not depend on the configuration (links no control joint moves, zero / unit rotation
+    // entries, Jacobian columns of joints that do not move the link): (component index, value).  kin_eval_host does
+    // not move these rows over PCIe: the host fills them (SoA layout).
+    std::vector<std::pair<int, double>> const_T, const_J;
 };
 
 // Returns false (with err) when the program cannot be specialised (the caller then uses the interpreting kernel).

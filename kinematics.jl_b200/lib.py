@@ -64,7 +64,7 @@ EXPORTS = ["kin_last_error", "kin_abi_version", "kin_build_id", "kin_debug_build
            "kin_model_set_boxes", "kin_model_n_dof", "kin_model_n_spheres", "kin_model_n_boxes", "kin_eval",
            "kin_eval_host", "kin_fk_links", "kin_fk_jacobian", "kin_collision", "kin_launch_count",
            "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual", "kin_pose_residual_multi", "kin_probe_fp64",
-           "kin_jit_status", "kin_jit_stats", "kin_codegen_dump", "kin_ik_solve"]
+           "kin_jit_status", "kin_jit_stats", "kin_codegen_dump", "kin_ik_solve", "kin_host_transfer_bytes"]
 
 
 def source_files():
@@ -209,6 +209,7 @@ def lib():
         L.kin_jit_status.restype = C.c_char_p
         _lp = C.POINTER(C.c_int64)
         L.kin_jit_stats.argtypes = [_lp, _lp, _lp, _lp]
+        L.kin_host_transfer_bytes.argtypes = [_lp, _lp, _lp]
         L.kin_codegen_dump.argtypes = [C.POINTER(KinModelDesc), C.POINTER(KinCall), C.c_int32, C.c_char_p]
         L.kin_program_dump.argtypes = [C.POINTER(KinModelDesc), _ip, C.c_int32, _ip, C.c_int32, C.c_int32, C.c_int32,
                                        _ip, C.c_int32, _ip, C.c_int32, _dp, C.c_int32]

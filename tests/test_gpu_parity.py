@@ -660,7 +660,7 @@ def test_host_entry_point_tiled_layout_ragged_sizes():
     fk = np.arange(1, 26, dtype=np.int32)
     jac = np.array([K.find_link(m, "gripper_link").id], dtype=np.int32)
     nl, S, nd = 25, 16, 8
-    for N in (1, 33, 1000, 65536 + 77):
+    for N in (1, 33, 1000, 131072 + 77):
         q = scenes.random_configs(jo, N, False, seed=43)
         K.set_joint_angles(m, joints, dev(q[:1]))
         K.compute_coll_dists(sscc, joints, sdf)
@@ -725,10 +725,16 @@ def test_debug_build_bounds_checks_pass():
     assert "smoke ok" in out.stdout and "KIN_DEBUG assertion failed" not in out.stdout + out.stderr
 
 
+def _transfer_counters():
+    vals = [C.c_int64() for _ in range(3)]
+    L.check(L.lib().kin_host_transfer_bytes(*[C.byref(v) for v in vals]))
+    return vals
+
+
 @pytest.mark.parametrize("layout", [L.AOS, L.SOA])
 def test_fused_device_and_host_entry_points(layout):
     m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
-    N = 70000                                   # > one staging chunk (65536) of kin_eval_host
+    N = 140000                                  # > one staging chunk (131072) of kin_eval_host
     q = scenes.random_configs(jo, N, False, seed=41)
     K.set_joint_angles(m, joints, dev(q[:1]))
     K.compute_coll_dists(sscc, joints, sdf)     # uploads the sphere / box tables into the device model
@@ -738,11 +744,31 @@ def test_fused_device_and_host_entry_points(layout):
     nl, S, nd = 25, 16, 8
     qh = np.ascontiguousarray(q if layout == L.AOS else q.T)
     shapes = {"T": nl * 12, "J": 6 * nd, "V": S, "G": nd * S}
-    outs_h = {k: np.zeros((N, c) if layout == L.AOS else (c, N)) for k, c in shapes.items()}
+    outs_h = {k: np.full((N, c) if layout == L.AOS else (c, N), -7.0) for k, c in shapes.items()}     # every element must be written
     am_h = np.zeros((N, S) if layout == L.AOS else (S, N), dtype=np.int32)
     c = _fused_call(dm, N, qh.ctypes.data, layout, fk, jac, outs_h["T"].ctypes.data, outs_h["J"].ctypes.data,
                     outs_h["V"].ctypes.data, outs_h["G"].ctypes.data, am_h.ctypes.data)
+    cnt = lambda: tuple(x.value for x in _transfer_counters())
+    b0 = cnt()
     L.check(L.lib().kin_eval_host(dm.h, C.byref(c)))
+    h2d, d2h, filled = (a - b for a, b in zip(cnt(), b0))
+    full = 8 * N * (nl * 12 + 6 * nd + S + nd * S) + 4 * N * S
+    assert h2d == 8 * N * nd
+    if layout == L.SOA:
+        # the rows of T / J that do not depend on the configuration are filled by host threads, not copied over PCIe
+        assert filled > 8 * N * 100 and d2h + filled == full
+        outs_2 = {k: np.full_like(v, -7.0) for k, v in outs_h.items()}
+        c2 = _fused_call(dm, N, qh.ctypes.data, layout, fk, jac, outs_2["T"].ctypes.data, outs_2["J"].ctypes.data,
+                         outs_2["V"].ctypes.data, outs_2["G"].ctypes.data, am_h.ctypes.data)
+        os.environ["KIN_HOST_NO_CONST_FILL"] = "1"
+        try:
+            L.check(L.lib().kin_eval_host(dm.h, C.byref(c2)))
+        finally:
+            del os.environ["KIN_HOST_NO_CONST_FILL"]
+        for k in outs_h:
+            assert np.array_equal(outs_h[k], outs_2[k]), k
+    else:
+        assert filled == 0 and d2h == full
     qd = dev(qh)
     outs_d = {k: torch.zeros(v.shape, dtype=torch.float64, device="cuda") for k, v in outs_h.items()}
     am_d = torch.zeros(am_h.shape, dtype=torch.int32, device="cuda")

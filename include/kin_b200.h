@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define KIN_B200_ABI_VERSION 3
+#define KIN_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define KIN_API __attribute__((visibility("default")))
@@ -88,6 +88,16 @@ typedef enum { KIN_GRAD_FD = 0, KIN_GRAD_ANALYTIC = 1, KIN_GRAD_FD_DIRECT = 2 } 
  * KIN_SCRATCH_REFERENCE reproduces that bit for bit in sphere order; KIN_SCRATCH_CLEAN zeroes
  * them (the mathematically correct gradient). */
 typedef enum { KIN_SCRATCH_REFERENCE = 0, KIN_SCRATCH_CLEAN = 1 } KinScratchMode;
+
+/* SDF primitives.  The reference has boxes only (load_urdf.jl:10-15 prints "primitive type other than box is not
+ * supported yet", sdf.jl:92-94 warns); spheres and cylinders are an EXTENSION that plugs into the same
+ * contract: value at a point, the generic forward-difference gradient! of sdf.jl:34-41 (or the closed form with
+ * KIN_GRAD_ANALYTIC), first-minimum argmin inside a UnionSDF.  A table row of any kind has a pose (the primitive's
+ * frame in the world) and a size triple:
+ *   KIN_PRIM_BOX       size = full extents (BoxSDF.width)
+ *   KIN_PRIM_SPHERE    size = (radius, -, -)
+ *   KIN_PRIM_CYLINDER  size = (radius, length, -), axis = local z, centred on the pose (URDF <cylinder>) */
+typedef enum { KIN_PRIM_BOX = 0, KIN_PRIM_SPHERE = 1, KIN_PRIM_CYLINDER = 2 } KinPrimKind;
 
 #define KIN_MAX_LINKS 512
 #define KIN_MAX_JOINTS 32          /* control joints (bitmask width), base columns excluded */
@@ -185,6 +195,10 @@ KIN_API int kin_model_set_spheres(KinModel *model, int32_t n_spheres, const int3
                           const double *sphere_center, const double *sphere_radius);
 /* UnionSDF / BoxSDF poses after the obstacle moved (sdf.jl:14-32): replaces the whole box table */
 KIN_API int kin_model_set_boxes(KinModel *model, int32_t n_boxes, const double *box_pose, const double *box_width);
+/* The same table with mixed primitive kinds (kinds[n]: KinPrimKind; NULL = all boxes; size[n][3] as described at
+ * KinPrimKind).  A table with a sphere / cylinder row makes the specialised kernels carry one warp-uniform test per
+ * row; box-only tables compile exactly the code they always did. */
+KIN_API int kin_model_set_primitives(KinModel *model, int32_t n, const int32_t *kinds, const double *pose, const double *size);
 KIN_API int kin_model_n_dof(const KinModel *model);      /* n_joints (+3) */
 KIN_API int kin_model_n_spheres(const KinModel *model);
 KIN_API int kin_model_n_boxes(const KinModel *model);
@@ -225,6 +239,11 @@ KIN_API int kin_collision(KinModel *model, int32_t precision, int32_t layout, co
 KIN_API int kin_sdf_points(int32_t n_boxes, const double *box_pose, const double *box_width, int32_t precision,
                    int32_t layout, const void *pts, int64_t n, int32_t grad_mode, void *vals_out,
                    void *grads_out, int32_t *argmin_out, void *stream);
+
+/* ... for a union of mixed primitives (kinds / size as in kin_model_set_primitives) */
+KIN_API int kin_sdf_points_prims(int32_t n, const int32_t *kinds, const double *pose, const double *size, int32_t precision,
+                                 int32_t layout, const void *pts, int64_t n_pts, int32_t grad_mode, void *vals_out,
+                                 void *grads_out, int32_t *argmin_out, void *stream);
 
 /* Pose residuals of one link against target poses -- the per-iteration evaluations of the IK and
  * planning callers:

@@ -190,6 +190,15 @@ function set_boxes!(dm::DeviceMechanism, sdf::AbstractSDF)
                                           dm.handle, B, pointer(bpose), pointer(bwidth)))
 end
 
+# Extension (no reference counterpart: the reference's SDFs are boxes, sdf.jl:92-94): a table of mixed primitives.
+# kinds[i] = 0 box (size = widths) | 1 sphere (radius, -, -) | 2 cylinder along local z (radius, length, -);
+# pose (16, n) column-major world poses, size (3, n).
+function set_primitives!(dm::DeviceMechanism, kinds::Vector{Cint}, pose::Matrix{Cdouble}, size_::Matrix{Cdouble})
+    @assert size(pose) == (16, length(kinds)) && size(size_) == (3, length(kinds))
+    GC.@preserve kinds pose size_ check(ccall((:kin_model_set_primitives, libkin), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}), dm.handle, length(kinds), pointer(kinds), pointer(pose), pointer(size_)))
+end
+
 function make_call(dm, Q, layout, fk_links, T, jac_links, J, with_rot, rpy_jac, keep_irrelevant, vals, grads, argmin,
                    truncation_dist, grad_mode, scratch_mode, vals_offset, qptr, dptr, stream)
     N = nbatch(Q, layout)

@@ -58,8 +58,7 @@ def _prepare(sscc, joints, sdf):
     _check_joints(m, joints)
     dm = device_model(m)
     dm.set_spheres(sscc._parents, sscc._centers, sscc.sphere_radii)
-    poses, widths = sdf.world_boxes()
-    dm.set_boxes(poses, widths)
+    dm.set_boxes(*sdf.world_primitives())
     return m, dm
 
 

@@ -128,11 +128,19 @@ int load_spheres(kin::HostModel &hm, int32_t n, const int32_t *link, const doubl
     return KIN_OK;
 }
 
-int load_boxes(kin::HostModel &hm, int32_t n, const double *pose, const double *width) {
+// The SDF table: boxes (BoxSDF, sdf.jl:48-74) and, as an extension, spheres / cylinders.  kinds == null: all boxes.
+// size: box = full widths; sphere = (radius, -, -); cylinder = (radius, length, -), axis = local z (URDF convention).
+int load_prims(kin::HostModel &hm, int32_t n, const int32_t *kinds, const double *pose, const double *size) {
     if (n < 0 || n > KIN_MAX_BOXES) return fail(KIN_ERR_LIMIT, "n_boxes exceeds KIN_MAX_BOXES");
-    if (n > 0 && (!pose || !width)) return fail(KIN_ERR_INVALID_ARGUMENT, "null box table");
+    if (n > 0 && (!pose || !size)) return fail(KIN_ERR_INVALID_ARGUMENT, "null box table");
+    for (int b = 0; b < n; ++b) {            // validate before mutating
+        const int k = kinds ? kinds[b] : KIN_PRIM_BOX;
+        if (k != KIN_PRIM_BOX && k != KIN_PRIM_SPHERE && k != KIN_PRIM_CYLINDER) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown primitive kind");
+        if (k != KIN_PRIM_BOX && !(size[3 * b] >= 0.0)) return fail(KIN_ERR_INVALID_ARGUMENT, "negative radius");
+    }
     hm.n_box = n;
     hm.box_inv.resize(n); hm.box_half.assign(3 * (size_t)n, 0.0);
+    hm.box_kind.assign(n, 0); hm.box_round.assign(n, 0.0);
     for (int b = 0; b < n; ++b) {
         kin::Xf P = kin::Xf::from_colmajor16(pose + 16 * b), inv;
         // inv(tf) = (-R' t, R')  (transform.jl:62-65)
@@ -141,10 +149,20 @@ int load_boxes(kin::HostModel &hm, int32_t n, const double *pose, const double *
         for (int r = 0; r < 3; ++r)
             inv.p[r] = (-inv.r[r * 3 + 0]) * P.p[0] + (-inv.r[r * 3 + 1]) * P.p[1] + (-inv.r[r * 3 + 2]) * P.p[2];
         hm.box_inv[b] = inv;
-        for (int k = 0; k < 3; ++k) hm.box_half[3 * b + k] = 0.5 * width[3 * b + k];   // sdf.jl:68
+        const int k = kinds ? kinds[b] : KIN_PRIM_BOX;
+        if (k == KIN_PRIM_SPHERE) {            // a rounded box with zero half extents
+            hm.box_kind[b] = 1; hm.box_round[b] = size[3 * b];
+        } else if (k == KIN_PRIM_CYLINDER) {
+            hm.box_kind[b] = 2;
+            hm.box_half[3 * b] = hm.box_half[3 * b + 1] = size[3 * b];
+            hm.box_half[3 * b + 2] = 0.5 * size[3 * b + 1];
+        } else {
+            for (int i = 0; i < 3; ++i) hm.box_half[3 * b + i] = 0.5 * size[3 * b + i];   // sdf.jl:68
+        }
     }
     return KIN_OK;
 }
+int load_boxes(kin::HostModel &hm, int32_t n, const double *pose, const double *width) { return load_prims(hm, n, nullptr, pose, width); }
 
 int host_model_from_desc(const KinModelDesc *d, kin::HostModel &hm) {
     if (d->n_links <= 0 || d->n_links > KIN_MAX_LINKS) return fail(KIN_ERR_LIMIT, "n_links out of range (KIN_MAX_LINKS)");
@@ -193,6 +211,13 @@ const KernelFn kWsKernels[2][2][2] = {{KIN_WS(0, false), KIN_WS(0, true)}, {KIN_
 // collision-only variant: no link transforms / Jacobians requested, no truncation (with a finite truncation
 // distance most spheres skip the gradient stage, the consumers are idle already and the box search would make the
 // producer the bottleneck: trajectory stack of config 5 0.19 -> 0.23 ms), and its larger consumer state still fits
+// does the program's SDF table hold rows other than boxes (slot 15 of a row = kind)?
+bool prog_has_prims(const kin::Program &p) {
+    for (int b = 0; b < p.h.n_box; ++b)
+        if (p.reals[(size_t)p.h.ro_box + (size_t)b * kin::BOX_REALS + 15] != 0.0) return true;
+    return false;
+}
+
 bool ws_pre(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
     return !c->T_out && !c->J_out && std::isinf(c->truncation_dist) && c->truncation_dist > 0 && !std::getenv("KIN_DISABLE_WS_PRE") &&
            kin::ws_smem_bytes(dp->prog.h, true) <= (size_t)m->dev_smem;
@@ -207,6 +232,7 @@ bool ws_eligible(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
     if (!c->vals_out || h.n_sph <= 0 || h.n_joints > kin::JF_REGS || h.n_dof > kin::WS_MAX_COLS) return false;
     if (h.so_jf != h.so_save) return false;
     if (c->n < kWsMinBatch && !std::getenv("KIN_FORCE_WS")) return false;
+    if (prog_has_prims(dp->prog)) return false;               // the hand-tuned kernel knows boxes only
     return kin::ws_smem_bytes(h, false) <= (size_t)m->dev_smem;
 }
 
@@ -321,6 +347,8 @@ long long env_ll(const char *name, long long dflt) {
 kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
     const kin::ProgHeader &h = dp->prog.h;
     kin::GenOptions o;
+    // (KIN_JIT_FORCE_PRIMS: compile the row-kind test into a box-only kernel -- build check / cost measurement)
+    o.prims = (c->vals_out != nullptr && h.n_sph > 0 && (prog_has_prims(dp->prog) || std::getenv("KIN_JIT_FORCE_PRIMS"))) ? 1 : 0;
     o.precision = c->precision == KIN_F32 ? 1 : 0;
     o.layout = c->layout;
     o.want_T = c->T_out != nullptr && h.n_fk > 0;
@@ -735,11 +763,15 @@ int kin_model_set_spheres(KinModel *m, int32_t n, const int32_t *link, const dou
 }
 
 int kin_model_set_boxes(KinModel *m, int32_t n, const double *pose, const double *width) {
+    return kin_model_set_primitives(m, n, nullptr, pose, width);
+}
+
+int kin_model_set_primitives(KinModel *m, int32_t n, const int32_t *kinds, const double *pose, const double *width) {
     if (!m) return fail(KIN_ERR_INVALID_ARGUMENT, "null model");
     DeviceGuard guard(m->device);
     std::lock_guard<std::mutex> lock(m->mu);
     const int old_n = m->hm.n_box;
-    int rc = load_boxes(m->hm, n, pose, width);
+    int rc = load_prims(m->hm, n, kinds, pose, width);
     if (rc != KIN_OK) return rc;
     if (n != old_n) { clear_cache(m); return KIN_OK; }
     // Same number of boxes (the obstacle moved, sdf.jl:14-32): the compiled programs stay valid, only the box rows
@@ -1018,6 +1050,13 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
 int kin_sdf_points(int32_t n_boxes, const double *box_pose, const double *box_width, int32_t precision, int32_t layout,
                    const void *pts, int64_t n, int32_t grad_mode, void *vals_out, void *grads_out, int32_t *argmin_out,
                    void *stream_) {
+    return kin_sdf_points_prims(n_boxes, nullptr, box_pose, box_width, precision, layout, pts, n, grad_mode, vals_out, grads_out,
+                                argmin_out, stream_);
+}
+
+int kin_sdf_points_prims(int32_t n_boxes, const int32_t *kinds, const double *box_pose, const double *box_width, int32_t precision,
+                         int32_t layout, const void *pts, int64_t n, int32_t grad_mode, void *vals_out, void *grads_out,
+                         int32_t *argmin_out, void *stream_) {
     if (n < 0 || (n > 0 && (!pts || !vals_out))) return fail(KIN_ERR_INVALID_ARGUMENT, "null points or vals_out");
     if (n_boxes <= 0) return fail(KIN_ERR_INVALID_ARGUMENT, "kin_sdf_points needs at least one box");
     if (precision != KIN_F64 && precision != KIN_F32) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown precision");
@@ -1029,16 +1068,11 @@ int kin_sdf_points(int32_t n_boxes, const double *box_pose, const double *box_wi
         return fail(KIN_ERR_NO_DEVICE, "no CUDA device: libkin_b200 has no CPU fallback");
     }
     kin::HostModel hm;
-    int rc = load_boxes(hm, n_boxes, box_pose, box_width);
+    int rc = load_prims(hm, n_boxes, kinds, box_pose, box_width);
     if (rc != KIN_OK) return rc;
     if (n == 0) return KIN_OK;
     std::vector<double> t64((size_t)n_boxes * kin::BOX_REALS, 0.0);
-    for (int b = 0; b < n_boxes; ++b) {
-        double *br = &t64[(size_t)b * kin::BOX_REALS];
-        std::memcpy(br, hm.box_inv[b].r, sizeof(double) * 9);
-        std::memcpy(br + 9, hm.box_inv[b].p, sizeof(double) * 3);
-        std::memcpy(br + 12, &hm.box_half[3 * b], sizeof(double) * 3);
-    }
+    kin::emit_box_rows(hm, t64.data());
     std::vector<float> t32(t64.begin(), t64.end());
     const size_t es = precision == KIN_F32 ? 4 : 8, bytes = es * t64.size();
     cudaStream_t stream = (cudaStream_t)stream_;

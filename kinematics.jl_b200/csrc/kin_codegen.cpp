@@ -10,10 +10,10 @@
 namespace kin {
 
 std::string GenOptions::key() const {
-    char b[160];
-    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d I%d W%d", precision, layout, (int)want_T, (int)want_J,
+    char b[192];
+    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d I%d W%d P%d", precision, layout, (int)want_T, (int)want_J,
                   (int)coll, with_rot, rpy_jac, keep_irrelevant, (int)want_grads, (int)want_argmin, (int)stale, (int)ws, block, min_blocks, qbatch,
-                  ksync, es32, grad_mode, fd_cold, ik, warp);
+                  ksync, es32, grad_mode, fd_cold, ik, warp, prims);
     return b;
 }
 
@@ -398,6 +398,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
     std::ostringstream c;
     c << "#define KREAL " << (f32 ? "float" : "double") << "\n";
     if (o.fd_cold) c << "#define KIN_FD_COLD 1\n";
+    c << "#define KPRIMS " << o.prims << "\n";
     c << "#define KWANT_T " << (o.want_T ? 1 : 0) << "\n#define KWANT_J " << (o.want_J ? 1 : 0) << "\n#define KCOLL " << (o.coll ? 1 : 0)
       << "\n#define KTILED " << (o.layout == 2 ? 1 : 0) << "\n#define KAOS " << (o.layout == 1 ? 1 : 0) << "\n#define KWS " << (o.ws ? 1 : 0) << "\n";
     c << "#define KBS " << o.block << "\n#define KMINB " << o.min_blocks << "\n#define KWARP " << o.warp << "\n#define KIK " << o.ik << "\n#define KQB " << o.qbatch << "\n#define KSYNC_ON "

@@ -64,13 +64,24 @@ __device__ __forceinline__ void tf_mul_const(const Tf<real> &a, const real *__re
     }
 }
 
-// One row of the box table in registers.
-template <typename real> struct BoxRow { real r[9], t[3], h[3]; };
+// KPRIMS: 1 = the SDF table may hold primitives other than boxes (sphere / cylinder rows, an extension beyond the
+// reference, which has boxes only: load_urdf.jl:10-15, sdf.jl:92-94); every row loop then tests the row's kind (a
+// warp-uniform branch) and leaves the box code path untouched.  The generated kernels define it per model (0 for a
+// box-only table: the test compiles out); the ahead-of-time kernels always carry the test.
+#ifndef KPRIMS
+#define KPRIMS 1
+#endif
+
+// One row of the SDF table in registers: inv_R[9] row-major, inv_t[3], half extents[3], kind (slot 15: 0 = box,
+// 1 = rounded box -- a sphere is a rounded box with zero half extents --, 2 = cylinder along the local z axis with
+// h[0] = radius, h[2] = half length); slot 16 holds the rounding radius (read only on the general path).
+template <typename real> struct BoxRow { real r[9], t[3], h[3], kind; };
 __device__ __forceinline__ void load_box(const float *__restrict__ b, BoxRow<float> &o) {
     #pragma unroll
     for (int i = 0; i < 9; ++i) o.r[i] = b[i];
     #pragma unroll
     for (int i = 0; i < 3; ++i) { o.t[i] = b[9 + i]; o.h[i] = b[12 + i]; }
+    o.kind = KPRIMS ? b[15] : 0.0f;
 }
 // FP64 rows are 16-byte aligned (even BOX_REALS, even ro_box, 16-byte aligned table): 8 x 128-bit loads
 __device__ __forceinline__ void load_box(const double *__restrict__ b, BoxRow<double> &o) {
@@ -82,6 +93,7 @@ __device__ __forceinline__ void load_box(const double *__restrict__ b, BoxRow<do
     for (int i = 0; i < 9; ++i) o.r[i] = v[i];
     #pragma unroll
     for (int i = 0; i < 3; ++i) { o.t[i] = v[9 + i]; o.h[i] = v[12 + i]; }
+    o.kind = v[15];              // the eighth 128-bit load brings it along for free
 }
 
 // BoxSDF call (sdf.jl:67-74) in "key" form.  With q = |inv_pose * p| - w/2 and s = |max(q,0)|^2 the
@@ -261,6 +273,83 @@ __device__ __forceinline__ bool box_gradient_fd_series(const BoxRow<double> &b, 
 }
 __device__ __forceinline__ bool box_gradient_fd_series(const BoxRow<float> &, float, float, float, float, float[3]) { return false; }
 
+// ---- primitives other than boxes (extension; KPRIMS) ----
+// Signed distance of one general row at p.  Out of line and rare by construction (a scene of boxes never gets here):
+// it reads the row through the pointer so that the call carries four arguments.
+//   kind 1  rounded box:  d = |max(q, 0)| + min(max q, 0) - rho,  q = |inv_pose p| - h   (sphere: h = 0, rho = radius)
+//   kind 2  cylinder:     the same formula on q = (hypot(l_x, l_y) - radius, |l_z| - half length)
+template <typename real>
+__device__ __noinline__ real prim_dist_general(const real *rowp, real px, real py, real pz) {
+    const real lx = fma_(rowp[0], px, fma_(rowp[1], py, fma_(rowp[2], pz, rowp[9])));
+    const real ly = fma_(rowp[3], px, fma_(rowp[4], py, fma_(rowp[5], pz, rowp[10])));
+    const real lz = fma_(rowp[6], px, fma_(rowp[7], py, fma_(rowp[8], pz, rowp[11])));
+    if (rowp[15] == real(2)) {
+        const real q0 = sqrt_(fma_(lx, lx, ly * ly)) - rowp[12], q1 = abs_(lz) - rowp[14];
+        const real m0 = relu_(q0), m1 = relu_(q1), mx = q0 > q1 ? q0 : q1;
+        return sqrt_(fma_(m0, m0, m1 * m1)) + (mx < real(0) ? mx : real(0));
+    }
+    const real q0 = abs_(lx) - rowp[12], q1 = abs_(ly) - rowp[13], q2 = abs_(lz) - rowp[14];
+    const real m0 = relu_(q0), m1 = relu_(q1), m2 = relu_(q2);
+    real mx = q0 > q1 ? q0 : q1;
+    mx = mx > q2 ? mx : q2;
+    return sqrt_(fma_(m0, m0, fma_(m1, m1, m2 * m2))) + (mx < real(0) ? mx : real(0)) - rowp[16];
+}
+// distance -> the monotone key of the union search (key_to_dist inverts it exactly: sqrt((2 d)^2) = 2 |d| in binary
+// floating point)
+template <typename real>
+__device__ __forceinline__ real dist_to_key(real d) { return d > real(0) ? real(4) * d * d : d; }
+
+// gradient!(sdf, p, out) of a general row: the reference's generic forward difference (sdf.jl:34-41; eps 1e-7, against
+// the cached value f), or the closed form with KIN_GRAD_ANALYTIC.
+template <typename real>
+__device__ __noinline__ void prim_gradient_general(const real *rowp, int grad_mode, real px, real py, real pz, real f, real g[3]) {
+    if (grad_mode != 1) {
+        const real eps = real(1e-7), ieps = real(1e7);
+        g[0] = (prim_dist_general(rowp, px + eps, py, pz) - f) * ieps;
+        g[1] = (prim_dist_general(rowp, px, py + eps, pz) - f) * ieps;
+        g[2] = (prim_dist_general(rowp, px, py, pz + eps) - f) * ieps;
+        return;
+    }
+    real l[3], gl[3] = {real(0), real(0), real(0)};
+    l[0] = fma_(rowp[0], px, fma_(rowp[1], py, fma_(rowp[2], pz, rowp[9])));
+    l[1] = fma_(rowp[3], px, fma_(rowp[4], py, fma_(rowp[5], pz, rowp[10])));
+    l[2] = fma_(rowp[6], px, fma_(rowp[7], py, fma_(rowp[8], pz, rowp[11])));
+    if (rowp[15] == real(2)) {
+        const real rxy = sqrt_(fma_(l[0], l[0], l[1] * l[1]));
+        const real q0 = rxy - rowp[12], q1 = abs_(l[2]) - rowp[14];
+        const real m0 = relu_(q0), m1 = relu_(q1), nrm = sqrt_(fma_(m0, m0, m1 * m1));
+        const real ux = rxy > real(0) ? l[0] / rxy : real(0), uy = rxy > real(0) ? l[1] / rxy : real(0);
+        const real sz = l[2] < real(0) ? real(-1) : real(1);
+        if (nrm > real(0)) { gl[0] = m0 / nrm * ux; gl[1] = m0 / nrm * uy; gl[2] = m1 / nrm * sz; }
+        else if (q0 > q1) { gl[0] = ux; gl[1] = uy; }
+        else gl[2] = sz;
+    } else {
+        real q[3], m[3];
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) { q[i] = abs_(l[i]) - rowp[12 + i]; m[i] = relu_(q[i]); }
+        const real nrm = sqrt_(fma_(m[0], m[0], fma_(m[1], m[1], m[2] * m[2])));
+        if (nrm > real(0)) {
+            #pragma unroll
+            for (int i = 0; i < 3; ++i) gl[i] = (m[i] / nrm) * (l[i] < real(0) ? real(-1) : real(1));
+        } else {
+            int k = 0;
+            if (q[1] > q[k]) k = 1;
+            if (q[2] > (k == 1 ? q[1] : q[0])) k = 2;
+            #pragma unroll
+            for (int i = 0; i < 3; ++i) if (i == k) gl[i] = l[i] < real(0) ? real(-1) : real(1);
+        }
+    }
+    #pragma unroll
+    for (int r = 0; r < 3; ++r) g[r] = fma_(rowp[0 + r], gl[0], fma_(rowp[3 + r], gl[1], rowp[6 + r] * gl[2]));   // R * g_local
+}
+
+// key of one table row at p: the box fast path, or the general primitive
+template <typename real>
+__device__ __forceinline__ real sdf_row_key(const real *rowp, const BoxRow<real> &row, real px, real py, real pz) {
+    if (KPRIMS && row.kind != real(0)) return dist_to_key(prim_dist_general(rowp, px, py, pz));
+    return box_key(row, px, py, pz);
+}
+
 // gradient!(sdf, p, out) on the argmin box (sdf.jl:34-41, 116-119).
 // grad_mode 0 = forward difference (series where valid, else direct), 1 = analytic, 2 = forward difference, always direct
 template <typename real>
@@ -276,6 +365,12 @@ __device__ __forceinline__ void box_gradient(const BoxRow<real> &b, int grad_mod
         return;
     }
     box_gradient_fd_direct(b, px, py, pz, dmin, g);
+}
+// ... on the argmin ROW, whatever its kind
+template <typename real>
+__device__ __forceinline__ void sdf_row_gradient(const real *rowp, const BoxRow<real> &row, int grad_mode, real px, real py, real pz, real dmin, real g[3]) {
+    if (KPRIMS && row.kind != real(0)) { prim_gradient_general(rowp, grad_mode, px, py, pz, dmin, g); return; }
+    box_gradient(row, grad_mode, px, py, pz, dmin, g);
 }
 
 // Euler-rate coefficients of rpy_derivative! (algorithm.jl:56-63) for the link rotation R (row-major):

@@ -35,6 +35,10 @@ __device__ __forceinline__ void phase2a_group(const int s0, const int ge, const 
         BoxRow<real> row;
         load_box(tb + b * BOX_REALS, row);
         real key[SPH_GROUP], qx[SPH_GROUP], qy[SPH_GROUP], qz[SPH_GROUP];
+        if (KPRIMS && row.kind != real(0)) {     // a sphere / cylinder row (extension): warp-uniform, out of line
+            #pragma unroll 1
+            for (int g = 0; g < SPH_GROUP; ++g) key[g] = dist_to_key(prim_dist_general(tb + b * BOX_REALS, px[g], py[g], pz[g]));
+        } else {
         bool any_inside = false;
         #pragma unroll
         for (int g = 0; g < SPH_GROUP; ++g) {
@@ -45,6 +49,7 @@ __device__ __forceinline__ void phase2a_group(const int s0, const int ge, const 
             #pragma unroll
             for (int g = 0; g < SPH_GROUP; ++g)
                 if (!(key[g] > real(0))) key[g] = box_inside_key(qx[g], qy[g], qz[g]);
+        }
         }
         #pragma unroll
         for (int g = 0; g < SPH_GROUP; ++g)
@@ -159,7 +164,7 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
             {
                 BoxRow<real> row;
                 load_box(tb + kmin * BOX_REALS, row);
-                box_gradient(row, KGRADMODE >= 0 ? KGRADMODE : grad_mode, px, py, pz, dmin, grad);
+                sdf_row_gradient(tb + kmin * BOX_REALS, row, KGRADMODE >= 0 ? KGRADMODE : grad_mode, px, py, pz, dmin, grad);
             }
             #pragma unroll
             for (int j = 0; j < ND; ++j) {
@@ -418,7 +423,8 @@ extern "C" __global__ void __launch_bounds__(KBS, 1) kin_gen_kernel(const __grid
             for (int i = 0; i < 9; ++i) row.r[i] = __ldg(tb + b * BOX_REALS + i);
             #pragma unroll
             for (int i = 0; i < 3; ++i) { row.t[i] = __ldg(tb + b * BOX_REALS + 9 + i); row.h[i] = __ldg(tb + b * BOX_REALS + 12 + i); }
-            const real key = box_key(row, px, py, pz);
+            row.kind = KPRIMS ? __ldg(tb + b * BOX_REALS + 15) : real(0);
+            const real key = sdf_row_key(tb + b * BOX_REALS, row, px, py, pz);
             if (key < kmin) { kmin = key; kidx = b; }
         }
         const real dmin = key_to_dist(kmin);
@@ -437,7 +443,8 @@ extern "C" __global__ void __launch_bounds__(KBS, 1) kin_gen_kernel(const __grid
                 for (int i = 0; i < 9; ++i) row.r[i] = __ldg(tb + kidx * BOX_REALS + i);
                 #pragma unroll
                 for (int i = 0; i < 3; ++i) { row.t[i] = __ldg(tb + kidx * BOX_REALS + 9 + i); row.h[i] = __ldg(tb + kidx * BOX_REALS + 12 + i); }
-                box_gradient(row, KGRADMODE >= 0 ? KGRADMODE : A.grad_mode, px, py, pz, dmin, grad);
+                row.kind = KPRIMS ? __ldg(tb + kidx * BOX_REALS + 15) : real(0);
+                sdf_row_gradient(tb + kidx * BOX_REALS, row, KGRADMODE >= 0 ? KGRADMODE : A.grad_mode, px, py, pz, dmin, grad);
             }
             const unsigned mask = KSPHMASK[s];
             real *Gp = reinterpret_cast<real *>(A.grads_out) + KREC_BASE((long long)KND * KS) + (size_t)s * KND * es;

@@ -387,6 +387,11 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                         BoxRow<real> row;
                         load_box(tr + ro_box + b * BOX_REALS, row);
                         real key[SPH_GROUP], qx[SPH_GROUP], qy[SPH_GROUP], qz[SPH_GROUP];
+                        if (KPRIMS && row.kind != real(0)) {     // a sphere / cylinder row (extension): warp-uniform, out of line
+                            #pragma unroll 1
+                            for (int g = 0; g < SPH_GROUP; ++g)
+                                key[g] = dist_to_key(prim_dist_general(tr + ro_box + b * BOX_REALS, px[g], py[g], pz[g]));
+                        } else {
                         bool any_inside = false;
                         #pragma unroll
                         for (int g = 0; g < SPH_GROUP; ++g) {
@@ -397,6 +402,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                             #pragma unroll
                             for (int g = 0; g < SPH_GROUP; ++g)
                                 if (!(key[g] > real(0))) key[g] = box_inside_key(qx[g], qy[g], qz[g]);
+                        }
                         }
                         #pragma unroll
                         for (int g = 0; g < SPH_GROUP; ++g)
@@ -436,7 +442,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                             {
                                 BoxRow<real> row;
                                 load_box(tr + ro_box + kmin * BOX_REALS, row);
-                                box_gradient(row, A.grad_mode, px, py, pz, dmin, grad);
+                                sdf_row_gradient(tr + ro_box + kmin * BOX_REALS, row, A.grad_mode, px, py, pz, dmin, grad);
                             }
                             const unsigned mask = (unsigned)ti[io_sph_mask + s];
                             real *st = stale0;
@@ -468,7 +474,7 @@ kin_eval_kernel(const __grid_constant__ KernelArgs A) {
                     {
                         BoxRow<real> row;
                         load_box(tr + ro_box + kmin * BOX_REALS, row);
-                        box_gradient(row, A.grad_mode, px, py, pz, dmin, grad);
+                        sdf_row_gradient(tr + ro_box + kmin * BOX_REALS, row, A.grad_mode, px, py, pz, dmin, grad);
                     }
                     const unsigned mask = (unsigned)ti[io_sph_mask + s];
                     const real *jf = jf0;
@@ -512,7 +518,7 @@ sdf_points_kernel(const real *__restrict__ boxes, int n_box, const real *__restr
         BoxRow<real> row;
         for (int b = 0; b < n_box; ++b) {
             load_box(tb + b * BOX_REALS, row);
-            const real key = box_key(row, px, py, pz);
+            const real key = sdf_row_key(tb + b * BOX_REALS, row, px, py, pz);
             if (key < kmin) { kmin = key; kidx = b; }
         }
         const real dmin = key_to_dist(kmin);
@@ -521,7 +527,7 @@ sdf_points_kernel(const real *__restrict__ boxes, int n_box, const real *__restr
         if (grads) {
             real g[3];
             load_box(tb + kidx * BOX_REALS, row);
-            box_gradient(row, grad_mode, px, py, pz, dmin, g);
+            sdf_row_gradient(tb + kidx * BOX_REALS, row, grad_mode, px, py, pz, dmin, g);
             #pragma unroll
             for (int i = 0; i < 3; ++i) grads[AOS ? 3 * n + i : (long long)i * n_pts + n] = g[i];
         }

@@ -116,6 +116,8 @@ void emit_box_rows(const HostModel &m, double *dst) {
         std::memcpy(br, m.box_inv[b].r, sizeof(double) * 9);
         std::memcpy(br + 9, m.box_inv[b].p, sizeof(double) * 3);
         std::memcpy(br + 12, &m.box_half[3 * b], sizeof(double) * 3);
+        br[15] = (size_t)b < m.box_kind.size() ? (double)m.box_kind[b] : 0.0;
+        br[16] = (size_t)b < m.box_round.size() ? m.box_round[b] : 0.0;
     }
 }
 

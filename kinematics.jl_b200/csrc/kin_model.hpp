@@ -31,6 +31,8 @@ struct HostModel {
     int n_box = 0;
     std::vector<Xf> box_inv;        // inv(pose)   (sdf.jl:58-61, transform.jl:62-65)
     std::vector<double> box_half;   // 0.5 * width (sdf.jl:68)
+    std::vector<int> box_kind;      // row kind of the device table: 0 box, 1 rounded box (sphere), 2 cylinder (extension)
+    std::vector<double> box_round;  // rounding radius of a kind-1 row (the sphere's radius)
     std::vector<int> topo;          // parents before children
     std::vector<unsigned> relmask;  // [L] bit c set <=> control column c moves link (rptable, mechanism.jl:117-139)
 
@@ -44,7 +46,7 @@ struct Program {
     std::vector<double> reals;
 };
 
-// the box table of a program: n_box rows of BOX_REALS doubles (inverse pose, half extents, padding)
+// the box table of a program: n_box rows of BOX_REALS doubles (inverse pose, half extents, kind, rounding radius, pad)
 void emit_box_rows(const HostModel &m, double *dst);
 
 // fk_links / jac_links are 0-based link indices in output order.

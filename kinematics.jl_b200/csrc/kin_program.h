@@ -41,7 +41,7 @@ constexpr int NODE_REALS = 16;  // R_off[9] row-major, t_off[3], axis[3], pad
 constexpr int ATT_INTS = 4;     // fk_index, flags, jac_index, relmask
 constexpr int ATT_REALS = 12;   // C: R[9] row-major, t[3]
 constexpr int SPH_REALS = 4;    // centre in node frame [3], radius
-constexpr int BOX_REALS = 18;   // inv_R[9] row-major, inv_t[3], half[3], pad x3.  Even stride from an even offset: an
+constexpr int BOX_REALS = 18;   // inv_R[9] row-major, inv_t[3], half[3], kind, rounding radius, pad.  Even stride from an even offset: an
                                 // FP64 row is 8 aligned 16-byte pairs (8 LDS.128 instead of 15 LDS.64); when lanes
                                 // read different rows in the gradient pass, row b starts at bank 4b mod 32, so up to 8
                                 // boxes are conflict-free

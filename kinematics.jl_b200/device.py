@@ -96,12 +96,16 @@ class DeviceModel:
             _lib.check(_lib.lib().kin_model_set_spheres(self.h, len(links), _iptr(links), _dptr(centers), _dptr(radii)))
             self._sph_sig, self.n_spheres = sig, len(links)
 
-    def set_boxes(self, poses, widths):
+    def set_boxes(self, poses, widths, kinds=None):
         poses = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)).reshape(-1, 16)
         widths = np.ascontiguousarray(widths, dtype=np.float64).reshape(-1, 3)
-        sig = (poses.tobytes(), widths.tobytes())
+        kinds = np.zeros(len(poses), dtype=np.int32) if kinds is None else np.ascontiguousarray(kinds, dtype=np.int32)
+        sig = (poses.tobytes(), widths.tobytes(), kinds.tobytes())
         if sig != self._box_sig:
-            _lib.check(_lib.lib().kin_model_set_boxes(self.h, len(poses), _dptr(poses), _dptr(widths)))
+            if kinds.any():         # sphere / cylinder rows (extension)
+                _lib.check(_lib.lib().kin_model_set_primitives(self.h, len(poses), _iptr(kinds), _dptr(poses), _dptr(widths)))
+            else:
+                _lib.check(_lib.lib().kin_model_set_boxes(self.h, len(poses), _dptr(poses), _dptr(widths)))
             self._box_sig, self.n_boxes = sig, len(poses)
 
 

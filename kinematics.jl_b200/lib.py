@@ -16,6 +16,7 @@ F64, F32 = 0, 1
 SOA, AOS, TILED32 = 0, 1, 2
 FIXED, REVOLUTE, PRISMATIC = 0, 1, 2
 GRAD_FD, GRAD_ANALYTIC, GRAD_FD_DIRECT = 0, 1, 2
+PRIM_BOX, PRIM_SPHERE, PRIM_CYLINDER = 0, 1, 2
 SCRATCH_REFERENCE, SCRATCH_CLEAN = 0, 1
 POSE_IK_OBJECTIVE, POSE_CONSTRAINT = 0, 1
 
@@ -61,7 +62,7 @@ class KinIkCall(C.Structure):
 ERR_UNAVAILABLE = -6
 
 EXPORTS = ["kin_last_error", "kin_abi_version", "kin_build_id", "kin_debug_build", "kin_model_create", "kin_model_destroy", "kin_model_set_spheres",
-           "kin_model_set_boxes", "kin_model_n_dof", "kin_model_n_spheres", "kin_model_n_boxes", "kin_eval",
+           "kin_model_set_boxes", "kin_model_set_primitives", "kin_sdf_points_prims", "kin_model_n_dof", "kin_model_n_spheres", "kin_model_n_boxes", "kin_eval",
            "kin_eval_host", "kin_fk_links", "kin_fk_jacobian", "kin_collision", "kin_launch_count",
            "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual", "kin_pose_residual_multi", "kin_probe_fp64",
            "kin_jit_status", "kin_jit_stats", "kin_codegen_dump", "kin_ik_solve", "kin_host_transfer_bytes"]
@@ -192,6 +193,9 @@ def lib():
         L.kin_model_destroy.argtypes = [C.c_void_p]
         L.kin_model_set_spheres.argtypes = [C.c_void_p, C.c_int32, _ip, _dp, _dp]
         L.kin_model_set_boxes.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
+        L.kin_model_set_primitives.argtypes = [C.c_void_p, C.c_int32, _ip, _dp, _dp]
+        L.kin_sdf_points_prims.argtypes = [C.c_int32, _ip, _dp, _dp, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         for f in (L.kin_model_n_dof, L.kin_model_n_spheres, L.kin_model_n_boxes):
             f.argtypes = [C.c_void_p]
         L.kin_eval.argtypes = [C.c_void_p, C.POINTER(KinCall)]

@@ -1,5 +1,9 @@
 """BoxSDF / UnionSDF (sdf.jl:1-119) on the B200 backend.  An SDF object is a description (box poses
-and widths); evaluating it at points or against a robot's collision spheres runs in libkin_b200."""
+and widths); evaluating it at points or against a robot's collision spheres runs in libkin_b200.
+
+SphereSDF / CylinderSDF are an EXTENSION: the reference supports boxes only
+(load_urdf.jl:10-15, sdf.jl:92-94).  They honour the same AbstractSDF contract -- ``sdf(p)``, the generic
+forward-difference ``gradient!`` (sdf.jl:34-41), membership in a UnionSDF with first-minimum argmin."""
 from __future__ import annotations
 
 import ctypes as C
@@ -8,7 +12,7 @@ import uuid
 import numpy as np
 
 from . import lib as _lib
-from .mechanism import BoxMetaData, Link, Mechanism, add_new_link
+from .mechanism import BoxMetaData, CylinderMetaData, Link, Mechanism, SphereMetaData, add_new_link
 from .transform import Transform
 
 
@@ -16,6 +20,11 @@ class AbstractSDF:
     def world_boxes(self):
         """-> (poses (B, 4, 4), widths (B, 3)) in UnionSDF.sdfs order."""
         raise NotImplementedError
+
+    def world_primitives(self):
+        """-> (poses (B, 4, 4), sizes (B, 3), kinds (B,) int32: lib.PRIM_BOX / PRIM_SPHERE / PRIM_CYLINDER)."""
+        poses, widths = self.world_boxes()
+        return poses, widths, np.zeros(len(poses), dtype=np.int32)
 
     # ---- sdf(p) and gradient!(sdf, p, out) -------------------------------------------------------
     def __call__(self, p, return_argmin=False):
@@ -38,15 +47,16 @@ class AbstractSDF:
             P = P.double()
         P = P.contiguous()
         N = P.shape[0]
-        poses, widths = self.world_boxes()
+        poses, widths, kinds = self.world_primitives()
         poses_cm = np.ascontiguousarray(poses.transpose(0, 2, 1)).reshape(-1, 16)
         widths = np.ascontiguousarray(widths, dtype=np.float64)
+        kinds = np.ascontiguousarray(kinds, dtype=np.int32)
         vals = torch.empty(N, dtype=P.dtype, device=P.device)
         grads = torch.empty((N, 3), dtype=P.dtype, device=P.device) if want_grad else None
         am = torch.empty(N, dtype=torch.int32, device=P.device) if want_argmin else None
         dp = C.POINTER(C.c_double)
-        _lib.check(_lib.lib().kin_sdf_points(
-            len(poses_cm), poses_cm.ctypes.data_as(dp), widths.ctypes.data_as(dp),
+        _lib.check(_lib.lib().kin_sdf_points_prims(
+            len(poses_cm), kinds.ctypes.data_as(C.POINTER(C.c_int32)), poses_cm.ctypes.data_as(dp), widths.ctypes.data_as(dp),
             _lib.F32 if P.dtype == torch.float32 else _lib.F64, _lib.AOS, P.data_ptr(), N, grad_mode,
             vals.data_ptr(), grads.data_ptr() if want_grad else None, am.data_ptr() if want_argmin else None,
             torch.cuda.current_stream(P.device).cuda_stream))
@@ -59,7 +69,7 @@ class AbstractSDF:
 class BoxSDF(AbstractSDF):
     """sdf.jl:48-65: ``BoxSDF(pose, width)`` stand-alone, or attached to a link of a mechanism."""
 
-    def __init__(self, pose, width, attach=None):
+    def __init__(self, pose, width=None, attach=None):
         if isinstance(pose, BoxMetaData):
             pose, width = pose.origin, pose.extents
         self.pose = pose if isinstance(pose, Transform) else Transform(pose)
@@ -75,6 +85,34 @@ class BoxSDF(AbstractSDF):
 
     def world_boxes(self):
         return self.world_pose()[None], self.width[None]
+
+
+class SphereSDF(BoxSDF):
+    """Extension: ``SphereSDF(pose, radius)``; d = |p - c| - r."""
+    kind = _lib.PRIM_SPHERE
+
+    def __init__(self, pose, radius=None, attach=None):
+        if isinstance(pose, SphereMetaData):
+            pose, radius = pose.origin, pose.radius
+        BoxSDF.__init__(self, pose, [radius, 0.0, 0.0], attach)
+        self.radius = float(radius)
+
+    def world_boxes(self):
+        raise _lib.KinError("a SphereSDF is not a box: use world_primitives()")
+
+    def world_primitives(self):
+        return self.world_pose()[None], self.width[None], np.array([self.kind], dtype=np.int32)
+
+
+class CylinderSDF(SphereSDF):
+    """Extension: ``CylinderSDF(pose, radius, length)``, axis = local z, centred on the pose (URDF <cylinder>)."""
+    kind = _lib.PRIM_CYLINDER
+
+    def __init__(self, pose, radius=None, length=None, attach=None):
+        if isinstance(pose, CylinderMetaData):
+            pose, radius, length = pose.origin, pose.radius, pose.length
+        BoxSDF.__init__(self, pose, [radius, length, 0.0], attach)
+        self.radius, self.length = float(radius), float(length)
 
 
 def _obstacle_transform(mech: Mechanism, link: Link):
@@ -96,15 +134,20 @@ class UnionSDF(AbstractSDF):
     metadata, in ``mech.links`` order, attached through a new link placed at the collision origin
     (sdf.jl:82-97); ``UnionSDF([sdf, ...])`` unions existing SDFs."""
 
-    def __init__(self, arg):
+    def __init__(self, arg, primitives=False):
+        """``primitives=True`` (extension) also turns the URDF's <sphere> / <cylinder> collision geometry into
+        SphereSDF / CylinderSDF members; the default skips them as the reference does (sdf.jl:92-94)."""
         if isinstance(arg, Mechanism):
             mech, sdfs = arg, []
             for link in list(mech.links):
                 meta = link.geometric_meta_data
-                if isinstance(meta, BoxMetaData):
+                cls = BoxSDF if isinstance(meta, BoxMetaData) else None
+                if primitives and link.link_type == "URDF":
+                    cls = SphereSDF if isinstance(meta, SphereMetaData) else CylinderSDF if isinstance(meta, CylinderMetaData) else cls
+                if cls is not None:
                     new_link = Link("boxsdf_" + str(uuid.uuid1()), link_type="SdfLinkType")
                     add_new_link(mech, new_link, link, meta.origin)
-                    sdfs.append(BoxSDF(meta.origin, meta.extents, attach=(mech, new_link)))
+                    sdfs.append(cls(meta, attach=(mech, new_link)))
             self.sdfs = sdfs
         else:
             self.sdfs = list(arg)
@@ -112,3 +155,7 @@ class UnionSDF(AbstractSDF):
     def world_boxes(self):
         parts = [s.world_boxes() for s in self.sdfs]
         return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+    def world_primitives(self):
+        parts = [s.world_primitives() for s in self.sdfs]
+        return tuple(np.concatenate([p[i] for p in parts]) for i in range(3))

@@ -444,6 +444,11 @@ typedef struct {           /* sdf.jl:48-56 (stand-alone boxes; attached boxes ar
     Tf pose, inv_pose;
     double width[3];
     double val_cache;
+    int kind;              /* 0 = box (the only primitive of the reference, load_urdf.jl:10-15, sdf.jl:92-94);
+                              EXTENSION (no reference counterpart, textbook formulas): 1 = sphere,
+                              width[0] = radius; 2 = cylinder along the local z axis, width[0] = radius,
+                              width[1] = length.  They plug into the same AbstractSDF contract: value at p,
+                              generic forward-difference gradient! (sdf.jl:34-41), UnionSDF argmin. */
 } Box;
 typedef struct {           /* sdf.jl:76-80 */
     int n; Box *boxes; double *vals_cache; int min_idx_cache;   /* 1-based argmin */
@@ -459,6 +464,12 @@ OR_EXPORT Sdf *or_sdf_create(int n_boxes, const double *pose16, const double *wi
     }
     return s;
 }
+/* union of mixed primitives (extension, see Box.kind): size3 = widths | (radius, -, -) | (radius, length, -) */
+OR_EXPORT Sdf *or_sdf_create_prims(int n, const int *kinds, const double *pose16, const double *size3) {
+    Sdf *s = or_sdf_create(n, pose16, size3);
+    for (int i = 0; i < n; ++i) s->boxes[i].kind = kinds ? kinds[i] : 0;
+    return s;
+}
 OR_EXPORT void or_sdf_destroy(Sdf *s) { if (s) { free(s->boxes); free(s->vals_cache); free(s); } }
 static Sdf *sdf_clone(const Sdf *s) {
     Sdf *c = calloc(1, sizeof(Sdf)); c->n = s->n;
@@ -471,11 +482,20 @@ static Sdf *sdf_clone(const Sdf *s) {
 static double box_eval(Box *b, const double p[3], int do_cache) {
     double q[3], pl[3];
     tf_apply(&b->inv_pose, p, pl);
-    for (int i = 0; i < 3; ++i) q[i] = fabs(pl[i]) - 0.5 * b->width[i];
-    double m0 = fmax(q[0], 0.0), m1 = fmax(q[1], 0.0), m2 = fmax(q[2], 0.0);
-    double nrm = sqrt(m0*m0 + m1*m1 + m2*m2);
-    double mx = fmax(fmax(q[0], q[1]), q[2]);
-    double d = nrm + fmin(mx, 0.0);
+    double d;
+    if (b->kind == 1) {            /* sphere: |p - c| - r */
+        d = sqrt(pl[0]*pl[0] + pl[1]*pl[1] + pl[2]*pl[2]) - b->width[0];
+    } else if (b->kind == 2) {     /* capped cylinder: the box formula on (radial, axial) */
+        double q0 = sqrt(pl[0]*pl[0] + pl[1]*pl[1]) - b->width[0], q1 = fabs(pl[2]) - 0.5 * b->width[1];
+        double m0 = fmax(q0, 0.0), m1 = fmax(q1, 0.0);
+        d = sqrt(m0*m0 + m1*m1) + fmin(fmax(q0, q1), 0.0);
+    } else {
+        for (int i = 0; i < 3; ++i) q[i] = fabs(pl[i]) - 0.5 * b->width[i];
+        double m0 = fmax(q[0], 0.0), m1 = fmax(q[1], 0.0), m2 = fmax(q[2], 0.0);
+        double nrm = sqrt(m0*m0 + m1*m1 + m2*m2);
+        double mx = fmax(fmax(q[0], q[1]), q[2]);
+        d = nrm + fmin(mx, 0.0);
+    }
     if (do_cache) b->val_cache = d;
     return d;
 }
@@ -508,6 +528,18 @@ static void sdf_gradient_analytic(Sdf *s, const double p[3], double g[3]) {
     Box *b = &s->boxes[s->min_idx_cache - 1];
     double pl[3], q[3], gl[3] = {0,0,0};
     tf_apply(&b->inv_pose, p, pl);
+    if (b->kind == 1) {
+        double nrm = sqrt(pl[0]*pl[0] + pl[1]*pl[1] + pl[2]*pl[2]);
+        if (nrm > 0.0) for (int i = 0; i < 3; ++i) gl[i] = pl[i] / nrm;
+    } else if (b->kind == 2) {
+        double rxy = sqrt(pl[0]*pl[0] + pl[1]*pl[1]);
+        double q0 = rxy - b->width[0], q1 = fabs(pl[2]) - 0.5 * b->width[1];
+        double m0 = fmax(q0, 0.0), m1 = fmax(q1, 0.0), nrm = sqrt(m0*m0 + m1*m1);
+        double ux = rxy > 0.0 ? pl[0] / rxy : 0.0, uy = rxy > 0.0 ? pl[1] / rxy : 0.0, sz = pl[2] < 0 ? -1.0 : 1.0;
+        if (nrm > 0.0) { gl[0] = m0 / nrm * ux; gl[1] = m0 / nrm * uy; gl[2] = m1 / nrm * sz; }
+        else if (q0 > q1) { gl[0] = ux; gl[1] = uy; }
+        else gl[2] = sz;
+    } else {
     for (int i = 0; i < 3; ++i) q[i] = fabs(pl[i]) - 0.5 * b->width[i];
     double m[3] = {fmax(q[0],0.0), fmax(q[1],0.0), fmax(q[2],0.0)};
     double nrm = sqrt(m[0]*m[0] + m[1]*m[1] + m[2]*m[2]);
@@ -516,6 +548,7 @@ static void sdf_gradient_analytic(Sdf *s, const double p[3], double g[3]) {
     } else {
         int k = 0; if (q[1] > q[k]) k = 1; if (q[2] > q[k]) k = 2;
         gl[k] = pl[k] < 0 ? -1.0 : 1.0;
+    }
     }
     /* world gradient = R * g_local  (inv_pose rotation is R') */
     for (int r = 0; r < 3; ++r) {

@@ -70,6 +70,8 @@ def lib():
         L.or_get_jacobian_inplace.argtypes = L.or_get_jacobian.argtypes
         L.or_sdf_create.restype = C.c_void_p
         L.or_sdf_create.argtypes = [C.c_int, _dp, _dp]
+        L.or_sdf_create_prims.restype = C.c_void_p
+        L.or_sdf_create_prims.argtypes = [C.c_int, _ip, _dp, _dp]
         L.or_sdf_destroy.argtypes = [C.c_void_p]
         L.or_sdf_eval.restype = C.c_double
         L.or_sdf_eval.argtypes = [C.c_void_p, _dp]
@@ -144,6 +146,7 @@ class RefLink:
     def __init__(self, name, id_, box=None):
         self.name, self.id = name, id_
         self.box = box          # (extents[3], origin 4x4) or None  -- BoxMetaData, mechanism.jl:3-6
+        self.prim = None        # extension: (kind, size[3], origin 4x4) of a sphere / cylinder collision primitive
         self.has_meta = False   # any collision geometry at all
 
 
@@ -200,6 +203,13 @@ def parse_urdf(urdf_path, with_base=False):
             if box is not None:
                 ext = np.array([float(v) for v in box.get("size").split()])
                 l.box = (ext, _origin(col))
+            # extension (no reference counterpart): sphere / cylinder collision primitives, kept as (kind, size, origin)
+            sph = geom.find("sphere") if geom is not None else None
+            cyl = geom.find("cylinder") if geom is not None else None
+            if sph is not None:
+                l.prim = (1, np.array([float(sph.get("radius")), 0.0, 0.0]), _origin(col))
+            if cyl is not None:
+                l.prim = (2, np.array([float(cyl.get("radius")), float(cyl.get("length")), 0.0]), _origin(col))
         links.append(l)
     joints = []
     for i, n in enumerate(joint_nodes):
@@ -297,12 +307,15 @@ def get_jacobian_inplace(m, link, joints, with_rot, mat, rpy_jac=False):
 class RefSDF:
     """UnionSDF over boxes with fixed world poses (a single BoxSDF is a union of one)."""
 
-    def __init__(self, poses, widths):
+    def __init__(self, poses, widths, kinds=None):
+        """kinds (extension beyond the reference, which has boxes only): 0 box (width = extents), 1 sphere
+        (width[0] = radius), 2 cylinder along local z (width[0] = radius, width[1] = length)."""
         self.poses = [np.asarray(p, dtype=np.float64) for p in poses]
         self.widths = [np.asarray(w, dtype=np.float64) for w in widths]
+        self.kinds = [0] * len(self.poses) if kinds is None else [int(k) for k in kinds]
         P = _dbl(np.stack([p.T.reshape(-1) for p in self.poses]))
         W = _dbl(np.stack(self.widths))
-        self.h = lib().or_sdf_create(len(self.poses), _d(P), _d(W))
+        self.h = lib().or_sdf_create_prims(len(self.poses), _i(_ints(self.kinds)), _d(P), _d(W))
 
     def __del__(self):
         try:
@@ -327,22 +340,38 @@ def BoxSDF(pose, width):
     return RefSDF([pose], [width])
 
 
-def UnionSDF(mech_or_sdfs):
+def SphereSDF(pose, radius):
+    return RefSDF([pose], [[radius, 0.0, 0.0]], [1])
+
+
+def CylinderSDF(pose, radius, length):
+    return RefSDF([pose], [[radius, length, 0.0]], [2])
+
+
+def UnionSDF(mech_or_sdfs, primitives=False):
     """sdf.jl:82-97: one box per link that carries box collision metadata, in
     ``mech.links`` order, world pose = get_transform(link) * meta.origin evaluated
-    at the obstacle mechanism's CURRENT joint angles / base pose (sdf.jl:14-32)."""
+    at the obstacle mechanism's CURRENT joint angles / base pose (sdf.jl:14-32).
+    ``primitives=True`` (extension) also takes sphere / cylinder collision primitives."""
     if isinstance(mech_or_sdfs, RefMechanism):
         m = mech_or_sdfs
-        poses, widths = [], []
+        poses, widths, kinds = [], [], []
         for l in list(m.links):
             if l.box is not None:
                 ext, origin = l.box
                 poses.append(get_transform(m, l) @ origin)
                 widths.append(ext)
-        return RefSDF(poses, widths)
+                kinds.append(0)
+            elif primitives and l.prim is not None:
+                kind, size, origin = l.prim
+                poses.append(get_transform(m, l) @ origin)
+                widths.append(size)
+                kinds.append(kind)
+        return RefSDF(poses, widths, kinds)
     poses = [p for s in mech_or_sdfs for p in s.poses]
     widths = [w for s in mech_or_sdfs for w in s.widths]
-    return RefSDF(poses, widths)
+    kinds = [k for s in mech_or_sdfs for k in s.kinds]
+    return RefSDF(poses, widths, kinds)
 
 
 # --------------------------------------------------------------------------

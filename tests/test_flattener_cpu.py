@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L.EXPORTS)
     for name in declared:
         assert hasattr(L.lib(), name), name
-    assert L.lib().kin_abi_version() == 3
+    assert L.lib().kin_abi_version() == 4
     assert L.lib().kin_build_id().decode() == L.source_id()        # the loaded binary is the one built from these sources
 
 
@@ -212,3 +212,22 @@ def test_codegen_and_nvrtc_compile_without_a_gpu(tmp_path):
         if fused:
             p2 = (out / "kin_gen_phase2.inc").read_text()
             assert p2.count("phase2b_group<") == 4 and p2.count("phase2a_group<") == 1   # four relevance masks, one shared box search
+            cfg = (out / "kin_gen_config.h").read_text()
+            assert "#define KPRIMS 0" in cfg                          # a table of boxes compiles the box-only code
+    # the same fused kernel with the sphere / cylinder row test compiled in (extension, KPRIMS = 1), every layout + the
+    # one-warp-per-configuration variant: must compile for sm_100a
+    os.environ["KIN_JIT_FORCE_PRIMS"] = "1"
+    try:
+        for layout, n in ((L.SOA, 1 << 20), (L.AOS, 1 << 20), (L.TILED32, 1 << 20), (L.SOA, 64)):
+            c = L.KinCall()
+            c.precision, c.layout, c.n, c.q = L.F64, layout, n, 1
+            c.n_fk_links, c.fk_links, c.T_out = 25, fk.ctypes.data_as(ip), 1
+            c.truncation_dist = float("inf")
+            c.vals_out, c.grads_out = 1, 1
+            out = tmp_path / ("prims_%d_%d" % (layout, n))
+            out.mkdir()
+            L.check(lib.kin_codegen_dump(C.byref(d), C.byref(c), 1, str(out).encode()))
+            assert "#define KPRIMS 1" in (out / "kin_gen_config.h").read_text()
+            assert (out / "kin_gen.cubin").stat().st_size > 10000
+    finally:
+        del os.environ["KIN_JIT_FORCE_PRIMS"]

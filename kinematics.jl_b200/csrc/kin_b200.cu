@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -883,10 +884,12 @@ void fill_row(void *dst, size_t n, double v, bool f32) {
 struct RowPlan {                         // of one output array with `comps` component rows
     std::vector<std::pair<int, int>> runs;                 // [begin, end) runs of rows that depend on the configuration
     std::vector<std::pair<int, double>> consts;            // (row, value) of the others
-    void build(size_t comps, const std::vector<std::pair<int, double>> &cs) {
+    void build(size_t comps, const std::vector<std::pair<int, double>> &cs, const std::vector<int> &dup_rows = {}) {
         std::vector<char> is_const(comps, 0);
         for (const auto &kv : cs)
             if (kv.first >= 0 && (size_t)kv.first < comps && !is_const[kv.first]) { is_const[kv.first] = 1; consts.push_back(kv); }
+        for (int r : dup_rows)             // rows the host copies from another row that did cross PCIe
+            if (r >= 0 && (size_t)r < comps) is_const[r] = 1;
         for (size_t r = 0; r < comps;) {
             if (is_const[r]) { ++r; continue; }
             size_t e = r;
@@ -895,6 +898,48 @@ struct RowPlan {                         // of one output array with `comps` com
             r = e;
         }
     }
+};
+
+// dst[i] = +-src[i] with non-temporal stores (the duplicate rows of a host-staged call)
+void copy_row(void *dst, const void *src, size_t n, bool negate, bool f32) {
+    if (f32) {
+        float *d = (float *)dst;
+        const float *p = (const float *)src;
+        for (size_t i = 0; i < n; ++i) d[i] = negate ? -p[i] : p[i];
+        return;
+    }
+    double *d = (double *)dst;
+    const double *p = (const double *)src;
+    size_t i = 0;
+#if defined(__SSE2__)
+    for (; i < n && ((uintptr_t)(d + i) & 15); ++i) d[i] = negate ? -p[i] : p[i];
+    const __m128d sign = _mm_set1_pd(negate ? -0.0 : 0.0);
+    for (; i + 2 <= n; i += 2) _mm_stream_pd(d + i, _mm_xor_pd(_mm_loadu_pd(p + i), sign));
+    _mm_sfence();
+#endif
+    for (; i < n; ++i) d[i] = negate ? -p[i] : p[i];
+}
+
+struct DupRow { unsigned char *dst; const unsigned char *src; bool negate; };
+
+// Progress of the chunk loop, for the threads that complete the duplicate rows behind it: chunk i may be read once
+// `issued` > i (its event has been recorded) and the event has completed.
+struct ChunkFeed {
+    std::mutex mu;
+    std::condition_variable cv;
+    long long issued = 0;
+    bool done = false;                   // no further chunk will be issued (normal end or error exit)
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::pair<long long, long long>> span;     // (n0, count) of chunk i
+    void publish(long long n0, long long cnt) {
+        { std::lock_guard<std::mutex> l(mu); span.emplace_back(n0, cnt); ++issued; }
+        cv.notify_all();
+    }
+    void finish() {
+        { std::lock_guard<std::mutex> l(mu); done = true; }
+        cv.notify_all();
+    }
+    ~ChunkFeed() { for (auto e : ev) cudaEventDestroy(e); }
 };
 
 struct FillJobs {                        // joins its threads on every exit path
@@ -961,14 +1006,40 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
     // call: host threads fill them while the device works on the rest.  Same values as the kernels write (up to the
     // sign of a zero).  get_jacobian! semantics (rows the kernel leaves untouched) and KIN_HOST_NO_CONST_FILL opt out.
     RowPlan planT, planJ;
+    auto dups = std::make_shared<std::vector<DupRow>>();
     bool elide = !aos && (cT || cJ) && !(c->J_out && c->keep_irrelevant) && !std::getenv("KIN_HOST_NO_CONST_FILL");
     if (elide) {
         kin::GenSource g;
         std::string err;
         elide = kin::generate_source(dp->prog, gen_options(m, c, dp), g, err);
-        if (elide) { planT.build(cT, g.const_T); planJ.build(cJ, g.const_J); }
-        if (planT.consts.empty() && planJ.consts.empty()) elide = false;
+        if (elide) {
+            // outputs that hold the same variable of the generated code (possibly negated): the first one crosses
+            // PCIe, the host copies the others from it (KIN_HOST_NO_DUP_COPY opts out)
+            std::vector<int> dupT, dupJ;
+            if (!std::getenv("KIN_HOST_NO_DUP_COPY")) {
+                std::map<std::string, const unsigned char *> first;
+                auto scan = [&](const std::vector<std::pair<int, std::string>> &ex, void *base_, size_t comps, std::vector<int> &dup) {
+                    for (const auto &kv : ex) {
+                        if (kv.first < 0 || (size_t)kv.first >= comps) continue;
+                        const bool neg = kv.second.size() > 3 && kv.second[0] == '(' && kv.second[1] == '-';
+                        const std::string canon = neg ? kv.second.substr(2, kv.second.size() - 3) : kv.second;
+                        unsigned char *row = (unsigned char *)base_ + es * (size_t)kv.first * ldh;
+                        auto it = first.find(canon);
+                        // the primary must hold +x: a negated first occurrence stays an ordinary row
+                        if (it == first.end()) { if (!neg) first.emplace(canon, row); continue; }
+                        dups->push_back({row, it->second, neg});
+                        dup.push_back(kv.first);
+                    }
+                };
+                if (cT) scan(g.expr_T, c->T_out, cT, dupT);
+                if (cJ) scan(g.expr_J, c->J_out, cJ, dupJ);
+            }
+            planT.build(cT, g.const_T, dupT);
+            planJ.build(cJ, g.const_J, dupJ);
+        }
+        if (planT.consts.empty() && planJ.consts.empty() && dups->empty()) elide = false;
     }
+    ChunkFeed feed;
     FillJobs fill;
     if (elide) {
         struct Job { unsigned char *row; double v; };
@@ -985,8 +1056,33 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
             fill.threads.emplace_back([jobs, t, nt, n_fill, f32] {
                 for (size_t j = (size_t)t; j < jobs->size(); j += (size_t)nt) fill_row((*jobs)[j].row, n_fill, (*jobs)[j].v, f32);
             });
-        g_host_fill_bytes.fetch_add((long long)(es * jobs->size() * (size_t)N));
+        g_host_fill_bytes.fetch_add((long long)(es * (jobs->size() + dups->size()) * (size_t)N));
+        if (!dups->empty()) {
+            // the duplicate rows of chunk i are copied once its device -> host copies have landed
+            long long nd = env_ll("KIN_HOST_DUP_THREADS", std::min<long long>(6, std::max<long long>(1, hw / 2)));
+            nd = std::max<long long>(1, std::min<long long>(nd, (long long)dups->size()));
+            ChunkFeed *fd = &feed;
+            for (long long t = 0; t < nd; ++t)
+                fill.threads.emplace_back([dups, fd, t, nd, f32, es] {
+                    for (long long i = 0;; ++i) {
+                        cudaEvent_t ev;
+                        std::pair<long long, long long> sp;
+                        {
+                            std::unique_lock<std::mutex> l(fd->mu);
+                            fd->cv.wait(l, [&] { return fd->issued > i || fd->done; });
+                            if (fd->issued <= i) return;
+                            ev = fd->ev[(size_t)i]; sp = fd->span[(size_t)i];
+                        }
+                        if (cudaEventSynchronize(ev) != cudaSuccess) return;
+                        for (size_t j = (size_t)t; j < dups->size(); j += (size_t)nd) {
+                            const DupRow &d = (*dups)[j];
+                            copy_row(d.dst + es * (size_t)sp.first, d.src + es * (size_t)sp.first, (size_t)sp.second, d.negate, f32);
+                        }
+                    }
+                });
+        }
     }
+    struct FeedCloser { ChunkFeed &f; ~FeedCloser() { f.finish(); } } feed_closer{feed};     // declared after `fill`: runs first
     int k = 0;
     for (long long n0 = 0; n0 < N; n0 += chunk, k = (k + 1) % HostStage::kStreams) {
         const long long mcount = (N - n0 < chunk) ? N - n0 : chunk;
@@ -1041,7 +1137,15 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
         CUDA_TRY(copy(dV, nullptr, c->vals_out, cV, es, false));
         CUDA_TRY(copy(dG, nullptr, c->grads_out, cG, es, false));
         CUDA_TRY(copy(dA, nullptr, c->argmin_out, cA, 4, false));
+        if (!dups->empty()) {
+            cudaEvent_t ev;
+            CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
+            { std::lock_guard<std::mutex> l(feed.mu); feed.ev.push_back(ev); }
+            CUDA_TRY(cudaEventRecord(ev, s));
+            feed.publish(n0, mcount);
+        }
     }
+    feed.finish();
     for (int i = 0; i < HostStage::kStreams; ++i) CUDA_TRY(cudaStreamSynchronize(st.stream[i]));
     for (auto &t : fill.threads) t.join();
     return KIN_OK;

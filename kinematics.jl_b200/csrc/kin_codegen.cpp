@@ -149,6 +149,8 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
     const bool f32 = o.precision == 1;
     out.const_T.clear();
     out.const_J.clear();
+    out.expr_T.clear();
+    out.expr_J.clear();
     Emitter E(f32);
     const int ND = h.n_dof, DC = h.n_joints, S = o.coll ? h.n_sph : 0;
     const int rows = o.with_rot ? 6 : 3;
@@ -258,8 +260,10 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
                 for (int c = 0; c < 3; ++c)
                     for (int r = 0; r < 3; ++r)
                         if (Tl.r[r * 3 + c].c) out.const_T.emplace_back(base + c * 3 + r, Tl.r[r * 3 + c].v);
+                        else out.expr_T.emplace_back(base + c * 3 + r, Tl.r[r * 3 + c].e);
                 for (int r = 0; r < 3; ++r)
                     if (Tl.p[r].c) out.const_T.emplace_back(base + 9 + r, Tl.p[r].v);
+                    else out.expr_T.emplace_back(base + 9 + r, Tl.p[r].e);
                 if (aos) {
                     for (int c = 0; c < 3; ++c)
                         for (int r = 0; r < 3; ++r) E.os << "KPUT(12, " << c * 3 + r << ", " << E.str(Tl.r[r * 3 + c]) << ");\n";
@@ -286,6 +290,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
                 int chunk_k0 = kbase, chunk_cnt = 0;
                 auto stv = [&](int k, const Val &v) -> std::string {       // a value of the symbolic evaluation
                     if (v.c) out.const_J.emplace_back(k, v.v);
+                    else out.expr_J.emplace_back(k, v.e);
                     return E.str(v);
                 };
                 auto stz = [&](int k) -> std::string { out.const_J.emplace_back(k, 0.0); return "real(0)"; };

@@ -53,6 +53,11 @@ struct GenSource {
     // entries, Jacobian columns of joints that do not move the link): (component index, value).  kin_eval_host does
     // not move these rows over PCIe: the host fills them (SoA layout).
     std::vector<std::pair<int, double>> const_T, const_J;
+    // the other outputs: (component index, expression) -- a variable of the generated code, possibly negated "(-tN)".
+    // Two outputs with the same variable hold the same bits (rotation blocks shared by links joined through fixed
+    // pure-translation joints, joint axes that are columns of a link rotation, ...): kin_eval_host moves one of them
+    // over PCIe and lets the host copy the others.
+    std::vector<std::pair<int, std::string>> expr_T, expr_J;
 };
 
 // Returns false (with err) when the program cannot be specialised (the caller then uses the interpreting kernel).

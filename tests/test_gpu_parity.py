@@ -756,7 +756,9 @@ def test_fused_device_and_host_entry_points(layout):
     assert h2d == 8 * N * nd
     if layout == L.SOA:
         # the rows of T / J that do not depend on the configuration are filled by host threads, not copied over PCIe
-        assert filled > 8 * N * 100 and d2h + filled == full
+        # ... nor are the rows that duplicate another row (same variable of the generated code, possibly negated):
+        # 175 constant + 67 duplicate rows of the 348 for Fetch with the 8 arm joints
+        assert filled >= 8 * N * 230 and d2h + filled == full
         outs_2 = {k: np.full_like(v, -7.0) for k, v in outs_h.items()}
         c2 = _fused_call(dm, N, qh.ctypes.data, layout, fk, jac, outs_2["T"].ctypes.data, outs_2["J"].ctypes.data,
                          outs_2["V"].ctypes.data, outs_2["G"].ctypes.data, am_h.ctypes.data)

@@ -669,7 +669,7 @@ def main():
         # the check depends on the copies AND on the host-side fill: every row of T and J of the LAST configuration and of
         # one in the middle, host result vs the device-resident result of the same inputs (T / J of the headline run)
         gcol = 12 * (gl.id - 1) + 9
-        cols = (0, Ne - 1, Ne // 2, Ne // 3 + 17, (1 << 17) - 1, 1 << 17)      # incl. both sides of a staging-chunk boundary
+        cols = sorted({i for i in (0, Ne - 1, Ne // 2, Ne // 3 + 17, (1 << 17) - 1, 1 << 17) if 0 <= i < Ne})   # incl. both sides of a staging-chunk boundary
         dT = max(float((Th[:, i] - T[:, i].cpu()).abs().max()) for i in cols)
         dJ = max(float((Jh[:, i] - J[:, i].cpu()).abs().max()) for i in cols)
         e2e = {"value": world * Ne * e_steps / e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d_b,

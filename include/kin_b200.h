@@ -301,8 +301,10 @@ typedef struct {
      * constraint is enforced by an augmented-Lagrangian Levenberg-Marquardt iteration (csrc/kin_ik_coll.cuh): per
      * iteration ONE kin_eval over the batch (link transform + Euler-rate Jacobian + sphere distances and gradients,
      * truncated at margin + 0.05 as planning.jl:56, forward-difference SDF gradient, clean Jacobian scratch) and ONE
-     * step kernel (accept / multiplier update / normal equations / Cholesky), no host synchronisation, `iters`
-     * iterations at most.  A problem stops when f < ftol and every dist >= margin - ctol.  Works without NVRTC (the
+     * step kernel (accept / multiplier update / normal equations / Cholesky), `iters` iterations at most.  For
+     * n >= 4096 the still-running problems are compacted into an active list at iterations 1, 2, 3, 4, 6, 8, 12, 16,
+     * 24, ... and the list length (8 bytes) is read back, so that later iterations cover only them: the call then
+     * synchronises `stream` about ten times (KIN_IK_NO_COMPACT=1: fully asynchronous, every iteration over the whole batch).  A problem stops when f < ftol and every dist >= margin - ctol.  Works without NVRTC (the
      * interpreting kernels evaluate).  ~ (30 + 21 n_dof + 2 S + S n_dof) * 8 bytes of stream-ordered scratch per problem. */
     int32_t collision;
     int32_t reserved_;

@@ -1267,13 +1267,16 @@ namespace {
 
 template <int ND>
 void launch_ik_coll_step(const kin::IkCollArgs &a, bool rot, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((a.n + 127) / 128);
+    const unsigned grid = (unsigned)((a.n_act + 127) / 128);
     if (rot) kin::ik_coll_step_kernel<ND, true><<<grid, 128, 0, stream>>>(a);
     else kin::ik_coll_step_kernel<ND, false><<<grid, 128, 0, stream>>>(a);
 }
 
 // The collision-constrained solve of kin_ik_solve (csrc/kin_ik_coll.cuh): a loop of (kin_eval, step kernel) pairs on the
-// caller's stream over a stream-ordered workspace; nothing is read back.
+// caller's stream over a stream-ordered workspace.  At iterations 1, 2, 3, 4, 6, 8, 12, 16, 24, ... the still-running
+// problems are compacted into an active list and its length (8 bytes) is read back -- the only host synchronisations --
+// so that the following pairs cover only those problems (KIN_IK_NO_COMPACT=1: every pair covers the whole batch and
+// nothing is read back).
 // With c->collision == 0 (the pose-only problem when the run-time compiler is unavailable) no sphere is evaluated.
 int ik_solve_coll(KinModel *m, const KinIkCall *c) {
     const int nd = m->hm.n_dof(), S = c->collision ? m->hm.n_sph : 0, rows = c->with_rot ? 6 : 3;
@@ -1285,9 +1288,9 @@ int ik_solve_coll(KinModel *m, const KinIkCall *c) {
     const long long n = c->n, ld = (n + 31) / 32 * 32;
     // workspace (doubles per problem): q_try, T, J, V, G | q, H, g, phi, fpose, damp, viol, mult | Vfin ; then int32 status, its
     const long long nh = (long long)nd * (nd + 1) / 2;
-    const long long per = nd + 12 + (long long)rows * nd + S + (long long)S * nd + nd + nh + nd + 4 + S + S;
+    const long long per = nd + 12 + (long long)rows * nd + S + (long long)S * nd + nd + nh + nd + 4 + S + S + nd;
     double *ws = nullptr;
-    CUDA_TRY(cudaMallocFromPoolAsync((void **)&ws, sizeof(double) * (size_t)(per * ld) + 2 * sizeof(int32_t) * (size_t)ld, m->pool, stream));
+    CUDA_TRY(cudaMallocFromPoolAsync((void **)&ws, sizeof(double) * (size_t)(per * ld + 2) + 4 * sizeof(int32_t) * (size_t)ld, m->pool, stream));
     kin::IkCollArgs a;
     std::memset(&a, 0, sizeof a);
     double *p = ws;
@@ -1299,7 +1302,12 @@ int ik_solve_coll(KinModel *m, const KinIkCall *c) {
     a.q = take(nd); a.H = take(nh); a.g = take(nd);
     a.phi = take(1); a.fpose = take(1); a.damp = take(1); a.viol = take(1); a.mult = take(S);
     double *Vfin = take(S);
+    double *q_try_b = take(nd);                                  // second trial-point buffer (compaction ping-pong)
+    unsigned long long *d_count = (unsigned long long *)p;
+    p += 2;
     a.status = (int32_t *)p; a.its = a.status + ld;
+    int32_t *act_buf[2] = {a.its + ld, a.its + 2 * ld};
+    a.n_act = n; a.act = nullptr;
     a.margin = c->margin; a.mu = c->coll_weight > 0 ? c->coll_weight : 100.0; a.ftol = c->ftol;
     a.ctol = c->ctol > 0 ? c->ctol : 1e-6; a.lambda0 = c->lambda0 > 0 ? c->lambda0 : 1e-2;
     a.trunc = c->margin + 0.05;                                  // planning.jl:56
@@ -1319,7 +1327,27 @@ int ik_solve_coll(KinModel *m, const KinIkCall *c) {
     ec.truncation_dist = a.trunc; ec.grad_mode = KIN_GRAD_FD; ec.scratch_mode = KIN_SCRATCH_CLEAN;
     if (S > 0) { ec.vals_out = V; ec.grads_out = G; }
     ec.stream = c->stream;
+    const bool compact = !std::getenv("KIN_IK_NO_COMPACT") && n >= 4096;
+    int next_compact = 1, compact_step = 1, act_i = 0;
     for (int it = 0; it <= c->iters && rc == KIN_OK; ++it) {
+        if (compact && it == next_compact) {
+            // iterations 1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, ...
+            if (it >= 4 && (it & (it - 1)) == 0) compact_step = it / 2;
+            next_compact = it + compact_step;
+            cudaError_t le = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream);
+            double *q_in = a.q_try, *q_out_ = (a.q_try == q_try_b) ? ws : q_try_b;       // ws = the first buffer (take order)
+            kin::ik_coll_compact_kernel<<<(unsigned)((a.n_act + 255) / 256), 256, 0, stream>>>(a, nd, q_in, act_buf[act_i], q_out_, d_count);
+            if (le == cudaSuccess) le = cudaGetLastError();
+            g_launches.fetch_add(1);
+            unsigned long long cnt = 0;
+            if (le == cudaSuccess) le = cudaMemcpyAsync(&cnt, d_count, sizeof cnt, cudaMemcpyDeviceToHost, stream);
+            if (le == cudaSuccess) le = cudaStreamSynchronize(stream);
+            if (le != cudaSuccess) { rc = fail_cuda(le, "compacting the active list of kin_ik_solve"); break; }
+            a.act = act_buf[act_i]; a.n_act = (long long)cnt; a.q_try = q_out_;
+            act_i ^= 1;
+            ec.q = a.q_try; ec.n = a.n_act;
+            if (cnt == 0) break;                                 // every problem has stopped
+        }
         rc = kin_eval(m, &ec);
         if (rc != KIN_OK) break;
         a.it = it;

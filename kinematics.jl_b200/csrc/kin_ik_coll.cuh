@@ -13,8 +13,12 @@
 //      multiplier update lambda_s <- mu * psi_s at every accepted point, Gauss-Newton normal equations
 //      H = J'J + mu * sum_{psi_s > 0} g_s g_s',  g = J'e - mu * sum psi_s g_s  in registers, joints on a limit that are
 //      pushed outward frozen, Cholesky of H + damping (I + diag H), next trial point clamped to the limits.
-// A problem stops when |e|^2 < ftol and every constraint holds to ctol; stopped problems keep their trial point (their
-// evaluation is repeated, results ignored).  All state is SoA in a stream-ordered workspace.
+// A problem stops when |e|^2 < ftol and every constraint holds to ctol.  All state is SoA in a stream-ordered workspace.
+// ACTIVE LIST: most problems stop after 2-3 iterations, a few need dozens.  At a handful of iterations (1, 2, 3, 4, 6, 8,
+// 12, 16, 24, ...) the still-running problems are compacted into an index list (ik_coll_compact_kernel), the host reads
+// its length (8 bytes, one stream synchronisation) and the following launches cover only that many problems: the trial
+// points / kin_eval outputs are then indexed by list position i, the solver state by problem act[i].  Between two
+// compactions a problem that stops stays in the list (its evaluation is repeated, results ignored).
 #pragma once
 
 #include <cstdint>
@@ -25,11 +29,13 @@ constexpr int IKC_MAX_DOF = 12;
 
 struct IkCollArgs {
     long long n, ld;                 // problems, SoA stride of every array below
+    long long n_act;                 // launch width: length of the active list (== n before the first compaction)
+    const int32_t *act;              // list position -> problem (null: identity)
     int n_sph, it;
     double margin, mu, ftol, ctol, lambda0, trunc;
     const double *targets;           // [n][6] AoS (caller's)
     const double *T, *J, *V, *G;     // kin_eval outputs at the trial points (SoA)
-    double *q_try;                   // [ND][ld]  trial points = input of the next kin_eval
+    double *q_try;                   // [ND][ld]  trial points = input of the next kin_eval (indexed by list position)
     double *q, *H, *g;               // current point, its normal equations (lower triangle, row-major packed) and gradient
     double *phi, *fpose, *damp, *viol, *mult;      // merit, |e|^2, LM damping, max_s (margin - d_s), multipliers [S][ld]
     int32_t *status;                 // 0 running, 1 stopped (converged)
@@ -59,8 +65,9 @@ __global__ void __launch_bounds__(256) ik_coll_init_kernel(const IkCollArgs A, c
 
 template <int ND, bool ROT>
 __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= A.n) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // position in the active list
+    if (i >= A.n_act) return;
+    const long long n = A.act ? A.act[i] : i;                                  // problem
     if (A.status[n]) return;
     constexpr int ROWS = ROT ? 6 : 3;
     const long long ld = A.ld;
@@ -71,7 +78,7 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
     // ---- residual at the trial point: e = [p - p_t; rpy - rpy_t] (planning.jl:114-138 sign), angles wrapped ----
     double e[ROWS];
     {
-        const double *Tn = A.T + n, *tg = A.targets + n * 6;
+        const double *Tn = A.T + i, *tg = A.targets + n * 6;
         #pragma unroll
         for (int i = 0; i < 3; ++i) e[i] = Tn[(9 + i) * ld] - tg[i];
         if (ROT) {        // rpy(T), transform.jl:45-48 (RotZYX): R[r][c] = T[c*3 + r]
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
     // ---- merit under the CURRENT multipliers ----
     double phi_t = ft;
     for (int s = 0; s < S; ++s) {
-        const double d = A.V[s * ld + n];
+        const double d = A.V[s * ld + i];
         const double psi = d >= A.trunc ? 0.0 : fmax(0.0, margin - d + A.mult[s * ld + n] / mu);
         phi_t = fma(mu * psi, psi, phi_t);
     }
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
         // ---- accepted: multipliers, merit and normal equations at this point ----
         #pragma unroll
         for (int a = 0; a < ND; ++a) {
-            q[a] = A.q_try[a * ld + n];
+            q[a] = A.q_try[a * ld + i];
             g[a] = 0.0;
             #pragma unroll
             for (int b = 0; b <= a; ++b) H[a][b] = 0.0;
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
         for (int r = 0; r < ROWS; ++r) {
             double jr[ND];
             #pragma unroll
-            for (int a = 0; a < ND; ++a) jr[a] = A.J[(long long)(a * ROWS + r) * ld + n];
+            for (int a = 0; a < ND; ++a) jr[a] = A.J[(long long)(a * ROWS + r) * ld + i];
             #pragma unroll
             for (int a = 0; a < ND; ++a) {
                 g[a] = fma(jr[a], e[r], g[a]);
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
         double phi_n = ft, viol = -CUDART_INF;
         #pragma unroll 1
         for (int s = 0; s < S; ++s) {
-            const double d = A.V[s * ld + n];
+            const double d = A.V[s * ld + i];
             double lam = 0.0, psi = 0.0;
             if (d < A.trunc) {
                 viol = fmax(viol, margin - d);
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
             if (psi > 0.0) {
                 double gs[ND];
                 #pragma unroll
-                for (int a = 0; a < ND; ++a) gs[a] = A.G[(long long)(s * ND + a) * ld + n];
+                for (int a = 0; a < ND; ++a) gs[a] = A.G[(long long)(s * ND + a) * ld + i];
                 const double w = mu * psi;
                 #pragma unroll
                 for (int a = 0; a < ND; ++a) {
@@ -218,7 +225,29 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
         x[a] = sum / H[a][a];
     }
     #pragma unroll
-    for (int a = 0; a < ND; ++a) A.q_try[a * ld + n] = fmin(fmax(q[a] - x[a], A.lo[a]), A.hi[a]);
+    for (int a = 0; a < ND; ++a) A.q_try[a * ld + i] = fmin(fmax(q[a] - x[a], A.lo[a]), A.hi[a]);
+}
+
+// Compaction of the active list: every still-running problem of the current list (act_in, or the identity when null)
+// appends itself to act_out and takes its trial point along (q_try_in[., i] -> q_try_out[., j]).  The order of the new
+// list depends on the scheduling of the atomics; nothing else does (problems are independent, every kernel evaluates a
+// configuration the same way wherever it sits).  count[0] must be zero on entry.
+__global__ void __launch_bounds__(256) ik_coll_compact_kernel(const IkCollArgs A, int nd, const double *__restrict__ q_try_in,
+                                                              int32_t *__restrict__ act_out, double *__restrict__ q_try_out,
+                                                              unsigned long long *__restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < A.n_act && !A.status[A.act ? A.act[i] : i];
+    // one atomic per warp
+    const unsigned ballot = __ballot_sync(0xffffffffu, live);
+    if (!ballot) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!live) return;
+    const long long j = (long long)base + __popc(ballot & ((1u << lane) - 1u));
+    act_out[j] = (int32_t)(A.act ? A.act[i] : i);
+    for (int a = 0; a < nd; ++a) q_try_out[a * A.ld + j] = q_try_in[a * A.ld + i];
 }
 
 // q (SoA) -> q_out (AoS, caller's), |e|^2, iterations, and the smallest signed distance of the final configuration

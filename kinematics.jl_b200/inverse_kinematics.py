@@ -87,7 +87,7 @@ def ik_solve_device(m: Mechanism, link, joints, targets, q0, with_rot=True, iter
 
     With ``sscc`` and ``sdf``: the reference's constrained problem (inverse_kinematics.jl:14-19: the same objective
     subject to ``dists - margin >= 0``) from the warm start ``q0``, by an augmented-Lagrangian Levenberg-Marquardt
-    iteration that issues one fused ``kin_eval`` and one step kernel per iteration with no host round trip
+    iteration that issues one fused ``kin_eval`` and one step kernel per iteration over the still-running problems (active list)
     (csrc/kin_ik_coll.cuh) -> (q, f, iterations, dmin) with dmin (N,) the smallest signed sphere distance at q."""
     import torch
     collide = sscc is not None and sdf is not None
@@ -144,7 +144,7 @@ def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=T
     With ``sscc`` and ``sdf`` the reference's two-stage driver (inverse_kinematics.jl:1-21) runs on the device for the
     whole batch: the collision-free warm start (``use_bistage``, :8-13) and then the solve under the HARD constraint
     ``dists - margin >= 0`` (IneqConst with margin 0.02, :14-19), an augmented-Lagrangian Levenberg-Marquardt loop of
-    at most ``coll_iters`` (fused evaluation, step kernel) launch pairs without a host round trip.  ``restarts``
+    at most ``coll_iters`` (fused evaluation, step kernel) launch pairs over the still-running problems (the active list is re-compacted about ten times per solve).  ``restarts``
     re-seeds the problems that end with pose error > ``tol`` or a distance below ``margin - ctol`` (a local method can
     end pressed against the obstacle on the wrong side of it).
     ``targets`` (N, 6) [x y z roll pitch yaw], ``q0`` (N, n_dof).  Returns (q, f) with f the pose objective

@@ -270,7 +270,9 @@ KIN_API int kin_pose_residual_multi(KinModel *model, int32_t precision, int32_t 
                                     int32_t target_per_config, int32_t mode, void *val_out, void *jac_out, void *stream);
 
 /* The whole batched IK solve of config 4 in ONE kernel launch (device-resident loop; no host round trip per
- * iteration).  One thread per problem runs up to `iters` Levenberg-Marquardt iterations on the reference's objective
+ * iteration) -- for n >= 16384 in a few launches ("stages" of 3, 4, 6, 9 and the remaining iterations; KIN_IK_STAGES)
+ * over the still-running problems, whose index list is compacted between stages (its length, 8 bytes, is read back:
+ * the call then synchronises `stream` once per stage); the iterates are the ones of the single launch, bit for bit.  One thread per problem runs up to `iters` Levenberg-Marquardt iterations on the reference's objective
  * f = |[p - p_t; rpy - rpy_t]|^2 (inverse_kinematics.jl:38-50; angle residuals wrapped to (-pi, pi]) with the joint
  * limits as bounds (inverse_kinematics.jl:52-63: active set + clamping) and stops on its own when f < ftol.  The
  * kernel is generated for this model / link (straight-line FK + Euler-rate Jacobian, csrc/kin_codegen.cpp) and

@@ -1420,11 +1420,78 @@ int kin_ik_solve(KinModel *m, const KinIkCall *c) {
         a.lo[j] = c->lower ? c->lower[j] : -INFINITY;
         a.hi[j] = c->upper ? c->upper[j] : INFINITY;
     }
-    void *args[] = {&a};
-    const long long grid = (c->n + k->block - 1) / k->block;
-    CUDA_TRY(cudaLaunchKernel((const void *)k->kern, dim3((unsigned)grid), dim3((unsigned)k->block), args, 0, (cudaStream_t)c->stream));
-    g_launches.fetch_add(1);
-    g_jit_launches.fetch_add(1);
+    cudaStream_t stream = (cudaStream_t)c->stream;
+    auto launch_stage = [&](kin::IkArgs &st) -> cudaError_t {
+        void *args[] = {&st};
+        const long long grid = (st.n + k->block - 1) / k->block;
+        g_launches.fetch_add(1);
+        g_jit_launches.fetch_add(1);
+        return cudaLaunchKernel((const void *)k->kern, dim3((unsigned)grid), dim3((unsigned)k->block), args, 0, stream);
+    };
+    // STAGES.  One thread per problem leaves a warp busy until its slowest problem stops: most problems need 5-10
+    // iterations, a few per cent all of them, so nearly every warp runs the whole budget.  A long solve over a large
+    // batch is therefore split into a few launches (default: 3, 4, 6, 9 and the remaining iterations; 2^20 Fetch targets x 40
+    // iterations: 17.9 -> 6.1 ms, profiles/sweep_ik_stages.sh); between two of them
+    // the still-running problems (f >= ftol) are compacted into an index list whose length (8 bytes) is the only thing
+    // read back.  A later stage restarts from the best point and the damping of the one before, re-evaluates there
+    // (one extra evaluation per stage) and takes exactly the steps the single launch would have taken: same results.
+    // KIN_IK_STAGES="a,b,..." overrides the schedule, KIN_IK_STAGES=0 disables it.
+    std::vector<int> stages;
+    {
+        const char *e = std::getenv("KIN_IK_STAGES");
+        std::string spec = e ? e : "3,4,6,9";
+        if (c->n >= 16384 && spec != "0") {
+            int left = c->iters;
+            size_t pos = 0;
+            while (pos < spec.size() && left > 0) {
+                const int v = std::atoi(spec.c_str() + pos);
+                if (v <= 0 || v >= left) break;
+                stages.push_back(v);
+                left -= v;
+                pos = spec.find(',', pos);
+                if (pos == std::string::npos) break;
+                ++pos;
+            }
+            if (!stages.empty()) stages.push_back(left);
+        }
+    }
+    if (stages.empty()) {
+        CUDA_TRY(launch_stage(a));
+        return KIN_OK;
+    }
+    // workspace: damping per problem, two index lists, the counter
+    const long long n = c->n;
+    unsigned char *ws = nullptr;
+    CUDA_TRY(cudaMallocFromPoolAsync((void **)&ws, sizeof(double) * (size_t)(n + 2) + 2 * sizeof(int32_t) * (size_t)n, m->pool, stream));
+    double *lam = (double *)ws;
+    unsigned long long *d_count = (unsigned long long *)(lam + n);
+    int32_t *lists[2] = {(int32_t *)(lam + n + 2), (int32_t *)(lam + n + 2) + n};
+    a.lam_io = lam;
+    cudaError_t le = cudaSuccess;
+    long long n_act = n;
+    const int32_t *act = nullptr;
+    int done = 0;
+    for (size_t si = 0; si < stages.size() && le == cudaSuccess && n_act > 0; ++si) {
+        kin::IkArgs st = a;
+        st.n = n_act; st.idx = act; st.iters = stages[si]; st.it0 = done;
+        if (si > 0) st.q0 = c->q_out;                      // restart from the best point of the previous stage
+        le = launch_stage(st);
+        done += stages[si];
+        if (le != cudaSuccess || si + 1 == stages.size()) break;
+        int32_t *next = lists[si & 1];
+        le = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream);
+        if (le == cudaSuccess) {
+            kin::ik_compact_kernel<<<(unsigned)((n_act + 255) / 256), 256, 0, stream>>>(n_act, act, (const double *)c->f_out, c->ftol, next, d_count);
+            le = cudaGetLastError();
+            g_launches.fetch_add(1);
+        }
+        unsigned long long cnt = 0;
+        if (le == cudaSuccess) le = cudaMemcpyAsync(&cnt, d_count, sizeof cnt, cudaMemcpyDeviceToHost, stream);
+        if (le == cudaSuccess) le = cudaStreamSynchronize(stream);
+        act = next; n_act = (long long)cnt;
+    }
+    cudaFreeAsync(ws, stream);
+    if (le != cudaSuccess) return fail_cuda(le, "staged kin_ik_solve");
     return KIN_OK;
 }
 

@@ -446,11 +446,16 @@ struct IkArgs {
     void *q_out;                 // [n][n_dof]
     void *f_out;                 // [n] pose objective at q_out
     int32_t *iters_out;          // [n] iterations used, or null
-    long long n;
+    long long n;                 // launch width (length of idx when it is set)
     int iters;
     double ftol, lambda0;
     double lo[32], hi[32];       // joint limits per column (+-inf allowed)
+    // staged solve (kin_ik_solve splits a long solve into a few launches over the still-running problems):
+    const int32_t *idx;          // list position -> problem (null: identity); every array above is indexed by problem
+    double *lam_io;              // [n problems] damping carried from stage to stage (null: lambda0, nothing stored)
+    int it0;                     // iterations done by earlier stages (0: first stage, the damping starts at lambda0)
 };
+
 
 // Explicitly rounded single operations (never contracted into an FMA by the compiler): the generated kernels emit
 // every multiplication / addition through these, so that their results are bit-for-bit the ones of the hand-written

@@ -227,8 +227,9 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
 extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_ik_kernel(const __grid_constant__ kin::IkArgs A) {
     using namespace kin;
     constexpr int BS = KBS, ND = KND, ROWS = KROWS;
-    const long long n = (long long)blockIdx.x * BS + threadIdx.x;
-    if (n >= A.n) return;
+    const long long li = (long long)blockIdx.x * BS + threadIdx.x;      // position in the active list
+    if (li >= A.n) return;
+    const long long n = A.idx ? A.idx[li] : li;                         // problem
     const real PI = real(3.14159265358979323846);
     real q[ND], qt[ND], g[ND], tg[6], H[ND][ND];
     {
@@ -243,7 +244,7 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_ik_kernel(const __g
             #pragma unroll
             for (int b = 0; b <= a; ++b) H[a][b] = real(0);
     }
-    real f = CUDART_INF, lam = (real)A.lambda0;
+    real f = CUDART_INF, lam = (A.lam_io && A.it0 > 0) ? (real)A.lam_io[n] : (real)A.lambda0;
     int it = 0;
     #pragma unroll 1
     for (;; ++it) {
@@ -356,7 +357,8 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_ik_kernel(const __g
     #pragma unroll
     for (int c = 0; c < ND; ++c) qo[c] = q[c];
     reinterpret_cast<real *>(A.f_out)[n] = f;
-    if (A.iters_out) A.iters_out[n] = it;
+    if (A.iters_out) A.iters_out[n] = A.it0 + it;
+    if (A.lam_io) A.lam_io[n] = (double)lam;
 }
 #endif
 

@@ -250,6 +250,22 @@ __global__ void __launch_bounds__(256) ik_coll_compact_kernel(const IkCollArgs A
     for (int a = 0; a < nd; ++a) q_try_out[a * A.ld + j] = q_try_in[a * A.ld + i];
 }
 
+// The same for the staged pose-only solve (kin_gen_skeleton.cuh: kin_ik_kernel, IkArgs::idx): a problem is still running
+// while its objective f is >= ftol.  Only the index list is built, the kernel reads the caller's arrays through it.
+__global__ void __launch_bounds__(256) ik_compact_kernel(long long n_act, const int32_t *__restrict__ act_in, const double *__restrict__ f,
+                                                         double ftol, int32_t *__restrict__ act_out, unsigned long long *__restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = i < n_act ? (act_in ? act_in[i] : i) : 0;
+    const bool live = i < n_act && !(f[n] < ftol);
+    const unsigned ballot = __ballot_sync(0xffffffffu, live);
+    if (!ballot) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (live) act_out[(long long)base + __popc(ballot & ((1u << lane) - 1u))] = (int32_t)n;
+}
+
 // q (SoA) -> q_out (AoS, caller's), |e|^2, iterations, and the smallest signed distance of the final configuration
 // (from a final UNtruncated distance evaluation Vfin at q)
 __global__ void __launch_bounds__(256) ik_coll_finish_kernel(const IkCollArgs A, const double *__restrict__ Vfin, int nd,

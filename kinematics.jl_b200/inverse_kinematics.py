@@ -1,5 +1,5 @@
 """The per-iteration evaluations of the reference's IK driver (inverse_kinematics.jl:38-50) on the B200 backend,
-batched over independent problems; the device-resident batched solvers built on them (pose only: one kernel launch;
+batched over independent problems; the device-resident batched solvers built on them (pose only: one kernel launch, a few staged launches over the still-running problems for large batches;
 collision constrained: one fused evaluation + one step kernel per iteration); and the reference's own single-problem
 driver with SLSQP (scipy's, the reference's SCIPY back-end; NLopt is third party and not installed)."""
 from __future__ import annotations
@@ -136,7 +136,8 @@ def inverse_kinematics_batch(m: Mechanism, link, joints, targets, q0, with_rot=T
     """Batched IK for N independent pose targets (config 4 of BASELINE.json) on the reference's objective
     f = |[p - p_t; rpy - rpy_t]|^2 (inverse_kinematics.jl:38-50), iterates clamped to the joint limits (:52-63).
 
-    Without ``sscc`` / ``sdf`` the whole solve is one kernel launch (``ik_solve_device``); ``restarts`` > 0 re-solves
+    Without ``sscc`` / ``sdf`` the whole solve is one kernel launch (``ik_solve_device``; large batches: a few stages over
+    the still-running problems, same iterates); ``restarts`` > 0 re-solves
     the problems that did not reach ``tol`` (max |pose error|, as test/test_inverse_kinematics.jl:22-23 measures it)
     from random in-limit seeds, that many times -- a local method started from one seed leaves a few per cent of the
     reachable targets in a local minimum at a joint limit.

@@ -522,3 +522,32 @@ def test_device_resident_ik_solve(with_base, monkeypatch):
     q4, f4, _ = K.ik_solve_device(m, link, joints, dev(tg), dev(q0), with_rot=False, iters=40)
     err4 = _pose_err(m, joints, link, q4, tg, with_rot=False).cpu().numpy()
     assert (err4 < 1e-3).mean() > 0.97
+
+
+def test_staged_ik_solve_is_bitwise_the_single_launch(monkeypatch):
+    """Large batches run the device-resident solve in stages over the still-running problems (kin_b200.cu: STAGES):
+    a later stage restarts from the best point and the damping of the one before and takes exactly the steps the single
+    launch would have taken, so configurations, objectives and iteration counts are identical bit for bit."""
+    m, joints, _ = scenes.product_fetch(False)
+    mo, jo, _ = scenes.oracle_fetch(False)
+    link = K.find_link(m, "gripper_link")
+    N = 40000
+    tg = _pose_targets(m, joints, link, scenes.random_configs(jo, N, False, seed=83))
+    q0 = np.tile(np.array([0.2, 0, 0, 0, 0.5, 0, 0.5, 0]), (N, 1))
+    lib = K.load_library()
+    monkeypatch.setenv("KIN_IK_STAGES", "0")
+    n0 = lib.kin_launch_count()
+    qa, fa, ia = K.ik_solve_device(m, link, joints, dev(tg), dev(q0), with_rot=True, iters=40)
+    torch.cuda.synchronize()
+    assert lib.kin_launch_count() - n0 == 1
+    for spec in (None, "3,5,7,9", "39"):
+        if spec is None:
+            monkeypatch.delenv("KIN_IK_STAGES")
+        else:
+            monkeypatch.setenv("KIN_IK_STAGES", spec)
+        n0 = lib.kin_launch_count()
+        qb, fb, ib = K.ik_solve_device(m, link, joints, dev(tg), dev(q0), with_rot=True, iters=40)
+        torch.cuda.synchronize()
+        assert lib.kin_launch_count() - n0 > 1                          # stages + compactions
+        assert torch.equal(qa, qb) and torch.equal(fa, fb) and torch.equal(ia, ib), spec
+    assert float((fa < 1e-10).double().mean()) > 0.9 and int(ia.max()) == 40

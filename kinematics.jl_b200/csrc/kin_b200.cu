@@ -376,8 +376,12 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
         o.grad_mode = o.want_grads ? c->grad_mode : -1;
         return o;
     }
-    o.block = (int)env_ll("KIN_JIT_BLOCK", (o.coll && tiled) ? 256 : 128);
-    o.min_blocks = (int)env_ll("KIN_JIT_MINB", o.coll ? (tiled ? 1 : 2) : 1);
+    //   collision, FP32:  an FP32 thread holds half the state, so twice the warps fit if the register allocation is
+    //                     bounded accordingly: 256 threads x 2 CTAs/SM (<= 128 registers, 16 warps/SM) instead of 8 warps
+    //                     at 254 registers: SoA 1.85 -> 1.61, tiled 1.48 -> 1.46 (profiles/sweep_jit_f32.py)
+    const bool f32c = o.coll && o.precision == 1;
+    o.block = (int)env_ll("KIN_JIT_BLOCK", ((o.coll && tiled) || f32c) ? 256 : 128);
+    o.min_blocks = (int)env_ll("KIN_JIT_MINB", o.coll ? ((tiled && !f32c) ? 1 : 2) : 1);
     o.grad_mode = o.want_grads ? c->grad_mode : -1;
     o.fd_cold = (int)env_ll("KIN_JIT_FD_COLD", 0);
     o.ksync = (int)env_ll("KIN_JIT_KSYNC", (o.coll && !tiled) ? 1 : 0);
@@ -1046,7 +1050,8 @@ int kin_eval_host(KinModel *m, const KinCall *c) {
         auto jobs = std::make_shared<std::vector<Job>>();
         for (const auto &kv : planT.consts) jobs->push_back({(unsigned char *)c->T_out + es * (size_t)kv.first * ldh, kv.second});
         for (const auto &kv : planJ.consts) jobs->push_back({(unsigned char *)c->J_out + es * (size_t)kv.first * ldh, kv.second});
-        const unsigned hw = std::thread::hardware_concurrency();
+        // host threads of this process's share of the machine (one process per GPU under torchrun: LOCAL_WORLD_SIZE)
+        const unsigned hw = std::max<unsigned>(2u, std::thread::hardware_concurrency() / (unsigned)std::max<long long>(1, env_ll("LOCAL_WORLD_SIZE", 1)));
         // 2 .. 4 threads keep up with the PCIe stream; more only compete with the DMA writes for host memory bandwidth
         long long nt = env_ll("KIN_HOST_FILL_THREADS", std::min<long long>(4, std::max<long long>(1, hw / 2)));
         nt = std::max<long long>(1, std::min<long long>(nt, (long long)jobs->size()));

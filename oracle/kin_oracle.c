@@ -531,6 +531,7 @@ static void sdf_gradient_analytic(Sdf *s, const double p[3], double g[3]) {
     if (b->kind == 1) {
         double nrm = sqrt(pl[0]*pl[0] + pl[1]*pl[1] + pl[2]*pl[2]);
         if (nrm > 0.0) for (int i = 0; i < 3; ++i) gl[i] = pl[i] / nrm;
+        else gl[0] = 1.0;      /* exactly at the centre the gradient is undefined: the +x axis of the primitive frame */
     } else if (b->kind == 2) {
         double rxy = sqrt(pl[0]*pl[0] + pl[1]*pl[1]);
         double q0 = rxy - b->width[0], q1 = fabs(pl[2]) - 0.5 * b->width[1];

@@ -36,6 +36,12 @@ def test_primitive_points_vs_oracle(dtype):
     sdf, so = _mixed_union()
     rng = np.random.default_rng(5)
     pts = np.array([0.75, 0.0, 0.8]) + (rng.random((6000, 3)) - 0.5) * 1.6
+    # special places: the sphere's centre (gradient undefined: both sides return the primitive's +x axis), points on
+    # the axes through it, the disc-shaped cylinder's centre, its axis inside and outside, a point off its rim
+    special = [[0.7, -0.35, 0.9], [0.7, -0.35, 1.15], [0.95, -0.35, 0.9], [0.85, -0.1, 1.25], [0.85, -0.1, 1.5], [1.3, -0.1, 1.4],
+               [0.85, -0.1, 1.27]]
+    if dtype == torch.float64:
+        pts = np.concatenate([pts, np.array(special)])
     vals, am = sdf(dev(pts, dtype), return_argmin=True)
     g_fd = sdf.gradient(dev(pts, dtype))
     g_an = sdf.gradient(dev(pts, dtype), grad_mode=K.GRAD_ANALYTIC)

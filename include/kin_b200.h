@@ -216,6 +216,11 @@ KIN_API int kin_eval_host(KinModel *model, const KinCall *call);
  * copied back over PCIe, which is what bounds this call: up to 4 host threads (KIN_HOST_FILL_THREADS) write them into
  * the caller's arrays while the device produces the rest.  The values are the ones the kernels write (up to the sign of
  * a zero).  keep_irrelevant = 1 and KIN_HOST_NO_CONST_FILL=1 opt out.
+ * Likewise the rows that hold the same variable of the generated code as an earlier row, possibly negated (rotation
+ * blocks of links joined by fixed pure-translation joints, geometric Jacobian rows 4:6 that are a column of a link
+ * rotation, ...): the first occurrence crosses PCIe, up to 6 host threads (KIN_HOST_DUP_THREADS) copy / negate it into
+ * the other rows behind each staging chunk; bit-identical by construction.  KIN_HOST_NO_DUP_COPY=1 opts out.
+ * Under torchrun (LOCAL_WORLD_SIZE ranks on one host) the thread counts are scaled to this rank's share of the cores.
  * kin_host_transfer_bytes: bytes kin_eval_host moved host -> device, device -> host, and filled on the host, since load. */
 KIN_API int kin_host_transfer_bytes(int64_t *h2d, int64_t *d2h, int64_t *host_filled);
 

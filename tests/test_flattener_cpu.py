@@ -231,3 +231,58 @@ def test_codegen_and_nvrtc_compile_without_a_gpu(tmp_path):
             assert (out / "kin_gen.cubin").stat().st_size > 10000
     finally:
         del os.environ["KIN_JIT_FORCE_PRIMS"]
+
+
+def test_constant_and_duplicate_rows_claimed_by_the_generator_hold_in_the_oracle(tmp_path):
+    """kin_eval_host does not move over PCIe the output rows the code generator declares constant (stored as a literal)
+    or equal to another row (stored from the same variable, possibly negated).  Both claims are checked here, without a
+    GPU, against the ORACLE's outputs on random configurations: a literal row must hold that value for every
+    configuration, two rows of one variable must be equal (or opposite) for every configuration."""
+    import ctypes as C
+    import re
+    import scene_fetch
+    from kinematics_jl_b200 import lib as L
+    from kinematics_jl_b200.device import make_desc
+    lib = L.lib()
+    if not lib.kin_jit_status().startswith(b"ok"):
+        pytest.skip("NVRTC not available: " + lib.kin_jit_status().decode())
+    m, joints, sscc = scene_fetch.product_fetch(False)
+    d, keep = make_desc(m, [j.id for j in joints])
+    fk = np.arange(1, 26, dtype=np.int32)
+    jac = np.array([K.find_link(m, "gripper_link").id], dtype=np.int32)
+    ip = C.POINTER(C.c_int32)
+    c = L.KinCall()
+    c.precision, c.layout, c.n, c.q = L.F64, L.SOA, 1 << 20, 1
+    c.n_fk_links, c.fk_links, c.T_out = 25, fk.ctypes.data_as(ip), 1
+    c.n_jac_links, c.jac_links, c.J_out, c.with_rot = 1, jac.ctypes.data_as(ip), 1, 1
+    c.truncation_dist = float("inf")
+    L.check(lib.kin_codegen_dump(C.byref(d), C.byref(c), 0, str(tmp_path).encode()))
+    src = (tmp_path / "kin_gen_phase1.inc").read_text()
+    stores = re.findall(r"KST_([TJ])\((\d+), ([^;]*)\);", src)
+    assert len(stores) == 348
+    mo, jo, _ = scenes.oracle_fetch(False)
+    q = scenes.random_configs(jo, 64, False, seed=5)
+    T = R.batch_fk(mo, jo, q, mo.links[:25])[:, :, :3, :]                         # (N, 25, 3, 4)
+    T = T.transpose(0, 1, 3, 2).reshape(len(q), 300)                               # 3x4 column-major per link
+    J = R.batch_jacobian(mo, jo, q, [R.find_link(mo, "gripper_link")], True)[:, 0]  # (N, 6, 8)
+    J = J.transpose(0, 2, 1).reshape(len(q), 48)                                   # column-major
+    out = {"T": T, "J": J}
+    first, n_const, n_dup = {}, 0, 0
+    for arr, k, expr in stores:
+        k, expr = int(k), expr.strip()
+        col = out[arr][:, k]
+        mlit = re.fullmatch(r"real\((-?[0-9a-fx.p+-]+)\)", expr)
+        if mlit:
+            n_const += 1
+            np.testing.assert_allclose(col, float.fromhex(mlit.group(1)) if "x" in mlit.group(1) else float(mlit.group(1)),
+                                       rtol=0, atol=1e-15, err_msg="%s row %d is not the constant %s" % (arr, k, expr))
+            continue
+        neg = expr.startswith("(-")
+        canon = expr[2:-1] if neg else expr
+        if canon in first:
+            n_dup += 1
+            np.testing.assert_allclose(col, -first[canon] if neg else first[canon], rtol=0, atol=1e-15,
+                                       err_msg="%s row %d is not %s" % (arr, k, expr))
+        elif not neg:
+            first[canon] = col
+    assert n_const == 175 and n_dup == 67          # the counts DESIGN.md / bench.py quote for Fetch with the 8 arm joints

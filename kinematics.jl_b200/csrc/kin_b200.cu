@@ -400,6 +400,10 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
         // per-configuration scratch and are not write-bound: no batching there unless asked for (KIN_JIT_QBATCH_COLL)
         long long qb = (long long)(budget / (2 * (size_t)h.n_dof * o.block * rs));
         qb = std::min<long long>(qb, 16);
+        // ... and a call that writes little per configuration (the gripper transform + its Jacobian: 480 B) is not
+        // write-bound either: plain loads, 3 CTAs/SM: 1.76 -> 1.68 ms per 2^24, tiled 1.84 -> 1.62 (sweep_jit.py fkg)
+        const size_t out_bytes = rs * ((o.want_T ? (size_t)12 * h.n_fk : 0) + (o.want_J ? (size_t)(o.with_rot ? 6 : 3) * h.n_dof * h.n_jac : 0));
+        if (out_bytes < 1024) qb = 0;
         qb = o.coll ? env_ll("KIN_JIT_QBATCH_COLL", 0) : env_ll("KIN_JIT_QBATCH", qb);
         if (qb >= 1 && (qb >= 2 || o.coll)) { o.qbatch = (int)qb; o.min_blocks = 1; }
     }

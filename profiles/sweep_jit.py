@@ -1,6 +1,7 @@
 """Launch-shape sweep of the model-specialised kernels: (block, min CTAs/SM) for the headline FK + Jacobian call and the
 fused call, SoA and tiled.  KIN_JIT_BLOCK / KIN_JIT_MINB are read when a kernel is first built and are part of its
-cache key, so one process can sweep them.   python profiles/sweep_jit.py [log2 N] [fkj|fused|all]"""
+cache key, so one process can sweep them.   python profiles/sweep_jit.py [log2 N] [fkj|fused|all|fkg|coll]
+(fkg: FK of the gripper link + its Jacobian, 544 B per configuration; coll: collision cost + gradient only, 1216 B)"""
 import ctypes as C
 import os
 import sys
@@ -64,6 +65,29 @@ def timed(c, reps=10):
     L.check(lib.kin_query_launch(dm.h, C.byref(c), C.byref(regs), C.byref(smem), C.byref(block), C.byref(grid)))
     return a.elapsed_time(b) / reps, regs.value, smem.value, block.value, grid.value
 
+
+if what in ("fkg", "coll"):
+    fkg = np.array([jac[0]], dtype=np.int32)
+    shapes = [(128, 1, 12), (128, 1, 0), (128, 2, 0), (128, 4, 0), (256, 1, 6), (256, 2, 0), (256, 3, 0), (512, 1, 3), (512, 2, 0), (256, 2, 3), (128, 4, 3)] \
+        if what == "fkg" else [(128, 2, 0), (128, 3, 0), (256, 1, 0), (160, 2, 0), (192, 2, 0), (96, 3, 0), (64, 4, 0)]
+    bytes_cfg = 544 if what == "fkg" else 1216
+    for layout, lname in ((L.SOA, "soa"), (L.TILED32, "tiled")):
+        for blk, minb, qb in shapes:
+            os.environ["KIN_JIT_BLOCK"], os.environ["KIN_JIT_MINB"], os.environ["KIN_JIT_QBATCH"] = str(blk), str(minb), str(qb)
+            c = call(layout, what == "coll")
+            if what == "fkg":
+                c.n_fk_links, c.fk_links = 1, fkg.ctypes.data_as(ip)
+            else:
+                c.n_fk_links = c.n_jac_links = 0
+                c.T_out = c.J_out = None
+            try:
+                ms, regs, smem, block, grid = timed(c)
+            except Exception as e:
+                print("%-6s %-6s block %4d minb %d qbatch %2d: %s" % (what, lname, blk, minb, qb, str(e)[:80]))
+                continue
+            print("%-6s %-6s block %4d minb %d qbatch %2d: %7.3f ms  %6.1f GB/s (%.3f of 6553.6)  regs %3d smem %6d launch block %d grid %d"
+                  % (what, lname, blk, minb, qb, ms, bytes_cfg * N / ms / 1e6, bytes_cfg * N / ms / 1e6 / 6553.6, regs, smem, block, grid), flush=True)
+    sys.exit(0)
 
 shapes_fkj = [(128, 3, 0), (256, 1, 0), (128, 1, 12), (256, 1, 6), (256, 1, 4), (256, 1, 2), (384, 1, 4), (512, 1, 3), (128, 1, 6)]
 shapes_fused = [(128, 2, 0), (256, 1, 0), (288, 1, 0), (320, 1, 0), (352, 1, 0), (160, 2, 0), (176, 2, 0)]

@@ -551,3 +551,25 @@ def test_staged_ik_solve_is_bitwise_the_single_launch(monkeypatch):
         assert lib.kin_launch_count() - n0 > 1                          # stages + compactions
         assert torch.equal(qa, qb) and torch.equal(fa, fb) and torch.equal(ia, ib), spec
     assert float((fa < 1e-10).double().mean()) > 0.9 and int(ia.max()) == 40
+
+
+def test_fridge_demo_example():
+    """examples/fridge_demo.py = the reference's fridge_demo.jl (same call sequence, Fetch with the planar base instead of
+    PR2): collision-constrained IK into the cabinet, then a 10-waypoint trajectory with margin 0.03 whose straight-line
+    initialisation passes through the cabinet wall.  The plan must keep the margin and agree with the same SLSQP driven
+    by the oracle's evaluations."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("fridge_demo", os.path.join(os.path.dirname(DATA), "examples", "fridge_demo.py"))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    res, ret, d_goal, d, d_line = demo.main()
+    assert res.success and ret.success
+    assert d_goal.min() > 0.02 - 1e-6                       # the IK's hard constraint (inverse_kinematics.jl:14-19)
+    assert d.min() > 0.03 - 1e-3 and d_line.min() < -0.05   # planned: margin kept; straight line: through the wall
+    mo, jo, so = scenes.oracle_fetch(True)
+    q_seq = ret.x.reshape(10, 11)
+    ret_o = _oracle_plan(so, jo, scenes.oracle_fridge_sdf(), q_seq[0], q_seq[-1], 10, 0.03, 1e-4)
+    assert ret_o.success
+    np.testing.assert_allclose(ret.fun, ret_o.fun, rtol=2e-3, atol=1e-5)
+    print("fridge demo: objective %.6f vs oracle-driven %.6f, iterations %d vs %d" % (ret.fun, ret_o.fun, ret.nit, ret_o.nit))

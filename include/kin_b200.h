@@ -237,6 +237,16 @@ KIN_API int kin_collision(KinModel *model, int32_t precision, int32_t layout, co
                   double truncation_dist, int32_t grad_mode, int32_t scratch_mode,
                   void *vals_out, void *grads_out, int32_t *argmin_out, void *stream);
 
+/* Per-configuration reductions of compute_coll_dists! (collision.jl:51-58; an extension -- what a sampling-based planner
+ * or a penalty method consumes instead of the S individual distances), untruncated distances d_s = sdf(c_s) - r_s:
+ *   dmin_out[N]  min_s d_s                       amin_out[N]  the sphere attaining it, 1-based, first minimum (nullable)
+ *   cost_out[N]  sum_s max(0, margin - d_s)^2    (nullable)
+ * q in `layout`; the outputs are plain [N] arrays of the call's precision (amin: int32).  The distances go through a
+ * stream-ordered temporary in chunks of 2^20 configurations and are reduced by coll_summary_kernel (AoS: one group of
+ * lanes per configuration, warp-shuffle min / argmin / sum; SoA, tiled: one thread per configuration). */
+KIN_API int kin_collision_summary(KinModel *model, int32_t precision, int32_t layout, const void *q, int64_t n, double margin,
+                                  void *dmin_out, int32_t *amin_out, void *cost_out, void *stream);
+
 /* BoxSDF / UnionSDF call and gradient! at arbitrary points (sdf.jl:34-41, 67-74, 108-119): for a
  * union of n_boxes boxes (HOST tables, same format as KinModelDesc), pts (DEVICE, N points x 3
  * components in `layout`) -> vals_out[N], grads_out (3 per point in `layout`, nullable),

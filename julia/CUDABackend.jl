@@ -342,6 +342,17 @@ function inverse_kinematics_batch(dm::DeviceMechanism, link::Link, targets::CuMa
     return q, f, its, dmin
 end
 
+# Reductions of compute_coll_dists per configuration (extension): smallest sphere distance, the sphere attaining it
+# (1-based, first minimum), hinge cost sum_s max(0, margin - d_s)^2
+function collision_summary(dm::DeviceMechanism, Q::CuMatrix{Float64}; layout::Symbol=:soa, margin::Float64=0.0)
+    N = nbatch(Q, layout)
+    dmin = CuArray{Float64}(undef, N); amin = CuArray{Cint}(undef, N); cost = CuArray{Float64}(undef, N)
+    check(ccall((:kin_collision_summary, libkin), Cint,
+        (Ptr{Cvoid}, Cint, Cint, CuPtr{Cvoid}, Int64, Cdouble, CuPtr{Cvoid}, CuPtr{Cint}, CuPtr{Cvoid}, Ptr{Cvoid}),
+        dm.handle, KIN_F64, layout_code(layout), pointer(Q), N, margin, pointer(dmin), pointer(amin), pointer(cost), cuda_stream()))
+    return dmin, amin, cost
+end
+
 # sdf(p) and gradient!(sdf, p, out) (sdf.jl:34-41, 67-74, 108-119) for a batch of points P (N, 3) [SoA] / (3, N) [AoS]
 function sdf_points(sdf::AbstractSDF, P::CuMatrix{Float64}; layout::Symbol=:soa, with_grad=false, grad_mode=KIN_GRAD_FD)
     N = nbatch(P, layout)

@@ -11,7 +11,7 @@ from .load_urdf import parse_urdf
 from .algorithm import get_jacobian, get_jacobian_, get_transform
 from .sdf import BoxSDF, CylinderSDF, SphereSDF, UnionSDF
 from .collision import (SweptSphereCollisionChecker, add_coll_links, compute_coll_dists,
-                        compute_coll_dists_and_grads)
+                        compute_coll_dists_and_grads, compute_coll_summary)
 
 from .inverse_kinematics import ik_objective, ik_solve_device, inverse_kinematics, inverse_kinematics_batch
 from .planning import (ConfigurationConstraint, EqConst, IneqConst, Objective, PoseConstraint, construct_problem,

@@ -88,3 +88,21 @@ def compute_coll_dists_and_grads(sscc, joints, sdf, truncation_dist=np.inf, grad
         return res + (out["argmin"][0].cpu().numpy(),) if return_argmin else res
     res = (out["vals"], out["grads"])
     return res + (out["argmin"],) if return_argmin else res
+
+
+def compute_coll_summary(sscc, joints, sdf, margin=0.0, dtype=None):
+    """Reductions of ``compute_coll_dists`` per configuration (extension; ``kin_collision_summary``): the smallest sphere
+    distance, the sphere that attains it (1-based, first minimum) and the hinge cost ``sum_s max(0, margin - d_s)^2``.
+    single -> (float, int, float); batch -> tensors (N,), (N,) int32, (N,)."""
+    import torch
+    m, dm = _prepare(sscc, joints, sdf)
+    Q, ql, N = current_q(m, dtype)
+    dmin = torch.empty(N, dtype=Q.dtype, device=Q.device)
+    cost = torch.empty(N, dtype=Q.dtype, device=Q.device)
+    amin = torch.empty(N, dtype=torch.int32, device=Q.device)
+    _lib.check(_lib.lib().kin_collision_summary(dm.h, _lib.F32 if Q.dtype == torch.float32 else _lib.F64, ql, Q.data_ptr(), N,
+                                                float(margin), dmin.data_ptr(), amin.data_ptr(), cost.data_ptr(),
+                                                torch.cuda.current_stream(Q.device).cuda_stream))
+    if m._single:
+        return float(dmin[0]), int(amin[0]), float(cost[0])
+    return dmin, amin, cost

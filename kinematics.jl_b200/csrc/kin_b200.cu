@@ -1506,6 +1506,65 @@ int kin_ik_solve(KinModel *m, const KinIkCall *c) {
 
 // FP64 peak probe (the denominator of the "FP64 pipe" column of the rooflines): every thread runs 8 independent
 // DFMA chains, 8 CTAs of 256 threads per SM.
+int kin_collision_summary(KinModel *m, int32_t precision, int32_t layout, const void *q, int64_t n, double margin,
+                          void *dmin_out, int32_t *amin_out, void *cost_out, void *stream_) {
+    if (!m) return fail(KIN_ERR_INVALID_ARGUMENT, "null model");
+    if (n < 0 || (n > 0 && (!q || !dmin_out))) return fail(KIN_ERR_INVALID_ARGUMENT, "null q or dmin_out");
+    if (precision != KIN_F64 && precision != KIN_F32) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown precision");
+    if (layout != KIN_LAYOUT_SOA && layout != KIN_LAYOUT_AOS && layout != KIN_LAYOUT_TILED32) return fail(KIN_ERR_INVALID_ARGUMENT, "unknown layout");
+    if (n == 0) return KIN_OK;
+    DeviceGuard guard(m->device);
+    const int S = m->hm.n_sph, nd = m->hm.n_dof();
+    if (S < 1 || m->hm.n_box < 1) return fail(KIN_ERR_INVALID_ARGUMENT, "collision summary: the model has no spheres / no boxes");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t es = precision == KIN_F32 ? 4 : 8;
+    // the distances of a chunk go through a stream-ordered temporary (S values per configuration), then the reduction
+    const long long chunk = std::min<long long>(n, env_ll("KIN_SUMMARY_CHUNK", 1 << 20));     // a multiple of 32
+    void *tmp = nullptr;
+    CUDA_TRY(cudaMallocFromPoolAsync(&tmp, es * (size_t)S * (size_t)((chunk + 31) / 32 * 32), m->pool, stream));
+    int rc = KIN_OK;
+    for (long long n0 = 0; n0 < n && rc == KIN_OK; n0 += chunk) {
+        const long long cnt = std::min<long long>(chunk, n - n0);
+        KinCall c;
+        std::memset(&c, 0, sizeof c);
+        c.precision = precision; c.layout = layout; c.n = cnt; c.stream = stream_;
+        c.truncation_dist = INFINITY; c.vals_out = tmp;
+        // AoS / tiled: a chunk is a contiguous part of q (chunk starts are multiples of 32).  SoA: q and the outputs of
+        // one call share one row stride, so a chunk of a longer batch gets its q rows gathered into a [n_dof][cnt] block
+        c.q = (const unsigned char *)q + es * (size_t)n0 * nd;
+        void *qtmp = nullptr;
+        if (layout == KIN_LAYOUT_SOA) {
+            c.q = q;
+            if (cnt != n) {
+                cudaError_t e = cudaMallocFromPoolAsync(&qtmp, es * (size_t)nd * (size_t)cnt, m->pool, stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpy2DAsync(qtmp, es * cnt, (const unsigned char *)q + es * (size_t)n0, es * (size_t)n, es * cnt, nd,
+                                          cudaMemcpyDeviceToDevice, stream);
+                if (e != cudaSuccess) { if (qtmp) cudaFreeAsync(qtmp, stream); rc = fail_cuda(e, "staging a SoA chunk"); break; }
+                c.q = qtmp;
+            }
+        }
+        rc = kin_eval(m, &c);
+        if (qtmp) cudaFreeAsync(qtmp, stream);
+        if (rc != KIN_OK) break;
+        const long long ld = cnt;                                  // row stride of the temporary (SoA)
+        const bool aos = layout == KIN_LAYOUT_AOS;
+        long long grid = aos ? (cnt * 32 + 255) / 256 : (cnt + 255) / 256;
+        grid = std::max<long long>(1, std::min<long long>(grid, (long long)m->n_sm * 16));
+        unsigned char *dm = (unsigned char *)dmin_out + es * (size_t)n0, *co = cost_out ? (unsigned char *)cost_out + es * (size_t)n0 : nullptr;
+        int32_t *am = amin_out ? amin_out + n0 : nullptr;
+#define KIN_SUMMARY(real, lay) kin::coll_summary_kernel<real, lay><<<(unsigned)grid, 256, 0, stream>>>((const real *)tmp, cnt, ld, S, (real)margin, (real *)dm, am, (real *)co)
+        if (precision == KIN_F64) { if (layout == KIN_LAYOUT_SOA) KIN_SUMMARY(double, 0); else if (aos) KIN_SUMMARY(double, 1); else KIN_SUMMARY(double, 2); }
+        else { if (layout == KIN_LAYOUT_SOA) KIN_SUMMARY(float, 0); else if (aos) KIN_SUMMARY(float, 1); else KIN_SUMMARY(float, 2); }
+#undef KIN_SUMMARY
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) { rc = fail_cuda(le, "launching coll_summary_kernel"); break; }
+        g_launches.fetch_add(1);
+    }
+    cudaFreeAsync(tmp, stream);
+    return rc;
+}
+
 }  // extern "C"
 namespace {
 __global__ void __launch_bounds__(256) probe_dfma_kernel(double *out, int iters) {

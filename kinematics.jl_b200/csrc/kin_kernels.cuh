@@ -534,6 +534,64 @@ sdf_points_kernel(const real *__restrict__ boxes, int n_box, const real *__restr
     }
 }
 
+// Per-configuration reductions over the S sphere distances of a collision call (kin_collision_summary): the minimum
+// distance, the sphere that attains it (first minimum, 1-based) and the hinge cost sum_s max(0, margin - d_s)^2.
+//   SoA / tiled: one thread per configuration walks its S values (coalesced across the threads);
+//   AoS: the S values of a configuration are contiguous, so a group of G = 2^k >= min(S, 32) lanes takes one
+//        configuration (lane = sphere) and the group reduces with warp shuffles: min / argmin by a butterfly on
+//        (value, index) pairs, the cost by a butterfly sum.
+template <typename real, int LAY>
+__global__ void __launch_bounds__(256)
+coll_summary_kernel(const real *__restrict__ vals, long long n, long long ld, int S, real margin, real *__restrict__ dmin,
+                    int32_t *__restrict__ amin, real *__restrict__ cost) {
+    if (LAY != 1) {
+        for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+            const real *v = vals + (LAY == 2 ? (c >> 5) * ((long long)S * 32) + (c & 31) : c);
+            const long long es = LAY == 2 ? 32 : ld;
+            real best = CUDART_INF, sum = real(0);
+            int bi = 0;
+            for (int s = 0; s < S; ++s) {
+                const real d = v[s * es];
+                if (d < best) { best = d; bi = s; }
+                const real h = margin - d;
+                if (h > real(0)) sum = fma_(h, h, sum);
+            }
+            dmin[c] = best;
+            if (amin) amin[c] = bi + 1;
+            if (cost) cost[c] = sum;
+        }
+        return;
+    }
+    int G = 1;
+    while (G < S && G < 32) G <<= 1;
+    const int lane = threadIdx.x & 31, lg = lane & (G - 1), per_warp = 32 / G;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long c0 = warp * per_warp; c0 < n; c0 += n_warps * per_warp) {     // warp-uniform trip count
+        const long long c = c0 + lane / G;
+        real best = CUDART_INF, sum = real(0);
+        int bi = 0x7fffffff;
+        if (c < n)
+            for (int s = lg; s < S; s += G) {
+                const real d = vals[c * S + s];
+                if (d < best) { best = d; bi = s; }
+                const real h = margin - d;
+                if (h > real(0)) sum = fma_(h, h, sum);
+            }
+        for (int off = G >> 1; off > 0; off >>= 1) {
+            const real ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            const real os = __shfl_xor_sync(0xffffffffu, sum, off);
+            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }   // first minimum wins, as in the serial walk
+            sum += os;
+        }
+        if (c < n && lg == 0) {
+            dmin[c] = best;
+            if (amin) amin[c] = bi + 1;
+            if (cost) cost[c] = sum;
+        }
+    }
+}
+
 // Pose residuals / IK objective from the link transforms T (12 per link per configuration) and their Euler-rate
 // Jacobians J (rows_j x n_dof per link), both produced by kin_eval_kernel in the same layout, for ALL the
 // (link, target, with_rot) triples of a constraint in one launch (the loop of planning.jl:124-137).

@@ -62,7 +62,7 @@ class KinIkCall(C.Structure):
 ERR_UNAVAILABLE = -6
 
 EXPORTS = ["kin_last_error", "kin_abi_version", "kin_build_id", "kin_debug_build", "kin_model_create", "kin_model_destroy", "kin_model_set_spheres",
-           "kin_model_set_boxes", "kin_model_set_primitives", "kin_sdf_points_prims", "kin_model_n_dof", "kin_model_n_spheres", "kin_model_n_boxes", "kin_eval",
+           "kin_model_set_boxes", "kin_model_set_primitives", "kin_sdf_points_prims", "kin_collision_summary", "kin_model_n_dof", "kin_model_n_spheres", "kin_model_n_boxes", "kin_eval",
            "kin_eval_host", "kin_fk_links", "kin_fk_jacobian", "kin_collision", "kin_launch_count",
            "kin_query_launch", "kin_sdf_points", "kin_program_dump", "kin_pose_residual", "kin_pose_residual_multi", "kin_probe_fp64",
            "kin_jit_status", "kin_jit_stats", "kin_codegen_dump", "kin_ik_solve", "kin_host_transfer_bytes"]
@@ -204,6 +204,8 @@ def lib():
         L.kin_query_launch.argtypes = [C.c_void_p, C.POINTER(KinCall), _ip, _ip, _ip, _ip]
         L.kin_sdf_points.argtypes = [C.c_int32, _dp, _dp, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kin_collision_summary.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_double, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
         L.kin_pose_residual.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.kin_pose_residual_multi.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, _ip, _ip,

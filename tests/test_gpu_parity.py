@@ -937,3 +937,45 @@ def test_edge_cases_and_errors():
         evaluate(device_model(m2), *current_q(m2), collision=True)
     with pytest.raises(ValueError):                               # joints must be the ones of set_joint_angles
         K.get_jacobian(m, K.find_link(m, "gripper_link"), joints[:3], True)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-configuration reductions of the sphere distances (kin_collision_summary, extension)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 777, (1 << 20) + 77])          # the last one spans two chunks of the temporary
+def test_collision_summary_reductions(n, monkeypatch):
+    from kinematics_jl_b200.device import tile32
+    m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
+    q = scenes.random_configs(jo, n, False, seed=91, zeros_every=50)
+    Q = dev(q)
+    margin = 0.1
+    K.set_joint_angles(m, joints, Q)                               # AoS: groups of lanes + warp shuffles
+    d_all = K.compute_coll_dists(sscc, joints, sdf)
+    dmin_a, amin_a, cost_a = K.compute_coll_summary(sscc, joints, sdf, margin=margin)
+    K.set_joint_angles(m, joints, soa(Q))                          # SoA: one thread per configuration
+    dmin_s, amin_s, cost_s = K.compute_coll_summary(sscc, joints, sdf, margin=margin)
+    ref_min, ref_arg = d_all.min(dim=1)
+    ref_cost = torch.clamp(margin - d_all, min=0).pow(2).sum(dim=1)
+    for dmin, amin, cost in ((dmin_a, amin_a, cost_a), (dmin_s, amin_s, cost_s)):
+        assert torch.equal(dmin, ref_min)                          # a minimum is exact whatever the order
+        first = (d_all == ref_min[:, None]).int().argmax(dim=1)    # first minimum, as the serial walk
+        assert torch.equal(amin.long(), first + 1)
+        np.testing.assert_allclose(host(cost), host(ref_cost), rtol=1e-13, atol=1e-15)
+    if n > 1:
+        assert float(cost_a.max()) > 0 and bool((cost_a == 0).any())      # both branches of the hinge
+    # tiled layout through the C ABI
+    dm_ = device_model(m)
+    Qt = tile32(Q)
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    am = torch.empty(n, dtype=torch.int32, device="cuda")
+    co = torch.empty(n, dtype=torch.float64, device="cuda")
+    L.check(L.lib().kin_collision_summary(dm_.h, L.F64, L.TILED32, Qt.data_ptr(), n, margin, out.data_ptr(), am.data_ptr(), co.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_min) and torch.equal(am, amin_s) and torch.equal(co, cost_s)
+    # against the oracle
+    sub = slice(0, min(n, 400))
+    v_ref, _, _ = R.batch_collision(so, jo, sdf_o, q[sub], with_grads=False)
+    np.testing.assert_allclose(host(dmin_a[sub]), v_ref.min(axis=1), rtol=RTOL, atol=ATOL)
+    assert np.array_equal(amin_a[sub].cpu().numpy(), v_ref.argmin(axis=1) + 1)
+    np.testing.assert_allclose(host(cost_a[sub]), (np.clip(margin - v_ref, 0, None) ** 2).sum(axis=1), rtol=1e-11, atol=1e-13)

@@ -387,6 +387,10 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
     o.ksync = (int)env_ll("KIN_JIT_KSYNC", (o.coll && !tiled) ? 1 : 0);
     o.es32 = (o.layout == KIN_LAYOUT_SOA && (c->batch_stride ? c->batch_stride : c->n) < (1ll << 32)) ? (int)env_ll("KIN_JIT_ES32", 1) : 0;
     if (o.layout == KIN_LAYOUT_AOS) o.keep_irrelevant = 0;     // (calls with keep_irrelevant never get here: jit_wanted)
+    // tiled FK / Jacobian-only kernels: outputs staged per warp and written by the TMA engine (cp.async.bulk; kin_gen_skeleton.cuh)
+    // 2^24 configurations, FK-all + Jacobian: 7.67 -> 7.61 ms (0.950 -> 0.959 of the HBM peak), 8.36 -> 8.05 without the input
+    // batching (profiles/sweep_bulk.py): the write path, not the store instructions, bounds the kernel -- a small gain
+    o.bulk = (tiled && !o.coll && !o.keep_irrelevant && (o.want_T || o.want_J)) ? (int)env_ll("KIN_JIT_BULK", 1) : 0;
     o.qbatch = 0;
     // input batching (kin_gen_skeleton.cuh): the FK / Jacobian-only kernels are bound by the DRAM write path and use
     // no other shared memory, so the configurations of as many tiles as fit twice in ~200 KB are fetched per batch
@@ -395,6 +399,7 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
         const size_t rs = o.precision ? sizeof(float) : sizeof(double);
         size_t budget = std::min<size_t>((size_t)(m ? m->dev_smem : 227 * 1024), 200 * 1024);
         if (o.layout == KIN_LAYOUT_AOS) budget -= std::min<size_t>(budget, 24 * 1024);     // room for the output stages
+        if (o.bulk) budget -= std::min<size_t>(budget, (size_t)o.block * 24 * rs);         // two [12][32] stages per warp
         // measured (profiles/sweep_jit.py, 2^24 configurations): 128 threads x 12 tiles per batch, one CTA per SM:
         // 8.72 -> 7.78 ms (0.84 -> 0.94 of the HBM peak); the collision kernels need their shared memory for the
         // per-configuration scratch and are not write-bound: no batching there unless asked for (KIN_JIT_QBATCH_COLL)
@@ -457,6 +462,7 @@ size_t jit_smem(const kin::GenOptions &o, const kin::ProgHeader &h, const JitKer
     if (o.coll) reals += (((size_t)h.n_box * kin::BOX_REALS + h.n_sph + 1) & ~size_t(1)) + (size_t)k.slots * k.block;
     if (o.layout == KIN_LAYOUT_AOS)      // the warps' output stages (AOS_STAGE_ROWS x 33 per warp)
         reals += (size_t)(k.block / 32) * (34 * std::max(12, (int)h.n_dof) + (o.coll ? 2 * 36 * kin::SPH_GROUP : 0));   // AOS_STAGE_REALS
+    if (o.bulk && o.layout == KIN_LAYOUT_TILED32) reals += (size_t)k.block * 24;     // (block / 32) warps x 2 stages x 12 x 32
     if (o.qbatch > 0) reals += (size_t)2 * o.qbatch * h.n_dof * k.block;
     return rs * reals;
 }

@@ -11,9 +11,9 @@ namespace kin {
 
 std::string GenOptions::key() const {
     char b[192];
-    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d I%d W%d P%d", precision, layout, (int)want_T, (int)want_J,
+    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d I%d W%d P%d B%d", precision, layout, (int)want_T, (int)want_J,
                   (int)coll, with_rot, rpy_jac, keep_irrelevant, (int)want_grads, (int)want_argmin, (int)stale, (int)ws, block, min_blocks, qbatch,
-                  ksync, es32, grad_mode, fd_cold, ik, warp, prims);
+                  ksync, es32, grad_mode, fd_cold, ik, warp, prims, bulk);
     return b;
 }
 
@@ -139,9 +139,10 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
     // AoS, one thread per configuration: the outputs of a warp are staged through shared memory in chunks of at most
     // AOS_CHUNK values per record (KPUT into a stage row, KFLUSH_* writes 32 records x chunk with the lanes running
     // along the records: whole sectors); get_jacobian! semantics (columns left untouched) cannot be staged
-    const bool aos = o.layout == 1 && !o.warp && !o.ik;
+    // (the tiled layout with bulk stores, GenOptions::bulk, stages the same chunks: a chunk of a tile is one contiguous block)
+    const bool aos = (o.layout == 1 || (o.layout == 2 && o.bulk)) && !o.warp && !o.ik;
     if (aos && o.want_J && o.keep_irrelevant) {
-        err = "AoS with keep_irrelevant is not specialised";
+        err = "staged outputs with keep_irrelevant are not specialised";
         return false;
     }
     constexpr int AOS_CHUNK = 12;
@@ -403,7 +404,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
     std::ostringstream c;
     c << "#define KREAL " << (f32 ? "float" : "double") << "\n";
     if (o.fd_cold) c << "#define KIN_FD_COLD 1\n";
-    c << "#define KPRIMS " << o.prims << "\n";
+    c << "#define KPRIMS " << o.prims << "\n#define KBULK " << ((o.bulk && o.layout == 2 && !o.warp && !o.ik) ? 1 : 0) << "\n";
     c << "#define KWANT_T " << (o.want_T ? 1 : 0) << "\n#define KWANT_J " << (o.want_J ? 1 : 0) << "\n#define KCOLL " << (o.coll ? 1 : 0)
       << "\n#define KTILED " << (o.layout == 2 ? 1 : 0) << "\n#define KAOS " << (o.layout == 1 ? 1 : 0) << "\n#define KWS " << (o.ws ? 1 : 0) << "\n";
     c << "#define KBS " << o.block << "\n#define KMINB " << o.min_blocks << "\n#define KWARP " << o.warp << "\n#define KIK " << o.ik << "\n#define KQB " << o.qbatch << "\n#define KSYNC_ON "

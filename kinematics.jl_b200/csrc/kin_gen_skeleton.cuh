@@ -503,10 +503,34 @@ __device__ __forceinline__ void kin_grid_barrier(unsigned *sync, unsigned n_cta)
 }
 #endif
 
+#if KBULK
+// ---- tiled layout, FK / Jacobian-only kernels: outputs leave through the TMA engine.  In the tiled layout the
+//      components of one tile are contiguous (256 B per component for doubles), so a chunk of cnt <= 12 components of a
+//      warp's 32 configurations is ONE contiguous cnt x 256 B block: every lane PUTs its values into a [12][32] stage of
+//      its warp and lane 0 hands the block to cp.async.bulk (SASS: UBLKCP) -- 29 bulk stores per tile instead of 348
+//      STG per thread.  Two stage buffers per warp: a buffer is refilled only after the bulk group issued from it one
+//      flush earlier has been read (wait_group.read 1). ----
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+template <typename real_>
+__device__ __forceinline__ void bulk_flush(real_ *gdst, real_ *&b0, real_ *&b1, const int cnt, const bool active, const int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this lane's stage writes -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0) {                                                  // (lane 0's column pointer is the buffer's base)
+        if (active) bulk_store(gdst, b0, (unsigned)(cnt * 32 * sizeof(real_)));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");      // an empty group when inactive keeps the count uniform
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the OTHER buffer's group has been read
+    }
+    real_ *t = b0; b0 = b1; b1 = t;
+    __syncwarp();
+}
+#endif
+
 extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __grid_constant__ kin::GenArgs A) {
     using namespace kin;
     constexpr int BS = KBS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     real *smem_next = reinterpret_cast<real *>(smem_raw);
 #if KCOLL
@@ -533,6 +557,11 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
     real *stw = smem_next + (tid >> 5) * AOS_STAGE_REALS;   // this warp's output stage
     real *stg = stw + lane;
     smem_next += (BS / 32) * AOS_STAGE_REALS;
+#endif
+#if KBULK
+    const int lane = tid & 31;
+    real *bst0 = smem_next + (tid >> 5) * (2 * 12 * 32) + lane, *bst1 = bst0 + 12 * 32;     // this lane's column of the warp's two stages
+    smem_next += (BS / 32) * (2 * 12 * 32);
 #endif
 #if KES32 && !KTILED && !KAOS
     // the component stride as a 32-bit value: address = base + es32 * (8 k) is ONE 32 x 32 -> 64-bit multiply-add per
@@ -620,6 +649,20 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
             real *Jw = reinterpret_cast<real *>(A.J_out) + KREC_BASE(KROWS * KND * KNJAC);
             #define KFLUSH_J(off, cnt) aos_flush<real, cnt, KROWS * KND * KNJAC>(stw, Jw + (off), nvalid, lane)
 #endif
+#elif KBULK
+            // tiled + bulk stores: the warp's tile is written chunk by chunk from the stage (bulk_flush)
+            const long long n_w0 = tile * BS + (tid & ~31);
+            const bool w_active = n_w0 < (long long)A.n;
+            #define KREC_BASE(rec) ((n_w0 >> 5) * ((long long)(rec) * 32))
+            #define KPUT(cnt, i, v) bst0[(i) * 32] = (v)
+#if KWANT_T
+            real *Tw = reinterpret_cast<real *>(A.T_out) + KREC_BASE(12 * KNFK);
+            #define KFLUSH_T(off, cnt) bulk_flush<real>(Tw + (off) * 32, bst0, bst1, cnt, w_active, lane)
+#endif
+#if KWANT_J
+            real *Jw = reinterpret_cast<real *>(A.J_out) + KREC_BASE(KROWS * KND * KNJAC);
+            #define KFLUSH_J(off, cnt) bulk_flush<real>(Jw + (off) * 32, bst0, bst1, cnt, w_active, lane)
+#endif
 #else
             #define KREC_BASE(rec) (KTILED ? (n >> 5) * ((long long)(rec) * 32) + (n & 31) : n)
 #if KWANT_T
@@ -669,6 +712,9 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
             for (int c = 0; c < KND; ++c) qcur[c] = qnxt[c];
         }
     }
+#endif
+#if KBULK
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every bulk store of this warp has completed
 #endif
 }
 #endif

@@ -40,9 +40,12 @@
  *   - a KinModel is immutable after creation except through kin_model_set_boxes /
  *     kin_model_set_spheres (which must not race with launches that use the model); concurrent
  *     kin_eval calls on different streams are allowed.  One model per device.
- *   - large FP64 SoA / tiled collision launches run the warp-specialised kernel (csrc/kin_kernels_ws.cuh),
- *     which takes ~28 MB of temporary device scratch per launch from a model-private stream-ordered pool
- *     (allocated and freed on `stream`); results are bitwise identical to the single-kernel path.
+ *   - which kernel runs is the library's business and never changes a result bit: batches of >= 32768 configurations
+ *     (and small batches that keep coming) run kernels generated for the model and compiled with NVRTC on first use
+ *     (see kin_jit_status below); without NVRTC large FP64 SoA / tiled collision launches run the warp-specialised
+ *     kernel (csrc/kin_kernels_ws.cuh), which takes ~28 MB of temporary device scratch per launch from a model-private
+ *     stream-ordered pool (allocated and freed on `stream`); everything else runs the interpreting kernel.
+ *   - KIN_LAYOUT_TILED32 buffers hold WHOLE tiles: the kernels may write the padding slots of the last tile.
  */
 #ifndef KIN_B200_H
 #define KIN_B200_H

@@ -1525,7 +1525,8 @@ int kin_collision_summary(KinModel *m, int32_t precision, int32_t layout, const 
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t es = precision == KIN_F32 ? 4 : 8;
     // the distances of a chunk go through a stream-ordered temporary (S values per configuration), then the reduction
-    const long long chunk = std::min<long long>(n, env_ll("KIN_SUMMARY_CHUNK", 1 << 20));     // a multiple of 32
+    long long chunk = std::max<long long>(32, env_ll("KIN_SUMMARY_CHUNK", 1 << 20)) / 32 * 32;      // a multiple of 32 (tiled: whole tiles)
+    if (chunk > n) chunk = n;
     void *tmp = nullptr;
     CUDA_TRY(cudaMallocFromPoolAsync(&tmp, es * (size_t)S * (size_t)((chunk + 31) / 32 * 32), m->pool, stream));
     int rc = KIN_OK;

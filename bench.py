@@ -457,7 +457,7 @@ def main():
     small = {}
     if not args.no_variants:
         small["note"] = "fused kin_eval (FK all links + gripper Jacobian + collision cost / gradient) of n configurations; after a few small " \
-                        "calls the library switches to its one-warp-per-configuration specialised kernel (negative block size)"
+                        "calls the library switches to the specialised kernel of this program (negative block size)"
         ld_s = 1024
         Qs_ = Q[:, :ld_s].contiguous()
         Ts_ = torch.empty((N_LINKS * 12, ld_s), dtype=torch.float64, device=dev)

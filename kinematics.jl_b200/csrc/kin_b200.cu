@@ -337,12 +337,25 @@ int validate_call(const KinModel *m, const KinCall *c) {
 
 // ---- model-specialised kernels (kin_codegen.hpp / kin_jit.hpp) ----
 constexpr long long kJitMinBatch = 32 * 1024;      // below this the compile is not worth it: interpreting kernels ...
-constexpr long long kWarpMaxBatch = 2048;          // ... except for SMALL batches that keep coming (a solver loop): after
-constexpr int kSmallCallsBeforeJit = 4;            // this many calls the one-warp-per-configuration kernel is built
+constexpr long long kWarpMaxBatch = 2048;          // ... except for smaller batches that keep coming (a solver loop): after
+constexpr int kSmallCallsBeforeJit = 4;            // this many calls of the same program its specialised kernel is built
+constexpr long long kQbatchMinBatch = 1 << 18;     // input batching (grid-wide barriers) only pays for long launches
 
 long long env_ll(const char *name, long long dflt) {
     const char *e = std::getenv(name);
     return e && *e ? std::atoll(e) : dflt;
+}
+
+// Which specialised kernel serves a batch below the large-batch threshold?  Measured (profiles/sweep_midsize.py, fused call,
+// device time per launch): one THREAD per configuration 18.7 us at n = 1, 22.7 us at n = 1024 .. 4096, 24.8 us at 16384 --
+// one WARP per configuration 31.0 / 32.9 / 96 us -- interpreting kernel 37 / 39 / 40 us.  So the thread-per-configuration
+// kernel is the default at every size; the warp-per-configuration kernel is kept for what the other cannot do
+// (get_jacobian! semantics -- columns left untouched -- in the AoS layout) and behind KIN_JIT_WARP_MAX.
+bool use_warp_kernel(const KinCall *c, const kin::ProgHeader &h) {
+    if (c->vals_out && h.n_sph > 32) return false;
+    const long long wm = env_ll("KIN_JIT_WARP_MAX", -1);
+    if (wm >= 0) return c->n <= wm;
+    return c->n <= kWarpMaxBatch && c->layout == KIN_LAYOUT_AOS && c->J_out && c->keep_irrelevant;
 }
 
 kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DeviceProgram *dp) {
@@ -370,7 +383,7 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
     //   FK / Jacobian only: 128 threads x 1 CTA/SM + input batching (below)
     const bool tiled = c->layout == KIN_LAYOUT_TILED32;
     // small batches: one warp per configuration (kin_gen_skeleton.cuh, KWARP)
-    o.warp = (c->n <= env_ll("KIN_JIT_WARP_MAX", kWarpMaxBatch) && (!o.coll || h.n_sph <= 32)) ? 1 : 0;
+    o.warp = use_warp_kernel(c, h) ? 1 : 0;
     if (o.warp) {
         o.block = 128; o.min_blocks = 1; o.qbatch = 0; o.ksync = 0; o.es32 = 0; o.fd_cold = 0;
         o.grad_mode = o.want_grads ? c->grad_mode : -1;
@@ -409,6 +422,10 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
         // write-bound either: plain loads, 3 CTAs/SM: 1.76 -> 1.68 ms per 2^24, tiled 1.84 -> 1.62 (sweep_jit.py fkg)
         const size_t out_bytes = rs * ((o.want_T ? (size_t)12 * h.n_fk : 0) + (o.want_J ? (size_t)(o.with_rot ? 6 : 3) * h.n_dof * h.n_jac : 0));
         if (out_bytes < 1024) qb = 0;
+        // ... nor is a short launch: the grid-wide barriers cost more than they save below 2^18 configurations
+        // (profiles/sweep_qbatch_min.py, fk + jac: 2^16: 42.7 us with / 36.8 without; 2^17: 70.2 / 68.5; 2^18: 130.7 / 134.3;
+        // 2^20: 486 / 541; 2^23: 3843 / 4413)
+        if (c->n < env_ll("KIN_JIT_QBATCH_MIN_N", kQbatchMinBatch)) qb = 0;
         qb = o.coll ? env_ll("KIN_JIT_QBATCH_COLL", 0) : env_ll("KIN_JIT_QBATCH", qb);
         if (qb >= 1 && (qb >= 2 || o.coll)) { o.qbatch = (int)qb; o.min_blocks = 1; }
     }
@@ -418,15 +435,15 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
 bool jit_wanted(const KinModel *m, const KinCall *c, const DeviceProgram *dp, bool count = true) {
     (void)m;
     if (std::getenv("KIN_DISABLE_JIT")) return false;
-    const bool small = c->n <= env_ll("KIN_JIT_WARP_MAX", kWarpMaxBatch) && (!c->vals_out || dp->prog.h.n_sph <= 32);
+    const bool small = use_warp_kernel(c, dp->prog.h);
     // large AoS batches: outputs staged through shared memory (kin_gen_skeleton.cuh: aos_flush); get_jacobian!
     // semantics (columns left untouched) cannot be staged and stay with the interpreting kernel
     if (c->layout == KIN_LAYOUT_AOS && !small && c->J_out && c->keep_irrelevant) return false;
     if (c->vals_out && dp->prog.h.n_sph > 0 && dp->prog.h.n_dof > 16) return false;     // frames would not fit in registers
     if (c->n < env_ll("KIN_JIT_MIN_BATCH", kJitMinBatch) && !std::getenv("KIN_FORCE_JIT")) {
-        // a small batch: worth a specialised (one warp per configuration) kernel once the same program keeps being
-        // called, as a solver callback does
-        if (c->n > env_ll("KIN_JIT_WARP_MAX", kWarpMaxBatch) || std::getenv("KIN_JIT_NO_SMALL")) return false;
+        // a batch too small to be worth a compile on its own: specialise once the same program keeps being called, as a
+        // solver callback (one configuration, n_wp waypoints, the active list of the batched IK) does
+        if (std::getenv("KIN_JIT_NO_SMALL")) return false;
         std::atomic<int> &calls = const_cast<DeviceProgram *>(dp)->small_calls;
         return (count ? calls.fetch_add(1) + 1 : calls.load()) >= kSmallCallsBeforeJit;
     }

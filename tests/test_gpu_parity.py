@@ -477,11 +477,14 @@ def test_stale_scratch_differs_from_clean_as_in_the_reference():
 # ------------------------------------------------------------------------------------------------
 # model-specialised (NVRTC) kernels: bit-identical to the interpreting kernels, and checked against the oracle
 # ------------------------------------------------------------------------------------------------
-def _eval_all(m, joints, sscc, sdf, Q, layout, jit, monkeypatch, **kw):
+def _eval_all(m, joints, sscc, sdf, Q, layout, jit, monkeypatch, warp_max=None, **kw):
     from kinematics_jl_b200.device import current_q, evaluate
     monkeypatch.delenv("KIN_DISABLE_JIT", raising=False)
     monkeypatch.delenv("KIN_FORCE_JIT", raising=False)
+    monkeypatch.delenv("KIN_JIT_WARP_MAX", raising=False)
     monkeypatch.setenv("KIN_FORCE_JIT" if jit else "KIN_DISABLE_JIT", "1")
+    if warp_max is not None:                  # batches up to this size: the one-warp-per-configuration kernel
+        monkeypatch.setenv("KIN_JIT_WARP_MAX", str(warp_max))
     K.set_joint_angles(m, joints, Q)
     if sscc is not None:
         K.compute_coll_dists(sscc, joints, sdf)
@@ -515,6 +518,11 @@ def test_specialised_kernel_is_bitwise_identical(layout, n, with_base, monkeypat
         assert b["launch"]["block"] < 0, lib.kin_jit_status()          # negative block size = specialised kernel
         for key in ("T", "J", "vals", "grads", "argmin"):
             assert torch.equal(a[key], b[key]), (key, kw)
+        if n <= 2048:     # ... and the one-warp-per-configuration variant (not the default at any size, KIN_JIT_WARP_MAX)
+            w = _eval_all(m, joints, sscc, sdf, Q, layout, True, monkeypatch, warp_max=2048, **kw)
+            assert w["launch"]["block"] < 0 and w["launch"]["grid"] == (n + 3) // 4      # 4 warps = 4 configurations per CTA
+            for key in ("T", "J", "vals", "grads", "argmin"):
+                assert torch.equal(a[key], w[key]), (key, kw)
     # FK / Jacobian only (no collision): the straight-line kernel without any shared memory
     a = _eval_all(m, joints, None, None, Q, layout, False, monkeypatch, with_rot=True, rpy_jac=True)
     b = _eval_all(m, joints, None, None, Q, layout, True, monkeypatch, with_rot=True, rpy_jac=True)
@@ -530,12 +538,17 @@ def test_specialised_kernel_is_bitwise_identical(layout, n, with_base, monkeypat
     assert failures.value == 0 and launches.value > 0
 
 
-def test_small_batches_switch_to_the_warp_per_configuration_kernel(monkeypatch):
+@pytest.mark.parametrize("warp_max", [None, 2048])
+def test_small_batches_switch_to_the_warp_per_configuration_kernel(warp_max, monkeypatch):
     """A solver callback evaluates one configuration (IK) or n_wp of them (planning) over and over: after a few small
-    calls of the same program the library builds the one-warp-per-configuration kernel for it; results stay bit-identical
-    across the switch and match the oracle."""
+    calls of the same program the library builds a specialised kernel for it (one thread per configuration -- the faster
+    one at every size, profiles/sweep_midsize.py -- or, with KIN_JIT_WARP_MAX, one warp per configuration); results stay
+    bit-identical across the switch and match the oracle."""
     monkeypatch.delenv("KIN_DISABLE_JIT", raising=False)
     monkeypatch.delenv("KIN_FORCE_JIT", raising=False)
+    monkeypatch.delenv("KIN_JIT_WARP_MAX", raising=False)
+    if warp_max is not None:
+        monkeypatch.setenv("KIN_JIT_WARP_MAX", str(warp_max))
     from kinematics_jl_b200.device import current_q, evaluate
     m, joints, sscc, sdf, mo, jo, so, sdf_o = _fridge_scene(False)
     q = scenes.random_configs(jo, 10, False, seed=37)

@@ -97,11 +97,13 @@ def test_every_kernel_agrees_bitwise_on_mixed_primitives(layout, monkeypatch):
     m, joints, sscc, sdf, mo, jo, so, sdf_o = _scene()
     gl = K.find_link(m, "gripper_link").id
 
-    def run(n, mode, **kw):
-        for k in ("KIN_DISABLE_JIT", "KIN_FORCE_JIT"):
+    def run(n, mode, warp_max=None, **kw):
+        for k in ("KIN_DISABLE_JIT", "KIN_FORCE_JIT", "KIN_JIT_WARP_MAX"):
             monkeypatch.delenv(k, raising=False)
         if mode:
             monkeypatch.setenv(mode, "1")
+        if warp_max is not None:
+            monkeypatch.setenv("KIN_JIT_WARP_MAX", str(warp_max))
         q = scenes.random_configs(jo, n, False, seed=43, zeros_every=50)
         K.set_joint_angles(m, joints, dev(q))
         K.compute_coll_dists(sscc, joints, sdf)
@@ -119,10 +121,12 @@ def test_every_kernel_agrees_bitwise_on_mixed_primitives(layout, monkeypatch):
         for key in ("T", "J", "vals", "grads", "argmin"):
             assert torch.equal(a[key], b[key]), (key, kw)
         _, c = run(77, "KIN_DISABLE_JIT", **kw)
-        _, d = run(77, "KIN_FORCE_JIT", **kw)                      # small batch + forced JIT = the warp kernel
-        assert c["launch"]["block"] > 0 and d["launch"]["block"] < 0
+        _, d = run(77, "KIN_FORCE_JIT", **kw)                      # small batch, one thread per configuration
+        _, e = run(77, "KIN_FORCE_JIT", warp_max=2048, **kw)       # small batch, one warp per configuration
+        assert c["launch"]["block"] > 0 and d["launch"]["block"] < 0 and e["launch"]["block"] < 0
+        assert d["launch"]["grid"] == 1 and e["launch"]["grid"] == 20
         for key in ("T", "J", "vals", "grads", "argmin"):
-            assert torch.equal(c[key], d[key]), (key, kw)
+            assert torch.equal(c[key], d[key]) and torch.equal(c[key], e[key]), (key, kw)
     v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, q[:300], 0.08, R.GRAD_ANALYTIC, R.SCRATCH_CLEAN)
     np.testing.assert_allclose(host(b["vals"][:300]) + 0.03, v_ref, rtol=RTOL, atol=ATOL)
     assert np.array_equal(b["argmin"][:300].cpu().numpy(), am_ref)

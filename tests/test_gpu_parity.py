@@ -992,3 +992,50 @@ def test_collision_summary_reductions(n, monkeypatch):
     np.testing.assert_allclose(host(dmin_a[sub]), v_ref.min(axis=1), rtol=RTOL, atol=ATOL)
     assert np.array_equal(amin_a[sub].cpu().numpy(), v_ref.argmin(axis=1) + 1)
     np.testing.assert_allclose(host(cost_a[sub]), (np.clip(margin - v_ref, 0, None) ** 2).sum(axis=1), rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("precision", [L.F64, L.F32])
+def test_host_entry_point_row_elision_with_padded_rows_and_fp32(precision):
+    """kin_eval_host, SoA, host arrays whose rows are LONGER than the batch (batch_stride > n) and the FP32 mode: the rows
+    that stay off PCIe (constants filled, duplicates copied by host threads) must land in the right place and hold the bits
+    the device-resident call produces; the padding behind each row is not touched."""
+    m, joints, _ = scenes.product_fetch(False)
+    mo, jo, _ = scenes.oracle_fetch(False)
+    N, ld = 140001, 140001 + 23                       # two staging chunks, ragged, padded rows
+    q = scenes.random_configs(jo, N, False, seed=97)
+    K.set_joint_angles(m, joints, dev(q[:1]))
+    dm = device_model(m)
+    fk = np.arange(1, 26, dtype=np.int32)
+    jac = np.array([K.find_link(m, "gripper_link").id], dtype=np.int32)
+    npdt = np.float64 if precision == L.F64 else np.float32
+    tdt = torch.float64 if precision == L.F64 else torch.float32
+    qh = np.zeros((8, ld), dtype=npdt)
+    qh[:, :N] = q.T
+    Th = np.full((300, ld), -7.0, dtype=npdt)
+    Jh = np.full((48, ld), -7.0, dtype=npdt)
+
+    def call(qp, tp, jp):
+        c = L.KinCall()
+        c.precision, c.layout, c.n, c.batch_stride, c.q = precision, L.SOA, N, ld, qp
+        c.n_fk_links, c.fk_links, c.T_out = 25, fk.ctypes.data_as(C.POINTER(C.c_int32)), tp
+        c.n_jac_links, c.jac_links, c.J_out, c.with_rot = 1, jac.ctypes.data_as(C.POINTER(C.c_int32)), jp, 1
+        c.truncation_dist = float("inf")
+        return c
+    b0 = [x.value for x in _transfer_counters()]
+    L.check(L.lib().kin_eval_host(dm.h, C.byref(call(qh.ctypes.data, Th.ctypes.data, Jh.ctypes.data))))
+    h2d, d2h, filled = (a.value - b for a, b in zip(_transfer_counters(), b0))
+    es = 8 if precision == L.F64 else 4
+    assert d2h + filled == es * N * 348 and filled >= es * N * 230
+    Qd = torch.as_tensor(qh, device="cuda")
+    Td = torch.zeros((300, ld), dtype=tdt, device="cuda")
+    Jd = torch.zeros((48, ld), dtype=tdt, device="cuda")
+    c = call(Qd.data_ptr(), Td.data_ptr(), Jd.data_ptr())
+    c.stream = torch.cuda.current_stream().cuda_stream
+    L.check(L.lib().kin_eval(dm.h, C.byref(c)))
+    torch.cuda.synchronize()
+    assert np.array_equal(Th[:, :N], Td[:, :N].cpu().numpy()) and np.array_equal(Jh[:, :N], Jd[:, :N].cpu().numpy())
+    assert np.all(Th[:, N:] == -7.0) and np.all(Jh[:, N:] == -7.0)
+    if precision == L.F64:
+        sub = slice(0, 500)
+        T = Th[:, sub].T.reshape(-1, 25, 4, 3).transpose(0, 1, 3, 2)
+        np.testing.assert_allclose(T, R.batch_fk(mo, jo, q[sub], mo.links[:25])[:, :, :3, :], rtol=RTOL, atol=ATOL)

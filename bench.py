@@ -399,6 +399,31 @@ def main():
         cc2.grad_mode, cc2.scratch_mode = L.GRAD_ANALYTIC, L.SCRATCH_CLEAN
         variant("collision_cost_grad(S=16,B=7,analytic,clean-scratch)", BYTES_COLL, cc2)
         del V, G
+        # distances only (compute_coll_dists!, collision.jl:51-58) and their per-configuration reductions
+        # (kin_collision_summary: min distance / sphere / hinge cost -- a collision CHECK; 20 B out per configuration)
+        dmin_ = torch.empty(N, dtype=torch.float64, device=dev)
+        cost_ = torch.empty(N, dtype=torch.float64, device=dev)
+        amin_ = torch.empty(N, dtype=torch.int32, device=dev)
+
+        def summary():
+            L.check(lib.kin_collision_summary(dm.h, L.F64, L.SOA, Q.data_ptr(), N, 0.03, dmin_.data_ptr(), amin_.data_ptr(),
+                                              cost_.data_ptr(), stream.cuda_stream))
+        for _ in range(W):
+            summary()
+        barrier()
+        s_steps = max(3, args.steps // 2)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(s_steps):
+            summary()
+        ev1.record(stream)
+        barrier()
+        ms_ = max_over_ranks(ev0.elapsed_time(ev1)) / s_steps
+        variants["collision_check_summary(min distance, argmin sphere, hinge cost)"] = {
+            "value": world * N / (ms_ * 1e-3), "unit": UNIT, "ms_per_step": ms_, "configs": N,
+            "algorithmic_bytes_per_config": 8 * N_DOF + 20, "note": "compute-bound: 16 spheres x 7 boxes per configuration, 84 B of I/O",
+            "fraction_in_collision": float((dmin_ < 0).double().mean())}
+        del dmin_, cost_, amin_
         # the tiled (AoSoA-32) layout: one contiguous block per warp
         Qt = Q.t().reshape(N // 32, 32, N_DOF).permute(0, 2, 1).contiguous()
         Tt = torch.empty((N // 32, N_LINKS * 12, 32), dtype=torch.float64, device=dev)

@@ -346,6 +346,9 @@ long long env_ll(const char *name, long long dflt) {
     return e && *e ? std::atoll(e) : dflt;
 }
 
+int jit_slots(const kin::GenOptions &o, const kin::ProgHeader &h);
+size_t jit_smem(const kin::GenOptions &o, const kin::ProgHeader &h, const JitKernel &k);
+
 // Which specialised kernel serves a batch below the large-batch threshold?  Measured (profiles/sweep_midsize.py, fused call,
 // device time per launch): one THREAD per configuration 18.7 us at n = 1, 22.7 us at n = 1024 .. 4096, 24.8 us at 16384 --
 // one WARP per configuration 31.0 / 32.9 / 96 us -- interpreting kernel 37 / 39 / 40 us.  So the thread-per-configuration
@@ -399,6 +402,18 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
     o.fd_cold = (int)env_ll("KIN_JIT_FD_COLD", 0);
     o.ksync = (int)env_ll("KIN_JIT_KSYNC", (o.coll && !tiled) ? 1 : 0);
     o.es32 = (o.layout == KIN_LAYOUT_SOA && (c->batch_stride ? c->batch_stride : c->n) < (1ll << 32)) ? (int)env_ll("KIN_JIT_ES32", 1) : 0;
+    // more than 12 columns: the joint frames of phase 2 (6 values per column) no longer fit in registers beside the rest;
+    // they are parked in the per-thread shared scratch as phase 1 computes them, and the CTA shrinks until the scratch fits
+    o.jf_smem = (o.coll && h.n_dof > env_ll("KIN_JIT_JF_REGS_MAX", 12)) ? 1 : 0;
+    if (o.jf_smem) {
+        const size_t avail = (size_t)(m ? m->dev_smem : 227 * 1024);
+        JitKernel probe;
+        for (;; o.block -= 32) {
+            probe.block = o.block; probe.slots = jit_slots(o, h);
+            const size_t need = jit_smem(o, h, probe);
+            if (need <= avail || o.block <= 32) { o.min_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)o.min_blocks, avail / std::max<size_t>(need, 1))); break; }
+        }
+    }
     if (o.layout == KIN_LAYOUT_AOS) o.keep_irrelevant = 0;     // (calls with keep_irrelevant never get here: jit_wanted)
     // tiled FK / Jacobian-only kernels: outputs staged per warp and written by the TMA engine (cp.async.bulk; kin_gen_skeleton.cuh)
     // 2^24 configurations, FK-all + Jacobian: 7.67 -> 7.61 ms (0.950 -> 0.959 of the HBM peak), 8.36 -> 8.05 without the input
@@ -439,7 +454,7 @@ bool jit_wanted(const KinModel *m, const KinCall *c, const DeviceProgram *dp, bo
     // large AoS batches: outputs staged through shared memory (kin_gen_skeleton.cuh: aos_flush); get_jacobian!
     // semantics (columns left untouched) cannot be staged and stay with the interpreting kernel
     if (c->layout == KIN_LAYOUT_AOS && !small && c->J_out && c->keep_irrelevant) return false;
-    if (c->vals_out && dp->prog.h.n_sph > 0 && dp->prog.h.n_dof > 16) return false;     // frames would not fit in registers
+    if (dp->prog.h.n_dof > 32) return false;                   // relevance masks of the generated phase 2 are 32 bits wide
     if (c->n < env_ll("KIN_JIT_MIN_BATCH", kJitMinBatch) && !std::getenv("KIN_FORCE_JIT")) {
         // a batch too small to be worth a compile on its own: specialise once the same program keeps being called, as a
         // solver callback (one configuration, n_wp waypoints, the active list of the batched IK) does
@@ -469,7 +484,7 @@ kin::JitHeaders jit_headers(const kin::GenSource &g) {
 // per-thread scratch slots of the generated kernel (kin_gen_skeleton.cuh)
 int jit_slots(const kin::GenOptions &o, const kin::ProgHeader &h) {
     if (!o.coll) return 0;
-    return 3 * h.n_sph + (o.stale ? 3 * h.n_dof : 0) + 2 * kin::SPH_GROUP;
+    return 3 * h.n_sph + (o.stale ? 3 * h.n_dof : 0) + 2 * kin::SPH_GROUP + (o.jf_smem ? 6 * h.n_dof : 0);
 }
 
 size_t jit_smem(const kin::GenOptions &o, const kin::ProgHeader &h, const JitKernel &k) {

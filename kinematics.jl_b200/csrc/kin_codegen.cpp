@@ -11,9 +11,9 @@ namespace kin {
 
 std::string GenOptions::key() const {
     char b[192];
-    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d I%d W%d P%d B%d", precision, layout, (int)want_T, (int)want_J,
+    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d I%d W%d P%d B%d F%d", precision, layout, (int)want_T, (int)want_J,
                   (int)coll, with_rot, rpy_jac, keep_irrelevant, (int)want_grads, (int)want_argmin, (int)stale, (int)ws, block, min_blocks, qbatch,
-                  ksync, es32, grad_mode, fd_cold, ik, warp, prims, bulk);
+                  ksync, es32, grad_mode, fd_cold, ik, warp, prims, bulk, jf_smem);
     return b;
 }
 
@@ -207,10 +207,10 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
                 for (int i = 0; i < 3; ++i) f.a[i] = E.fma(Aj.r[i * 3 + 0], x, E.fma(Aj.r[i * 3 + 1], y, E.mul(Aj.r[i * 3 + 2], z)));
             }
             frames[qcol] = f;
-            if (o.ws)
+            if (o.ws || (o.jf_smem && o.coll))       // frames handed over / parked in the shared scratch as they are computed
                 for (int i = 0; i < 6; ++i) {
                     const Val &v = i < 3 ? f.o[i] : f.a[i - 3];
-                    if (!v.c) E.os << "KJF_OUT(" << qcol << ", " << i << ", " << E.str(v) << ");\n";
+                    if (!v.c || o.jf_smem) E.os << "KJF_OUT(" << qcol << ", " << i << ", " << E.str(v) << ");\n";
                 }
             const Val qa = Emitter::V("q" + std::to_string(qcol));
             T = Aj;
@@ -404,6 +404,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
     std::ostringstream c;
     c << "#define KREAL " << (f32 ? "float" : "double") << "\n";
     if (o.fd_cold) c << "#define KIN_FD_COLD 1\n";
+    c << "#define KJFSMEM " << ((o.jf_smem && o.coll && !o.warp && !o.ik) ? 1 : 0) << "\n";
     c << "#define KPRIMS " << o.prims << "\n#define KBULK " << ((o.bulk && o.layout == 2 && !o.warp && !o.ik) ? 1 : 0) << "\n";
     c << "#define KWANT_T " << (o.want_T ? 1 : 0) << "\n#define KWANT_J " << (o.want_J ? 1 : 0) << "\n#define KCOLL " << (o.coll ? 1 : 0)
       << "\n#define KTILED " << (o.layout == 2 ? 1 : 0) << "\n#define KAOS " << (o.layout == 1 ? 1 : 0) << "\n#define KWS " << (o.ws ? 1 : 0) << "\n";

@@ -127,6 +127,7 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
 #if KAOS && !KWARP && !KIK
                                               , real_ *stw, const int nvalid
 #endif
+                                              , const real_ *jfs     // KJFSMEM: this thread's joint frames in the shared scratch, [6 j + i][thread]
                                               ) {
     typedef real_ real;
     constexpr int BS = KBS;
@@ -171,7 +172,15 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
                 real *st = stale0 + 3 * j * BS;
                 if ((MASK >> j) & 1u) {       // joint_jacobian!, algorithm.jl:65-81
                     real cx, cy, cz;
+#if KJFSMEM
+                    // more than 12 columns: the frames do not fit in registers; six shared loads with immediate offsets
+                    JFrame<real> fj;
+                    fj.o[0] = jfs[(6 * j + 0) * BS]; fj.o[1] = jfs[(6 * j + 1) * BS]; fj.o[2] = jfs[(6 * j + 2) * BS];
+                    fj.a[0] = jfs[(6 * j + 3) * BS]; fj.a[1] = jfs[(6 * j + 4) * BS]; fj.a[2] = jfs[(6 * j + 5) * BS];
+                    jac_col(fj, ((KREV >> j) & 1u) != 0, px, py, pz, cx, cy, cz);
+#else
                     jac_col(jfr[j], ((KREV >> j) & 1u) != 0, px, py, pz, cx, cy, cz);
+#endif
                     if (KSTALE) { st[0] = cx; st[BS] = cy; st[2 * BS] = cz; }
                     KP2_G(j, fma_(grad[0], cx, fma_(grad[1], cy, grad[2] * cz)));   // transpose(grad) * jac
                 } else if (KSTALE) {          // column left over from an earlier sphere (collision.jl:76,90)
@@ -542,7 +551,8 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
     real *cent0 = scr;
     real *stale0 = scr + 3 * KS * BS;
     real *hand = stale0 + (KSTALE ? 3 * KND : 0) * BS;
-    smem_next = tb + tab_reals + (3 * KS + (KSTALE ? 3 * KND : 0) + 2 * SPH_GROUP) * BS;
+    real *jfs = hand + 2 * SPH_GROUP * BS;                    // KJFSMEM: joint frames [6 j + i][thread]
+    smem_next = tb + tab_reals + (3 * KS + (KSTALE ? 3 * KND : 0) + 2 * SPH_GROUP + (KJFSMEM ? 6 * KND : 0)) * BS;
     {
         const real *src = reinterpret_cast<const real *>(A.boxes);
         for (int i = tid; i < n_box * BOX_REALS; i += BS) tb[i] = src[i];
@@ -683,7 +693,11 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
 #else
             #define KCEN_SET(s, i, v)
 #endif
+#if KJFSMEM
+            #define KJF_OUT(j, i, v) jfs[(6 * (j) + (i)) * BS] = (v)
+#else
             #define KJF_OUT(j, i, v)
+#endif
             {
 #include "kin_gen_phase1.inc"
 #if KCOLL
@@ -695,10 +709,14 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
                 real *Gp0 = reinterpret_cast<real *>(A.grads_out) + KREC_BASE((long long)KND * KS);
                 int32_t *Ap0 = KARGMIN ? A.argmin_out + KREC_BASE(KS) : nullptr;
                 #define KP2AARGS tb, n_box, cent0, hand
+#if KJFSMEM
+                #define KJFR_DEFINED
+                JFrame<real> jfr[KND];                        // unused: the frames were parked in the scratch by KJF_OUT
+#endif
 #if KAOS
-                #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, (size_t)lane, stw, nvalid
+                #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, (size_t)lane, stw, nvalid, jfs
 #else
-                #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, es
+                #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, es, jfs
 #endif
 #include "kin_gen_phase2.inc"
 #endif

@@ -233,6 +233,54 @@ def test_codegen_and_nvrtc_compile_without_a_gpu(tmp_path):
         del os.environ["KIN_JIT_FORCE_PRIMS"]
 
 
+@pytest.mark.parametrize("with_base", [False, True])
+def test_dual_arm_program_and_specialised_kernel_compile(with_base, tmp_path):
+    """15 / 18 configuration columns (tests/scenes_dual_arm.py): the compiled program against the oracle through the
+    numpy interpreter, and the specialised kernel of the fused call -- joint frames parked in the shared scratch
+    (KJFSMEM), CTA shrunk until the scratch fits -- compiled with NVRTC for sm_100a, every layout."""
+    import ctypes as C
+    import scenes_dual_arm as DA
+    import scenes_synthetic as SS
+    from kinematics_jl_b200 import lib as L
+    from kinematics_jl_b200.device import make_desc
+    m, joints, sscc, sdf = DA.product(with_base)
+    mo, jo, so, sdf_o = DA.oracle(with_base)
+    q = SS.random_q(jo, 60, with_base, seed=3)
+    ids = [l.id for l in m.links]
+    spheres = (sscc._parents, sscc._centers, sscc.sphere_radii)
+    boxes = (np.stack(DA.BOX_POSES), np.array(DA.BOX_WIDTHS))
+    h, ti, tr = dump_program(m, [j.id for j in joints], ids, ids, spheres, boxes)
+    assert h["n_dof"] == (18 if with_base else 15)
+    out = run_program(h, ti, tr, q, with_rot=True, rpy_jac=True)
+    np.testing.assert_allclose(out["T"], R.batch_fk(mo, jo, q, mo.links)[:, :, :3, :], rtol=0, atol=5e-14)
+    np.testing.assert_allclose(out["J"], R.batch_jacobian(mo, jo, q, mo.links, True, True), rtol=1e-11, atol=1e-11)
+    for scratch_ref, mode in ((True, R.SCRATCH_REFERENCE), (False, R.SCRATCH_CLEAN)):
+        o2 = run_program(h, ti, tr, q, truncation=0.3, scratch_ref=scratch_ref)
+        vals, grads, am = R.batch_collision(so, jo, sdf_o, q, 0.3, R.GRAD_FD, mode)
+        np.testing.assert_allclose(o2["vals"], vals, rtol=1e-12, atol=1e-13)
+        assert np.array_equal(o2["argmin"], am)
+        np.testing.assert_allclose(o2["grads"], grads.transpose(0, 2, 1), rtol=0, atol=1e-7)
+    lib = L.lib()
+    if not lib.kin_jit_status().startswith(b"ok"):
+        pytest.skip("NVRTC not available: " + lib.kin_jit_status().decode())
+    d, keep = make_desc(m, [j.id for j in joints], spheres=spheres, boxes=boxes)
+    fk = np.array(ids, dtype=np.int32)
+    for layout, prec in ((L.SOA, L.F64), (L.AOS, L.F64), (L.TILED32, L.F32)):
+        c = L.KinCall()
+        c.precision, c.layout, c.n, c.q = prec, layout, 1 << 20, 1
+        c.n_fk_links, c.fk_links, c.T_out = len(fk), fk.ctypes.data_as(C.POINTER(C.c_int32)), 1
+        c.truncation_dist = float("inf")
+        c.vals_out, c.grads_out = 1, 1
+        out_dir = tmp_path / ("l%d" % layout)
+        out_dir.mkdir()
+        L.check(lib.kin_codegen_dump(C.byref(d), C.byref(c), 1, str(out_dir).encode()))
+        cfg = (out_dir / "kin_gen_config.h").read_text()
+        assert "#define KJFSMEM 1" in cfg
+        kbs = int(__import__("re").search(r"#define KBS (\d+)", cfg).group(1))
+        assert kbs % 32 == 0 and 32 <= kbs <= 256
+        assert (out_dir / "kin_gen.cubin").stat().st_size > 10000
+
+
 def test_constant_and_duplicate_rows_claimed_by_the_generator_hold_in_the_oracle(tmp_path):
     """kin_eval_host does not move over PCIe the output rows the code generator declares constant (stored as a literal)
     or equal to another row (stored from the same variable, possibly negated).  Both claims are checked here, without a

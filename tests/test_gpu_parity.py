@@ -613,6 +613,63 @@ def test_specialised_kernel_fp32_and_general_models(monkeypatch):
     assert failures.value == 0
 
 
+@pytest.mark.parametrize("with_base", [False, True])
+@pytest.mark.parametrize("layout", [L.SOA, L.AOS, L.TILED32])
+def test_specialised_kernel_on_a_dual_arm_model(layout, with_base, monkeypatch):
+    """15 / 18 configuration columns (tests/scenes_dual_arm.py: the PR2 size class of fridge_demo.jl): the joint frames
+    of phase 2 no longer fit in registers, the specialised kernel parks them in its per-thread shared scratch
+    (GenOptions::jf_smem) and shrinks the CTA until the scratch fits.  Bit-identical to the interpreting kernel, and
+    both against the oracle; FP64 and FP32."""
+    import scenes_dual_arm as DA
+    import scenes_synthetic as SS
+    from kinematics_jl_b200.device import current_q, evaluate
+    m, joints, sscc, sdf = DA.product(with_base)
+    mo, jo, so, sdf_o = DA.oracle(with_base)
+    n = 5003
+    q = SS.random_q(jo, n, with_base, seed=41)
+    ids = [l.id for l in m.links]
+    tools = [K.find_link(m, "l_tool").id, K.find_link(m, "r_tool").id]
+    for dtype in (torch.float64, torch.float32):
+        for kw in (dict(truncation_dist=np.inf, grad_mode=L.GRAD_FD, scratch_mode=L.SCRATCH_REFERENCE),
+                   dict(truncation_dist=0.3, grad_mode=L.GRAD_FD, scratch_mode=L.SCRATCH_CLEAN, vals_offset=0.02),
+                   dict(truncation_dist=np.inf, grad_mode=L.GRAD_ANALYTIC, scratch_mode=L.SCRATCH_CLEAN)):
+            outs = []
+            for jit in (False, True):
+                monkeypatch.delenv("KIN_DISABLE_JIT", raising=False)
+                monkeypatch.delenv("KIN_FORCE_JIT", raising=False)
+                monkeypatch.setenv("KIN_FORCE_JIT" if jit else "KIN_DISABLE_JIT", "1")
+                K.set_joint_angles(m, joints, dev(q, dtype))
+                K.compute_coll_dists(sscc, joints, sdf)
+                dm = device_model(m)
+                Qc, ql, N = current_q(m)
+                o = evaluate(dm, Qc, ql, N, layout=layout, fk_links=ids, jac_links=tools, with_rot=True, rpy_jac=True,
+                             collision=True, want_argmin=True, launch_info=True, **kw)
+                torch.cuda.synchronize()
+                assert (o["launch"]["block"] < 0) == jit, (jit, o["launch"], L.lib().kin_jit_status())
+                outs.append(o)
+            for key in ("T", "J", "vals", "grads", "argmin"):
+                assert torch.equal(outs[0][key], outs[1][key]), (key, kw, dtype)
+        if dtype == torch.float64:        # the last combination (analytic gradient is an extension: FD combination re-run for the oracle)
+            sub = slice(0, 400)
+            b = outs[1]
+            np.testing.assert_allclose(host(b["T"][sub]), R.batch_fk(mo, jo, q[sub], mo.links)[:, :, :3, :], rtol=RTOL, atol=ATOL)
+            Jo = R.batch_jacobian(mo, jo, q[sub], [R.find_link(mo, "l_tool"), R.find_link(mo, "r_tool")], True, rpy_jac=True)
+            np.testing.assert_allclose(host(b["J"][sub]), Jo, rtol=1e-11, atol=1e-11)
+            K.set_joint_angles(m, joints, dev(q[sub], dtype))
+            for scratch, scratch_o in ((K.SCRATCH_REFERENCE, R.SCRATCH_REFERENCE), (K.SCRATCH_CLEAN, R.SCRATCH_CLEAN)):
+                Qc, ql, N = current_q(m)
+                o = evaluate(device_model(m), Qc, ql, N, layout=layout, collision=True, want_argmin=True, truncation_dist=0.3,
+                             scratch_mode=scratch, launch_info=True)
+                assert o["launch"]["block"] < 0
+                v_ref, g_ref, am_ref = R.batch_collision(so, jo, sdf_o, q[sub], 0.3, R.GRAD_FD, scratch_o)
+                np.testing.assert_allclose(host(o["vals"]), v_ref, rtol=RTOL, atol=ATOL)
+                assert np.array_equal(o["argmin"].cpu().numpy(), am_ref)
+                np.testing.assert_allclose(host(o["grads"]), g_ref.transpose(0, 2, 1), rtol=0, atol=1e-7)
+    compiles, hits, launches, failures = (C.c_int64() for _ in range(4))
+    L.lib().kin_jit_stats(C.byref(compiles), C.byref(hits), C.byref(launches), C.byref(failures))
+    assert failures.value == 0
+
+
 # ------------------------------------------------------------------------------------------------
 # FP32 mode (1e-5)
 # ------------------------------------------------------------------------------------------------

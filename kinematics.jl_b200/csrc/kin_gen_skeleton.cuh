@@ -75,7 +75,7 @@ __device__ __forceinline__ void phase2a_group(const int s0, const int ge, const 
 // pitch mod 16 = 16 / (records per half-warp); the PUTs (lanes along a row) are conflict free with any pitch.
 // (The FK / Jacobian-only kernels are bound by the DRAM write path, not by shared memory: there CNT lanes per record,
 // packed, with pitch 33 measured 5 % faster -- 0.97 against 0.92 of the HBM peak -- and is kept.)
-__host__ __device__ constexpr int aos_lpr(int cnt) { return !KCOLL ? cnt : cnt > 8 ? 16 : cnt > 4 ? 8 : cnt > 2 ? 4 : cnt > 1 ? 2 : 1; }
+__host__ __device__ constexpr int aos_lpr(int cnt) { return !KCOLL ? cnt : cnt > 16 ? 32 : cnt > 8 ? 16 : cnt > 4 ? 8 : cnt > 2 ? 4 : cnt > 1 ? 2 : 1; }
 __host__ __device__ constexpr int aos_ld(int cnt) {
     return !KCOLL ? 33 : 32 + (aos_lpr(cnt) == 16 ? 1 : aos_lpr(cnt) == 8 ? 2 : aos_lpr(cnt) == 4 ? 4 : aos_lpr(cnt) == 2 ? 8 : 1);
 }

@@ -629,10 +629,11 @@ def test_specialised_kernel_on_a_dual_arm_model(layout, with_base, monkeypatch):
     q = SS.random_q(jo, n, with_base, seed=41)
     ids = [l.id for l in m.links]
     tools = [K.find_link(m, "l_tool").id, K.find_link(m, "r_tool").id]
+    combos = (dict(truncation_dist=np.inf, grad_mode=L.GRAD_FD, scratch_mode=L.SCRATCH_REFERENCE),
+              dict(truncation_dist=0.3, grad_mode=L.GRAD_FD, scratch_mode=L.SCRATCH_CLEAN, vals_offset=0.02),
+              dict(truncation_dist=np.inf, grad_mode=L.GRAD_ANALYTIC, scratch_mode=L.SCRATCH_CLEAN))
     for dtype in (torch.float64, torch.float32):
-        for kw in (dict(truncation_dist=np.inf, grad_mode=L.GRAD_FD, scratch_mode=L.SCRATCH_REFERENCE),
-                   dict(truncation_dist=0.3, grad_mode=L.GRAD_FD, scratch_mode=L.SCRATCH_CLEAN, vals_offset=0.02),
-                   dict(truncation_dist=np.inf, grad_mode=L.GRAD_ANALYTIC, scratch_mode=L.SCRATCH_CLEAN)):
+        for kw in (combos if dtype == torch.float64 else combos[2:]):      # (every kernel is a 1-3 s NVRTC compile on a fresh box)
             outs = []
             for jit in (False, True):
                 monkeypatch.delenv("KIN_DISABLE_JIT", raising=False)

@@ -402,16 +402,31 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
     o.fd_cold = (int)env_ll("KIN_JIT_FD_COLD", 0);
     o.ksync = (int)env_ll("KIN_JIT_KSYNC", (o.coll && !tiled) ? 1 : 0);
     o.es32 = (o.layout == KIN_LAYOUT_SOA && (c->batch_stride ? c->batch_stride : c->n) < (1ll << 32)) ? (int)env_ll("KIN_JIT_ES32", 1) : 0;
-    // more than 12 columns: the joint frames of phase 2 (6 values per column) no longer fit in registers beside the rest;
-    // they are parked in the per-thread shared scratch as phase 1 computes them, and the CTA shrinks until the scratch fits
-    o.jf_smem = (o.coll && h.n_dof > env_ll("KIN_JIT_JF_REGS_MAX", 12)) ? 1 : 0;
-    if (o.jf_smem) {
-        const size_t avail = (size_t)(m ? m->dev_smem : 227 * 1024);
-        JitKernel probe;
-        for (;; o.block -= 32) {
-            probe.block = o.block; probe.slots = jit_slots(o, h);
+    // Models with many columns / spheres (a dual-arm mechanism with the planar base: 18 columns, 19 spheres = 952 B of
+    // per-thread shared scratch in FP64): the default shape no longer fits the SM's shared memory.  Measured
+    // (profiles/sweep_dual_arm.py, 18 columns, 2^21 configurations, collision-only, ms): what counts is the number of
+    // threads per SM -- 96 x 2: 3.27, 128 x 1: 4.87, 160 x 1: 3.88, 192 x 1: 3.28, 224 x 1: 2.84 (interpreting kernel: 6.91);
+    // FP32 256 x 1: 2.41, 192 x 2: 1.61, 224 x 2: 1.84, 384 x 1: 1.59, 448 x 1: 1.47 -- so the shape with the most threads
+    // that fits is taken (up to what the register file holds: 256 threads at 255 registers, 512 at 128 in FP32).
+    // The joint frames of phase 2 stay in registers at any column count: parking them in the shared scratch instead
+    // (jf_smem, opt-in through KIN_JIT_JF_REGS_MAX) costs threads and measured 4.15 against 2.52 ms at 15 columns,
+    // 6.21 against 2.84 at 18.
+    o.jf_smem = (o.coll && h.n_dof > env_ll("KIN_JIT_JF_REGS_MAX", 32)) ? 1 : 0;
+    if (o.coll && (!std::getenv("KIN_JIT_BLOCK") || o.jf_smem)) {
+        const size_t cta_max = (size_t)(m ? m->dev_smem : 227 * 1024), sm_total = cta_max + 1024;   // 228 KB per SM, 1 KB reserved per CTA
+        auto fits = [&](int block, int minb) {
+            JitKernel probe;
+            probe.block = block; probe.slots = jit_slots(o, h);
             const size_t need = jit_smem(o, h, probe);
-            if (need <= avail || o.block <= 32) { o.min_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)o.min_blocks, avail / std::max<size_t>(need, 1))); break; }
+            return need <= cta_max && (size_t)minb * (need + 1024) <= sm_total;
+        };
+        if (!fits(o.block, o.min_blocks)) {
+            const int cap = o.precision == 1 ? 512 : 256;
+            int best_b = 32, best_m = 1;
+            for (int minb = 1; minb <= 2; ++minb)
+                for (int b = 32; b * minb <= cap; b += 32)
+                    if (fits(b, minb) && b * minb > best_b * best_m) { best_b = b; best_m = minb; }
+            o.block = best_b; o.min_blocks = best_m;
         }
     }
     if (o.layout == KIN_LAYOUT_AOS) o.keep_irrelevant = 0;     // (calls with keep_irrelevant never get here: jit_wanted)

@@ -39,7 +39,7 @@ struct GenOptions {
     int fd_cold = 0;            // 1: the rare direct-FD fallback of the series gradient is an out-of-line call
     int ksync = 0;              // 1: CTA-wide barrier after every node of phase 1 (the warps of a CTA then fetch the
                                 //    straight-line code together: one instruction-cache fill serves all of them)
-    int jf_smem = 0;            // 1: the joint frames of phase 2 live in the per-thread shared scratch, not in registers (> 12 columns)
+    int jf_smem = 0;            // 1: the joint frames of phase 2 live in the per-thread shared scratch, not in registers (opt-in, KIN_JIT_JF_REGS_MAX: measured slower)
     int bulk = 0;               // 1: tiled layout, FK / Jacobian only: outputs staged per warp and written with cp.async.bulk (TMA)
     int prims = 0;              // 1: the SDF table holds rows other than boxes (sphere / cylinder): the row loops test the kind
     int es32 = 0;               // 1: SoA component stride held in 32 bits (ld < 2^32): one IMAD.WIDE per store address

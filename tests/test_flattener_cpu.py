@@ -265,20 +265,34 @@ def test_dual_arm_program_and_specialised_kernel_compile(with_base, tmp_path):
         pytest.skip("NVRTC not available: " + lib.kin_jit_status().decode())
     d, keep = make_desc(m, [j.id for j in joints], spheres=spheres, boxes=boxes)
     fk = np.array(ids, dtype=np.int32)
-    for layout, prec in ((L.SOA, L.F64), (L.AOS, L.F64), (L.TILED32, L.F32)):
-        c = L.KinCall()
-        c.precision, c.layout, c.n, c.q = prec, layout, 1 << 20, 1
-        c.n_fk_links, c.fk_links, c.T_out = len(fk), fk.ctypes.data_as(C.POINTER(C.c_int32)), 1
-        c.truncation_dist = float("inf")
-        c.vals_out, c.grads_out = 1, 1
-        out_dir = tmp_path / ("l%d" % layout)
-        out_dir.mkdir()
-        L.check(lib.kin_codegen_dump(C.byref(d), C.byref(c), 1, str(out_dir).encode()))
-        cfg = (out_dir / "kin_gen_config.h").read_text()
-        assert "#define KJFSMEM 1" in cfg
-        kbs = int(__import__("re").search(r"#define KBS (\d+)", cfg).group(1))
-        assert kbs % 32 == 0 and 32 <= kbs <= 256
-        assert (out_dir / "kin_gen.cubin").stat().st_size > 10000
+    import re
+    # launch shape: the most threads per SM whose shared scratch fits (kin_b200.cu: gen_options); 15 columns keep the
+    # default 128 x 2 (FP64) / 256 x 2 (FP32), 18 columns get one CTA of 224 (FP64) / 480 (FP32) threads
+    expect = {(L.SOA, L.F64): (128, 2) if not with_base else (224, 1), (L.AOS, L.F64): None,
+              (L.TILED32, L.F32): (256, 2) if not with_base else (480, 1), (L.TILED32, L.F64): (256, 1) if not with_base else (224, 1)}
+    for (layout, prec), shape in expect.items():
+        for jf_smem in ((False, True) if layout == L.SOA else (False,)):
+            c = L.KinCall()
+            c.precision, c.layout, c.n, c.q = prec, layout, 1 << 20, 1
+            c.n_fk_links, c.fk_links, c.T_out = len(fk), fk.ctypes.data_as(C.POINTER(C.c_int32)), 1
+            c.truncation_dist = float("inf")
+            c.vals_out, c.grads_out = 1, 1
+            out_dir = tmp_path / ("l%d_p%d_%d" % (layout, prec, jf_smem))
+            out_dir.mkdir()
+            if jf_smem:               # opt-in variant: joint frames parked in the shared scratch (measured slower, kept as a knob)
+                os.environ["KIN_JIT_JF_REGS_MAX"] = "12"
+            try:
+                L.check(lib.kin_codegen_dump(C.byref(d), C.byref(c), 1, str(out_dir).encode()))
+            finally:
+                os.environ.pop("KIN_JIT_JF_REGS_MAX", None)
+            cfg = (out_dir / "kin_gen_config.h").read_text()
+            assert ("#define KJFSMEM %d" % jf_smem) in cfg
+            kbs = int(re.search(r"#define KBS (\d+)", cfg).group(1))
+            minb = int(re.search(r"#define KMINB (\d+)", cfg).group(1))
+            assert kbs % 32 == 0 and 32 <= kbs <= 512
+            if shape is not None and not jf_smem:
+                assert (kbs, minb) == shape, (layout, prec, kbs, minb)
+            assert (out_dir / "kin_gen.cubin").stat().st_size > 10000
 
 
 def test_constant_and_duplicate_rows_claimed_by_the_generator_hold_in_the_oracle(tmp_path):

@@ -348,8 +348,9 @@ KIN_API int kin_query_launch(KinModel *model, const KinCall *call, int32_t *regs
  * interpreting kernels up to the sign of a zero) and compiles it with NVRTC for sm_100a on first use (1-3 s, then
  * cached in the model and on disk under KIN_JIT_CACHE_DIR, default /tmp/kin_b200_jit-<uid>).  libnvrtc is loaded with
  * dlopen (KIN_NVRTC_PATH overrides the search); without it, or with KIN_DISABLE_JIT set, every call runs the
- * ahead-of-time interpreting kernels -- as do calls on models with more than 32 configuration columns and AoS calls with
- * keep_irrelevant on batches above 2048.  kin_query_launch reports a NEGATIVE block size for a specialised kernel.
+ * ahead-of-time interpreting kernels -- as do AoS calls with keep_irrelevant on batches above 2048 (KIN_MAX_JOINTS = 32
+ * columns is the limit of every kernel; on models whose per-thread shared scratch is large -- many columns / spheres --
+ * the specialised collision kernels take the launch shape with the most threads per SM that fits).  kin_query_launch reports a NEGATIVE block size for a specialised kernel.
  *   kin_jit_status   "ok: <library> (<version>)" or the reason NVRTC is unavailable
  *   kin_jit_stats    kernels compiled / taken from the disk cache / launched / failed since load
  *   kin_codegen_dump host-only: writes the generated source of the kernel `call` would run (its pointers are only

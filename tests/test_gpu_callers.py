@@ -448,6 +448,85 @@ def test_collision_aware_inverse_kinematics_slsqp_hard_constraint():
     assert found >= 6
 
 
+def _oracle_ik(mo, jo, link, target, x0, with_rot, sscc=None, sdf=None, ftol=1e-8, margin=0.02):
+    """The solver of K.inverse_kinematics (scipy SLSQP, same options, same two stages) driven by the ORACLE's evaluations."""
+    from scipy.optimize import minimize
+    nb = mo.n_dof_extra
+    lo, hi = [j.lower for j in jo] + [-np.inf] * nb, [j.upper for j in jo] + [np.inf] * nb
+    bounds = [(a if np.isfinite(a) else None, b if np.isfinite(b) else None) for a, b in zip(lo, hi)]
+
+    def solve(x0, cons):
+        return minimize(lambda x: R.ik_objective(mo, link, jo, x, target, with_rot), x0, jac=True, method="SLSQP", bounds=bounds,
+                        constraints=cons, options={"ftol": ftol, "maxiter": 200})
+    if sscc is None:
+        return solve(x0, ())
+    x0 = solve(x0, ()).x
+    return solve(x0, [{"type": "ineq", "fun": lambda x: R.ineq_const(sscc, jo, sdf, x, 1, margin)[0],
+                       "jac": lambda x: R.ineq_const(sscc, jo, sdf, x, 1, margin)[1][0].T}])
+
+
+def _dual_arm_target(mo, jo, so, sdf_o, with_base, trial):
+    """A reachable tool pose: FK of an in-limit configuration (fixed seed; `trial` picks one of the draws)."""
+    rng = np.random.default_rng(5)
+    lo, hi = np.array([j.lower for j in jo]), np.array([j.upper for j in jo])
+    for _ in range(trial + 1):
+        qt = lo + (hi - lo) * (0.25 + 0.5 * rng.random(len(jo)))
+    if with_base:
+        qt = np.concatenate([qt, [0.2, -0.1, 0.3]])
+    R.set_joint_angles(mo, jo, qt)
+    return R.get_transform(mo, R.find_link(mo, "l_tool")).copy()
+
+
+@pytest.mark.parametrize("with_base", [False, True])
+def test_inverse_kinematics_dual_arm_as_the_pr2_test(with_base):
+    """test/test_inverse_kinematics.jl:26-88 ("inverse kinematics_pr2") on the dual-arm fixture (the PR2 URDF and its
+    meshes are not available; tests/scenes_dual_arm.py has the same shape: both arms = 14 joints, 17 columns with the
+    planar base, the left tool frame as the target link, collision spheres on both arms).  "no collision": with and
+    without rotation, status success and the pose within 1e-3; "with collision" (with_base, with_rot, bistage): the
+    pose within 1e-3 and every sphere clear (the reference asserts > -1e-5; the constraint is dists - 0.02 >= 0).
+    Each solve is also run with the oracle driving the same SLSQP: same iteration count, same solution."""
+    import scenes_dual_arm as DA
+    m, joints, sscc, sdf = DA.product(with_base)
+    mo, jo, so, sdf_o = DA.oracle(with_base)
+    joints, jo = joints[1:], jo[1:]                      # vcat(rarm_joints, larm_joints): the torso stays put
+    nd = len(joints) + (3 if with_base else 0)
+    link, link_o = K.find_link(m, "l_tool"), R.find_link(mo, "l_tool")
+    tgt = _dual_arm_target(mo, jo, so, sdf_o, with_base, 0)
+    for with_rot in (False, True):
+        K.set_joint_angles(m, joints, np.zeros(nd))
+        q, res = K.inverse_kinematics(m, link, joints, K.Transform(tgt), with_rot=with_rot, ftol=1e-8)
+        assert res.success
+        pose = K.get_transform(m, link)
+        assert np.linalg.norm(K.translation(pose) - tgt[:3, 3]) < 1e-3
+        if with_rot:
+            np.testing.assert_allclose(K.rpy(pose), K.rpy(K.Transform(tgt)), atol=1e-3)
+        R.set_joint_angles(mo, jo, np.zeros(nd))
+        res_o = _oracle_ik(mo, jo, link_o, tgt, np.zeros(nd), with_rot)
+        assert res.nit == res_o.nit
+        np.testing.assert_allclose(q, res_o.x, atol=1e-6)
+    if not with_base:
+        return
+    n_active = 0
+    for trial in (0, 2):            # unconstrained solutions come within 0.011 / 0.006 of a box (oracle-driven prototype)
+        tgt = _dual_arm_target(mo, jo, so, sdf_o, True, trial)
+        K.set_joint_angles(m, joints, np.zeros(nd))
+        K.inverse_kinematics(m, link, joints, K.Transform(tgt), with_rot=True, ftol=1e-8)
+        d_free = float(K.compute_coll_dists(sscc, joints, sdf).min())
+        K.set_joint_angles(m, joints, np.zeros(nd))
+        q, res = K.inverse_kinematics(m, link, joints, K.Transform(tgt), sscc=sscc, sdf=sdf, with_rot=True, use_bistage=True, ftol=1e-8)
+        assert res.success
+        pose = K.get_transform(m, link)
+        assert np.linalg.norm(K.translation(pose) - tgt[:3, 3]) < 1e-3
+        np.testing.assert_allclose(K.rpy(pose), K.rpy(K.Transform(tgt)), atol=1e-3)
+        d = np.asarray(K.compute_coll_dists(sscc, joints, sdf))          # one configuration: a host vector
+        assert np.all(d > -1e-5) and d.min() >= 0.02 - 1e-5
+        n_active += d_free < 0.02
+        res_o = _oracle_ik(mo, jo, link_o, tgt, np.zeros(nd), True, so, sdf_o)
+        assert res_o.success and abs(res.nit - res_o.nit) <= 1
+        np.testing.assert_allclose(q, res_o.x, atol=1e-4)
+    assert n_active == 2            # the constraint was needed in both cases
+
+
 # ------------------------------------------------------------------------------------------------
 # the device-resident batched IK solve (one kernel launch: kin_ik_solve)
 # ------------------------------------------------------------------------------------------------

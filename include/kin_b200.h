@@ -298,7 +298,8 @@ KIN_API int kin_pose_residual_multi(KinModel *model, int32_t precision, int32_t 
  * iteration (the loop of the collision-constrained solve below, without spheres).  FP64, per-problem contiguous
  * arrays (AoS), DEVICE pointers:
  * targets[n][6] = x y z roll pitch yaw, q0 / q_out [n][n_dof], f_out[n], iters_out[n] (nullable); lower / upper are
- * HOST [n_dof] (+-inf allowed, NULL = unbounded).  n_dof <= 12. */
+ * HOST [n_dof] (+-inf allowed, NULL = unbounded).  n_dof <= 20 (up to 12 columns the normal
+ * equations of a problem live in registers; above, in local memory). */
 typedef struct {
     int64_t n;
     int32_t link_id;           /* 1-based id of the link to place */

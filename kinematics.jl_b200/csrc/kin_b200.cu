@@ -1374,6 +1374,7 @@ int ik_solve_coll(KinModel *m, const KinIkCall *c) {
     a.ctol = c->ctol > 0 ? c->ctol : 1e-6; a.lambda0 = c->lambda0 > 0 ? c->lambda0 : 1e-2;
     a.trunc = c->margin + 0.05;                                  // planning.jl:56
     a.targets = (const double *)c->targets;
+    a.nd = nd;
     for (int j = 0; j < nd; ++j) {
         a.lo[j] = c->lower ? c->lower[j] : -INFINITY;
         a.hi[j] = c->upper ? c->upper[j] : INFINITY;
@@ -1418,7 +1419,7 @@ int ik_solve_coll(KinModel *m, const KinIkCall *c) {
             KIN_IKC_CASE(1) KIN_IKC_CASE(2) KIN_IKC_CASE(3) KIN_IKC_CASE(4) KIN_IKC_CASE(5) KIN_IKC_CASE(6)
             KIN_IKC_CASE(7) KIN_IKC_CASE(8) KIN_IKC_CASE(9) KIN_IKC_CASE(10) KIN_IKC_CASE(11) KIN_IKC_CASE(12)
 #undef KIN_IKC_CASE
-            default: break;
+            default: launch_ik_coll_step<0>(a, rows == 6, stream); break;       // 13 .. IKC_MAX_DOF columns: run-time-sized instance
         }
         cudaError_t le = cudaGetLastError();
         if (le != cudaSuccess) { rc = fail_cuda(le, "launching ik_coll_step_kernel"); break; }
@@ -1453,7 +1454,7 @@ int kin_ik_solve(KinModel *m, const KinIkCall *c) {
     if (c->n < 0 || (c->n > 0 && (!c->targets || !c->q0 || !c->q_out || !c->f_out))) return fail(KIN_ERR_INVALID_ARGUMENT, "null argument");
     if (c->iters < 0) return fail(KIN_ERR_INVALID_ARGUMENT, "negative iteration count");
     const int nd = m->hm.n_dof();
-    if (nd < 1 || nd > 12) return fail(KIN_ERR_LIMIT, "kin_ik_solve: 1..12 configuration columns");
+    if (nd < 1 || nd > kin::IKC_MAX_DOF) return fail(KIN_ERR_LIMIT, "kin_ik_solve: 1..20 configuration columns");
     if (c->link_id < 1 || c->link_id > m->hm.n_links) return fail(KIN_ERR_INVALID_ARGUMENT, "link id out of range");
     if (c->n == 0) return KIN_OK;
     if (c->collision) return ik_solve_coll(m, c);

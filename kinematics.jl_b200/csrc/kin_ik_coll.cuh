@@ -25,13 +25,14 @@
 
 namespace kin {
 
-constexpr int IKC_MAX_DOF = 12;
+constexpr int IKC_MAX_DOF = 20;         // configuration columns kin_ik_solve accepts (a dual-arm mechanism with the planar base: 17-18)
+constexpr int IKC_MAX_DOF_STATIC = 12;  // up to here the step kernel is instantiated per column count (everything in registers)
 
 struct IkCollArgs {
     long long n, ld;                 // problems, SoA stride of every array below
     long long n_act;                 // launch width: length of the active list (== n before the first compaction)
     const int32_t *act;              // list position -> problem (null: identity)
-    int n_sph, it;
+    int n_sph, it, nd;               // nd: configuration columns (read by the run-time-sized instance of the step kernel)
     double margin, mu, ftol, ctol, lambda0, trunc;
     const double *targets;           // [n][6] AoS (caller's)
     const double *T, *J, *V, *G;     // kin_eval outputs at the trial points (SoA)
@@ -63,8 +64,13 @@ __global__ void __launch_bounds__(256) ik_coll_init_kernel(const IkCollArgs A, c
     A.its[n] = 0;
 }
 
-template <int ND, bool ROT>
+// NDT > 0: the column count is a template constant (1 .. IKC_MAX_DOF_STATIC: normal equations in registers, every loop
+// unrolled); NDT == 0: read from A.nd at run time (up to IKC_MAX_DOF columns: the arrays are sized for the maximum and
+// live in local memory -- 17 columns would need 2 x 153 doubles of triangle in registers otherwise).
+template <int NDT, bool ROT>
 __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
+    constexpr int NDA = NDT > 0 ? NDT : IKC_MAX_DOF;
+    const int ND = NDT > 0 ? NDT : A.nd;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // position in the active list
     if (i >= A.n_act) return;
     const long long n = A.act ? A.act[i] : i;                                  // problem
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
         A.damp[n] = damp;
     }
 
-    double q[ND], g[ND], H[ND][ND];
+    double q[NDA], g[NDA], H[NDA][NDA];
     if (ok) {
         // ---- accepted: multipliers, merit and normal equations at this point ----
         #pragma unroll
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
         }
         #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-            double jr[ND];
+            double jr[NDA];
             #pragma unroll
             for (int a = 0; a < ND; ++a) jr[a] = A.J[(long long)(a * ROWS + r) * ld + i];
             #pragma unroll
@@ -147,7 +153,7 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
             }
             A.mult[s * ld + n] = lam;
             if (psi > 0.0) {
-                double gs[ND];
+                double gs[NDA];
                 #pragma unroll
                 for (int a = 0; a < ND; ++a) gs[a] = A.G[(long long)(s * ND + a) * ld + i];
                 const double w = mu * psi;
@@ -187,8 +193,8 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
     }
 
     // ---- step: active set on the limits, Cholesky of H + damp (I + diag H), q_try = clamp(q - x) ----
-    bool fr[ND];
-    double x[ND];
+    bool fr[NDA];
+    double x[NDA];
     #pragma unroll
     for (int a = 0; a < ND; ++a)
         fr[a] = !(((q[a] <= A.lo[a] + 1e-12) && (g[a] > 0.0)) || ((q[a] >= A.hi[a] - 1e-12) && (g[a] < 0.0)));

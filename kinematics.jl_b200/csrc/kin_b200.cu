@@ -1328,10 +1328,20 @@ int kin_pose_residual(KinModel *m, int32_t precision, int32_t layout, const void
 namespace {
 
 template <int ND>
-void launch_ik_coll_step(const kin::IkCollArgs &a, bool rot, cudaStream_t stream) {
-    const unsigned grid = (unsigned)((a.n_act + 127) / 128);
-    if (rot) kin::ik_coll_step_kernel<ND, true><<<grid, 128, 0, stream>>>(a);
-    else kin::ik_coll_step_kernel<ND, false><<<grid, 128, 0, stream>>>(a);
+void launch_ik_coll_step(const kin::IkCollArgs &a, bool rot, cudaStream_t stream, int dev_smem) {
+    int block = 128;
+    size_t smem = 0;
+    auto kern = rot ? kin::ik_coll_step_kernel<ND, true> : kin::ik_coll_step_kernel<ND, false>;
+    if (ND == 0) {
+        // run-time-sized instance (13 .. IKC_MAX_DOF columns): the normal equations of a problem live in shared memory,
+        // [slot][thread]; the largest CTA whose slots fit (18 columns: 1800 B per thread -> 96 threads)
+        const size_t per = kin::ikc_dyn_smem_per_thread(a.nd);
+        while (block > 32 && per * (size_t)block > (size_t)dev_smem) block -= 32;
+        smem = per * (size_t)block;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    const unsigned grid = (unsigned)((a.n_act + block - 1) / block);
+    kern<<<grid, block, smem, stream>>>(a);
 }
 
 // The collision-constrained solve of kin_ik_solve (csrc/kin_ik_coll.cuh): a loop of (kin_eval, step kernel) pairs on the
@@ -1415,11 +1425,11 @@ int ik_solve_coll(KinModel *m, const KinIkCall *c) {
         if (rc != KIN_OK) break;
         a.it = it;
         switch (nd) {
-#define KIN_IKC_CASE(N_) case N_: launch_ik_coll_step<N_>(a, rows == 6, stream); break;
+#define KIN_IKC_CASE(N_) case N_: launch_ik_coll_step<N_>(a, rows == 6, stream, m->dev_smem); break;
             KIN_IKC_CASE(1) KIN_IKC_CASE(2) KIN_IKC_CASE(3) KIN_IKC_CASE(4) KIN_IKC_CASE(5) KIN_IKC_CASE(6)
             KIN_IKC_CASE(7) KIN_IKC_CASE(8) KIN_IKC_CASE(9) KIN_IKC_CASE(10) KIN_IKC_CASE(11) KIN_IKC_CASE(12)
 #undef KIN_IKC_CASE
-            default: launch_ik_coll_step<0>(a, rows == 6, stream); break;       // 13 .. IKC_MAX_DOF columns: run-time-sized instance
+            default: launch_ik_coll_step<0>(a, rows == 6, stream, m->dev_smem); break;       // 13 .. IKC_MAX_DOF columns: run-time-sized instance
         }
         cudaError_t le = cudaGetLastError();
         if (le != cudaSuccess) { rc = fail_cuda(le, "launching ik_coll_step_kernel"); break; }

@@ -64,11 +64,38 @@ __global__ void __launch_bounds__(256) ik_coll_init_kernel(const IkCollArgs A, c
     A.its[n] = 0;
 }
 
-// NDT > 0: the column count is a template constant (1 .. IKC_MAX_DOF_STATIC: normal equations in registers, every loop
-// unrolled); NDT == 0: read from A.nd at run time (up to IKC_MAX_DOF columns: the arrays are sized for the maximum and
-// live in local memory -- 17 columns would need 2 x 153 doubles of triangle in registers otherwise).
+// Where a problem's normal equations live while a thread works on them.
+//   NDT > 0: the column count is a template constant (1 .. IKC_MAX_DOF_STATIC): plain arrays, every loop unrolled,
+//            everything in registers.
+//   NDT == 0: the column count is read from A.nd at run time (up to IKC_MAX_DOF columns; 17 columns would need 2 x 153
+//            doubles of triangle in registers).  The packed lower triangle and the three work vectors sit in SHARED memory,
+//            [slot][thread] (conflict free, immediate latency ~30 cycles); the host sizes the CTA so that
+//            (nd (nd + 1) / 2 + 3 nd) doubles per thread fit.  (First version: local memory -- ~5000 dependent L2 round
+//            trips per thread in the Cholesky loops, 1.5 ms per launch on 42 k problems; ncu launch list in profiles/.)
+template <int NDT>
+struct IkcStore {
+    double H_[NDT][NDT], g_[NDT], x_[NDT], v_[NDT];
+    __device__ __forceinline__ IkcStore(double *, int, int, int) {}
+    __device__ __forceinline__ double &H(int a, int b) { return H_[a][b]; }
+    __device__ __forceinline__ double &g(int a) { return g_[a]; }
+    __device__ __forceinline__ double &x(int a) { return x_[a]; }
+    __device__ __forceinline__ double &v(int a) { return v_[a]; }
+};
+template <>
+struct IkcStore<0> {
+    double *base;
+    int bs, tri, nd;
+    __device__ __forceinline__ IkcStore(double *smem, int tid, int bs_, int nd_) : base(smem + tid), bs(bs_), tri(nd_ * (nd_ + 1) / 2), nd(nd_) {}
+    __device__ __forceinline__ double &H(int a, int b) { return base[(a * (a + 1) / 2 + b) * bs]; }
+    __device__ __forceinline__ double &g(int a) { return base[(tri + a) * bs]; }
+    __device__ __forceinline__ double &x(int a) { return base[(tri + nd + a) * bs]; }
+    __device__ __forceinline__ double &v(int a) { return base[(tri + 2 * nd + a) * bs]; }
+};
+__host__ __device__ inline size_t ikc_dyn_smem_per_thread(int nd) { return sizeof(double) * (size_t)(nd * (nd + 1) / 2 + 3 * nd); }
+
 template <int NDT, bool ROT>
 __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
+    extern __shared__ double ikc_smem[];
     constexpr int NDA = NDT > 0 ? NDT : IKC_MAX_DOF;
     const int ND = NDT > 0 ? NDT : A.nd;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // position in the active list
@@ -80,6 +107,7 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
     const double PI = 3.14159265358979323846;
     const double mu = A.mu, margin = A.margin;
     const int S = A.n_sph;
+    IkcStore<NDT> W(ikc_smem, (int)threadIdx.x, (int)blockDim.x, ND);
 
     // ---- residual at the trial point: e = [p - p_t; rpy - rpy_t] (planning.jl:114-138 sign), angles wrapped ----
     double e[ROWS];
@@ -119,26 +147,26 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
         A.damp[n] = damp;
     }
 
-    double q[NDA], g[NDA], H[NDA][NDA];
+    double q[NDA];
     if (ok) {
         // ---- accepted: multipliers, merit and normal equations at this point ----
         #pragma unroll
         for (int a = 0; a < ND; ++a) {
             q[a] = A.q_try[a * ld + i];
-            g[a] = 0.0;
+            W.g(a) = 0.0;
             #pragma unroll
-            for (int b = 0; b <= a; ++b) H[a][b] = 0.0;
+            for (int b = 0; b <= a; ++b) W.H(a, b) = 0.0;
         }
         #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-            double jr[NDA];
             #pragma unroll
-            for (int a = 0; a < ND; ++a) jr[a] = A.J[(long long)(a * ROWS + r) * ld + i];
+            for (int a = 0; a < ND; ++a) W.v(a) = A.J[(long long)(a * ROWS + r) * ld + i];
             #pragma unroll
             for (int a = 0; a < ND; ++a) {
-                g[a] = fma(jr[a], e[r], g[a]);
+                const double ja = W.v(a);
+                W.g(a) = fma(ja, e[r], W.g(a));
                 #pragma unroll
-                for (int b = 0; b <= a; ++b) H[a][b] = fma(jr[a], jr[b], H[a][b]);
+                for (int b = 0; b <= a; ++b) W.H(a, b) = fma(ja, W.v(b), W.H(a, b));
             }
         }
         double phi_n = ft, viol = -CUDART_INF;
@@ -153,16 +181,16 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
             }
             A.mult[s * ld + n] = lam;
             if (psi > 0.0) {
-                double gs[NDA];
                 #pragma unroll
-                for (int a = 0; a < ND; ++a) gs[a] = A.G[(long long)(s * ND + a) * ld + i];
+                for (int a = 0; a < ND; ++a) W.v(a) = A.G[(long long)(s * ND + a) * ld + i];
                 const double w = mu * psi;
                 #pragma unroll
                 for (int a = 0; a < ND; ++a) {
-                    g[a] = fma(-w, gs[a], g[a]);
-                    const double ma = mu * gs[a];
+                    const double ga = W.v(a);
+                    W.g(a) = fma(-w, ga, W.g(a));
+                    const double ma = mu * ga;
                     #pragma unroll
-                    for (int b = 0; b <= a; ++b) H[a][b] = fma(ma, gs[b], H[a][b]);
+                    for (int b = 0; b <= a; ++b) W.H(a, b) = fma(ma, W.v(b), W.H(a, b));
                 }
                 phi_n = fma(w, psi, phi_n);
             }
@@ -170,9 +198,9 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
         #pragma unroll
         for (int a = 0; a < ND; ++a) {
             A.q[a * ld + n] = q[a];
-            A.g[a * ld + n] = g[a];
+            A.g[a * ld + n] = W.g(a);
             #pragma unroll
-            for (int b = 0; b <= a; ++b) A.H[(long long)(a * (a + 1) / 2 + b) * ld + n] = H[a][b];
+            for (int b = 0; b <= a; ++b) A.H[(long long)(a * (a + 1) / 2 + b) * ld + n] = W.H(a, b);
         }
         A.phi[n] = phi_n;
         A.fpose[n] = ft;
@@ -186,52 +214,53 @@ __global__ void __launch_bounds__(128) ik_coll_step_kernel(const IkCollArgs A) {
         #pragma unroll
         for (int a = 0; a < ND; ++a) {
             q[a] = A.q[a * ld + n];
-            g[a] = A.g[a * ld + n];
+            W.g(a) = A.g[a * ld + n];
             #pragma unroll
-            for (int b = 0; b <= a; ++b) H[a][b] = A.H[(long long)(a * (a + 1) / 2 + b) * ld + n];
+            for (int b = 0; b <= a; ++b) W.H(a, b) = A.H[(long long)(a * (a + 1) / 2 + b) * ld + n];
         }
     }
 
     // ---- step: active set on the limits, Cholesky of H + damp (I + diag H), q_try = clamp(q - x) ----
     bool fr[NDA];
-    double x[NDA];
     #pragma unroll
-    for (int a = 0; a < ND; ++a)
-        fr[a] = !(((q[a] <= A.lo[a] + 1e-12) && (g[a] > 0.0)) || ((q[a] >= A.hi[a] - 1e-12) && (g[a] < 0.0)));
+    for (int a = 0; a < ND; ++a) {
+        const double ga = W.g(a);
+        fr[a] = !(((q[a] <= A.lo[a] + 1e-12) && (ga > 0.0)) || ((q[a] >= A.hi[a] - 1e-12) && (ga < 0.0)));
+    }
     #pragma unroll
     for (int a = 0; a < ND; ++a) {
         #pragma unroll
-        for (int b = 0; b < a; ++b) H[a][b] = (fr[a] && fr[b]) ? H[a][b] : 0.0;
-        H[a][a] = fr[a] ? fma(damp, 1.0 + H[a][a], H[a][a]) : 1.0;
-        x[a] = fr[a] ? g[a] : 0.0;
+        for (int b = 0; b < a; ++b) W.H(a, b) = (fr[a] && fr[b]) ? W.H(a, b) : 0.0;
+        W.H(a, a) = fr[a] ? fma(damp, 1.0 + W.H(a, a), W.H(a, a)) : 1.0;
+        W.x(a) = fr[a] ? W.g(a) : 0.0;
     }
     #pragma unroll
     for (int a = 0; a < ND; ++a) {
         #pragma unroll
         for (int b = 0; b <= a; ++b) {
-            double sum = H[a][b];
+            double sum = W.H(a, b);
             #pragma unroll
-            for (int k = 0; k < b; ++k) sum = fma(-H[a][k], H[b][k], sum);
-            if (a == b) H[a][a] = sqrt(sum > 1e-300 ? sum : 1e-300);
-            else H[a][b] = sum / H[b][b];
+            for (int k = 0; k < b; ++k) sum = fma(-W.H(a, k), W.H(b, k), sum);
+            if (a == b) W.H(a, a) = sqrt(sum > 1e-300 ? sum : 1e-300);
+            else W.H(a, b) = sum / W.H(b, b);
         }
     }
     #pragma unroll
     for (int a = 0; a < ND; ++a) {
-        double sum = x[a];
+        double sum = W.x(a);
         #pragma unroll
-        for (int k = 0; k < a; ++k) sum = fma(-H[a][k], x[k], sum);
-        x[a] = sum / H[a][a];
+        for (int k = 0; k < a; ++k) sum = fma(-W.H(a, k), W.x(k), sum);
+        W.x(a) = sum / W.H(a, a);
     }
     #pragma unroll
     for (int a = ND - 1; a >= 0; --a) {
-        double sum = x[a];
+        double sum = W.x(a);
         #pragma unroll
-        for (int k = a + 1; k < ND; ++k) sum = fma(-H[k][a], x[k], sum);
-        x[a] = sum / H[a][a];
+        for (int k = a + 1; k < ND; ++k) sum = fma(-W.H(k, a), W.x(k), sum);
+        W.x(a) = sum / W.H(a, a);
     }
     #pragma unroll
-    for (int a = 0; a < ND; ++a) A.q_try[a * ld + i] = fmin(fmax(q[a] - x[a], A.lo[a]), A.hi[a]);
+    for (int a = 0; a < ND; ++a) A.q_try[a * ld + i] = fmin(fmax(q[a] - W.x(a), A.lo[a]), A.hi[a]);
 }
 
 // Compaction of the active list: every still-running problem of the current list (act_in, or the identity when null)

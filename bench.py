@@ -476,6 +476,24 @@ def main():
         bytes_b = 8 * (N_DOF + 3) + 8 * 12 * N_LINKS + 8 * 6 * (N_DOF + 3) + 8 * N_SPH + 8 * N_SPH * (N_DOF + 3)
         variant("fused_with_planar_base(11 columns)", bytes_b, cb, Nb, dmb)
         del Qb, Tb, Jb, Vb, Gb
+        # a dual-arm mechanism with the planar base (data/dual_arm.urdf: 18 columns, 37 links, 19 spheres, 3 boxes -- the size
+        # class of the PR2 of fridge_demo.jl): FK of all links + collision cost / gradient, SoA.  Above 16 columns the
+        # specialised kernel takes the launch shape with the most threads per SM whose shared scratch fits
+        md, jd, sd, sdfd = scene_fetch.product_dual_arm(True)
+        ndd, nld, nsd, Nd = len(jd) + 3, len(md.links), len(sd.sphere_radii), min(N, 1 << 21)
+        K.set_joint_angles(md, jd, torch.zeros((1, ndd), dtype=torch.float64, device=dev))
+        K.compute_coll_dists(sd, jd, sdfd)
+        dmd = device_model(md)
+        gd = torch.Generator(device=dev).manual_seed(2000 + rank)
+        Qd = 2.0 * torch.rand((ndd, Nd), generator=gd, device=dev, dtype=torch.float64) - 1.0
+        Td = torch.empty((nld * 12, Nd), dtype=torch.float64, device=dev)
+        Vd = torch.empty((nsd, Nd), dtype=torch.float64, device=dev)
+        Gd = torch.empty((nsd * ndd, Nd), dtype=torch.float64, device=dev)
+        fk_d = np.array([l.id for l in md.links], dtype=np.int32)
+        cd = make_call(Nd, Qd.data_ptr(), Td.data_ptr(), None, Vd.data_ptr(), Gd.data_ptr())
+        cd.n_fk_links, cd.fk_links, cd.n_jac_links, cd.jac_links = nld, fk_d.ctypes.data_as(ip), 0, None
+        variant("dual_arm_with_planar_base(18 columns,37 links,S=19,B=3):fk_all_links+collision_cost_grad", 8 * (ndd + 12 * nld + nsd + nsd * ndd), cd, Nd, dmd)
+        del Qd, Td, Vd, Gd
 
     # ---- small batches: the sizes the reference's solver callbacks really evaluate (one configuration per IK
     #      iteration, n_wp = 10..64 per planning iteration): latency of one fused kin_eval, launch to completion ----

@@ -1334,7 +1334,7 @@ void launch_ik_coll_step(const kin::IkCollArgs &a, bool rot, cudaStream_t stream
     auto kern = rot ? kin::ik_coll_step_kernel<ND, true> : kin::ik_coll_step_kernel<ND, false>;
     if (ND == 0) {
         // run-time-sized instance (13 .. IKC_MAX_DOF columns): the normal equations of a problem live in shared memory,
-        // [slot][thread]; the largest CTA whose slots fit (18 columns: 1800 B per thread -> 96 threads)
+        // [slot][thread]; the largest CTA whose slots fit (18 columns: 1800 B per thread, 128 threads = 225 KB; 20 columns: 96 threads)
         const size_t per = kin::ikc_dyn_smem_per_thread(a.nd);
         while (block > 32 && per * (size_t)block > (size_t)dev_smem) block -= 32;
         smem = per * (size_t)block;
@@ -1424,7 +1424,15 @@ int ik_solve_coll(KinModel *m, const KinIkCall *c) {
         rc = kin_eval(m, &ec);
         if (rc != KIN_OK) break;
         a.it = it;
-        switch (nd) {
+        // KIN_IK_STEP=warp sends the step through the one-warp-per-problem kernel (kin_ik_coll.cuh: an independent
+        // parallelisation with bit-identical iterates, kept as a cross-check; measured slower than one thread per problem
+        // at every list length: 18 columns, 42 k problems 1.7 against 1.06 ms, 262 k problems 9.3 against 4.6 ms)
+        const char *step_mode = std::getenv("KIN_IK_STEP");
+        if (step_mode && !std::strcmp(step_mode, "warp")) {
+            const unsigned grid = (unsigned)((a.n_act + 3) / 4);                 // 4 warps = 4 problems per CTA
+            if (rows == 6) kin::ik_coll_step_warp_kernel<true><<<grid, 128, 0, stream>>>(a);
+            else kin::ik_coll_step_warp_kernel<false><<<grid, 128, 0, stream>>>(a);
+        } else switch (nd) {
 #define KIN_IKC_CASE(N_) case N_: launch_ik_coll_step<N_>(a, rows == 6, stream, m->dev_smem); break;
             KIN_IKC_CASE(1) KIN_IKC_CASE(2) KIN_IKC_CASE(3) KIN_IKC_CASE(4) KIN_IKC_CASE(5) KIN_IKC_CASE(6)
             KIN_IKC_CASE(7) KIN_IKC_CASE(8) KIN_IKC_CASE(9) KIN_IKC_CASE(10) KIN_IKC_CASE(11) KIN_IKC_CASE(12)

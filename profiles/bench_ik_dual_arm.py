@@ -1,4 +1,4 @@
-"""Batched IK on the dual-arm model (tests/golden/dual_arm.urdf; 15 columns, 18 with the planar base): pose-only solve
+"""Batched IK on the dual-arm model (data/dual_arm.urdf; 15 columns, 18 with the planar base): pose-only solve
 (generated one-launch kernel, staged) and the collision-constrained solve (kin_eval + run-time-sized step kernel pairs)
 over 2^k reachable left-tool targets.   python profiles/bench_ik_dual_arm.py [log2 n]"""
 import os
@@ -11,22 +11,12 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import kinematics_jl_b200 as K  # noqa: E402
+import scene_fetch  # noqa: E402
 
 N = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 18)
-URDF = os.path.join(ROOT, "tests", "golden", "dual_arm.urdf")
-JOINTS = ["torso_joint"] + ["%s_joint%d" % (s, i) for s in "lr" for i in range(1, 8)]
 dev = torch.device("cuda", 0)
 for with_base in ((True,) if os.environ.get("IK_BASE_ONLY") else (False, True)):
-    m = K.parse_urdf(URDF, with_base=with_base)
-    joints = [K.find_joint(m, n) for n in JOINTS]
-    sscc = K.SweptSphereCollisionChecker(m)
-    for s in "lr":
-        for i in range(2, 8):
-            K.add_coll_links(sscc, K.find_link(m, "%s_link%d" % (s, i)), [[0.05, 0, 0]] if i % 2 else [[0.03, 0, 0], [0.1, 0, 0.01]], 0.05)
-    K.add_coll_links(sscc, K.find_link(m, "torso"), [[0, 0, 0.2]], 0.15)
-    poses = [np.eye(4) for _ in range(3)]
-    poses[0][:3, 3], poses[1][:3, 3], poses[2][:3, 3] = [0.8, 0, 0.9], [0.5, 0.5, 1.0], [0.5, -0.6, 0.6]
-    sdf = K.UnionSDF([K.BoxSDF(K.Transform(p), w) for p, w in zip(poses, [[0.3, 0.8, 0.05], [0.2, 0.2, 0.6], [0.4, 0.2, 0.3]])])
+    m, joints, sscc, sdf = scene_fetch.product_dual_arm(with_base)
     link = K.find_link(m, "l_tool")
     nd = len(joints) + (3 if with_base else 0)
     lo = torch.tensor([j.lower_limit for j in joints], device=dev, dtype=torch.float64)

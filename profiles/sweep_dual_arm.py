@@ -1,4 +1,4 @@
-"""A dual-arm mechanism (tests/golden/dual_arm.urdf: 15 columns, 18 with the planar base, 19 spheres, 3 boxes): the fused
+"""A dual-arm mechanism (data/dual_arm.urdf: 15 columns, 18 with the planar base, 19 spheres, 3 boxes): the fused
 call and the collision-only call, interpreting kernel against the specialised one whose joint frames live in the shared
 scratch (GenOptions::jf_smem), SoA.   python profiles/sweep_dual_arm.py [log2 n]
 SWEEP_JIT_ONLY=1 with KIN_JIT_JF_REGS_MAX / KIN_JIT_BLOCK / KIN_JIT_MINB: launch-shape variants of the specialised kernel."""
@@ -12,29 +12,19 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import kinematics_jl_b200 as K  # noqa: E402
+import scene_fetch  # noqa: E402
 from kinematics_jl_b200 import lib as L  # noqa: E402
 from kinematics_jl_b200.device import device_model  # noqa: E402
 
 N = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 21)
 F32 = bool(os.environ.get("SWEEP_F32"))
 DT, RS = (torch.float32, 4) if F32 else (torch.float64, 8)
-URDF = os.path.join(ROOT, "tests", "golden", "dual_arm.urdf")
-JOINTS = ["torso_joint"] + ["%s_joint%d" % (s, i) for s in "lr" for i in range(1, 8)]
 dev = torch.device("cuda", 0)
 lib = L.lib()
 stream = torch.cuda.current_stream(dev)
 ip = C.POINTER(C.c_int32)
 for with_base in (False, True):
-    m = K.parse_urdf(URDF, with_base=with_base)
-    joints = [K.find_joint(m, n) for n in JOINTS]
-    sscc = K.SweptSphereCollisionChecker(m)
-    for s in "lr":
-        for i in range(2, 8):
-            K.add_coll_links(sscc, K.find_link(m, "%s_link%d" % (s, i)), [[0.05, 0, 0]] if i % 2 else [[0.03, 0, 0], [0.1, 0, 0.01]], 0.05)
-    K.add_coll_links(sscc, K.find_link(m, "torso"), [[0, 0, 0.2]], 0.15)
-    poses = [np.eye(4) for _ in range(3)]
-    poses[0][:3, 3], poses[1][:3, 3], poses[2][:3, 3] = [0.8, 0, 0.9], [0.5, 0.5, 1.0], [0.5, -0.6, 0.6]
-    sdf = K.UnionSDF([K.BoxSDF(K.Transform(p), w) for p, w in zip(poses, [[0.3, 0.8, 0.05], [0.2, 0.2, 0.6], [0.4, 0.2, 0.3]])])
+    m, joints, sscc, sdf = scene_fetch.product_dual_arm(with_base)
     nd, S, nl = len(joints) + (3 if with_base else 0), len(sscc.sphere_radii), len(m.links)
     K.set_joint_angles(m, joints, torch.zeros((1, nd), dtype=torch.float64, device=dev))
     K.compute_coll_dists(sscc, joints, sdf)

@@ -44,3 +44,25 @@ def joint_limits(joints):
     lo = np.array([j.lower_limit if np.isfinite(j.lower_limit) else -np.pi for j in joints])
     hi = np.array([j.upper_limit if np.isfinite(j.upper_limit) else np.pi for j in joints])
     return lo, hi
+
+
+# ---- a dual-arm mechanism (data/dual_arm.urdf: torso + 2 x 7 joints; 15 configuration columns, 18 with the planar base:
+#      the size class of the PR2 that the reference's fridge_demo.jl and test_inverse_kinematics.jl:26-88 drive) ----
+DUAL_ARM_JOINT_NAMES = ["torso_joint"] + ["%s_joint%d" % (s, i) for s in "lr" for i in range(1, 8)]
+DUAL_ARM_SPHERES = [("%s_link%d" % (s, i), [[0.05, 0, 0]] if i % 2 else [[0.03, 0, 0], [0.1, 0, 0.01]], 0.05)
+                    for s in "lr" for i in range(2, 8)] + [("torso", [[0, 0, 0.2]], 0.15)]
+DUAL_ARM_BOX_POSES = [np.array([[1.0, 0, 0, 0.8], [0, 1, 0, 0.0], [0, 0, 1, 0.9], [0, 0, 0, 1.0]]),
+                      np.array([[0.36, -0.48, 0.8, 0.5], [0.8, 0.6, 0.0, 0.5], [-0.48, 0.64, 0.6, 1.0], [0, 0, 0, 1.0]]),
+                      np.array([[1.0, 0, 0, 0.5], [0, 1, 0, -0.6], [0, 0, 1, 0.6], [0, 0, 0, 1.0]])]
+DUAL_ARM_BOX_WIDTHS = [[0.3, 0.8, 0.05], [0.2, 0.2, 0.6], [0.4, 0.2, 0.3]]
+
+
+def product_dual_arm(with_base=False):
+    """-> (Mechanism, the 15 control joints, checker with 19 spheres on both arms and the torso, three-box UnionSDF)."""
+    m = K.parse_urdf(os.path.join(DATA, "dual_arm.urdf"), with_base=with_base)
+    joints = [K.find_joint(m, n) for n in DUAL_ARM_JOINT_NAMES]
+    sscc = K.SweptSphereCollisionChecker(m)
+    for link, centers, r in DUAL_ARM_SPHERES:
+        K.add_coll_links(sscc, K.find_link(m, link), centers, r)
+    sdf = K.UnionSDF([K.BoxSDF(K.Transform(p), w) for p, w in zip(DUAL_ARM_BOX_POSES, DUAL_ARM_BOX_WIDTHS)])
+    return m, joints, sscc, sdf

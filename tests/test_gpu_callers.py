@@ -135,7 +135,7 @@ def _thin_box():
     return pose, [0.05, 0.05, 0.5]                         # the pillar of test/test_planning.jl:23-25
 
 
-def test_batched_collision_aware_ik():
+def test_batched_collision_aware_ik(monkeypatch):
     """Config 4 with the reference's HARD collision constraint (inverse_kinematics.jl:14-19: dists - 0.02 >= 0 after the
     collision-free warm start) solved on the device for the whole batch (kin_ik_solve with collision = 1).
 
@@ -177,6 +177,11 @@ def test_batched_collision_aware_ik():
     assert lib.kin_launch_count() - n0 == 1 + 61 * 2 + 2
     r1, c1, dm1 = outcome(q1)
     np.testing.assert_allclose(dmin1.cpu().numpy(), dm1, rtol=1e-12, atol=1e-12)
+    # the one-warp-per-problem step kernel (opt-in; an independent parallelisation of the step) on the same problems: the same iterates, bit for bit
+    monkeypatch.setenv("KIN_IK_STEP", "warp")
+    q1w, f1w, itsw, dmin1w = K.ik_solve_device(m, link, joints, dev(tg), q_free, with_rot=True, iters=60, sscc=sscc, sdf=box, margin=margin)
+    monkeypatch.delenv("KIN_IK_STEP")
+    assert torch.equal(q1w, q1) and torch.equal(f1w, f1) and torch.equal(itsw, its) and torch.equal(dmin1w, dmin1)
     q2, f2, dmin2 = K.inverse_kinematics_batch(m, link, joints, dev(tg), dev(q0), with_rot=True, iters=40, sscc=sscc, sdf=box, margin=margin,
                                                restarts=3, return_dmin=True)
     r2, c2, dm2 = outcome(q2)
@@ -604,7 +609,7 @@ def test_device_resident_ik_solve(with_base, monkeypatch):
 
 
 @pytest.mark.parametrize("with_base", [False, True])
-def test_device_resident_ik_solve_dual_arm(with_base):
+def test_device_resident_ik_solve_dual_arm(with_base, monkeypatch):
     """kin_ik_solve on a model beyond 12 configuration columns (tests/scenes_dual_arm.py: 15, 18 with the planar base -- the
     shape of the reference's PR2 inverse-kinematics test, test_inverse_kinematics.jl:26-88): the generated one-launch
     kernel for the pose-only solve, and the collision-constrained solve whose step kernel runs its run-time-sized
@@ -650,6 +655,21 @@ def test_device_resident_ik_solve_dual_arm(with_base):
     print("dual-arm constrained IK (%d columns): reached %.1f %% / clear %.1f %% / both %.1f %%"
           % (nd, 100 * reached.mean(), 100 * clear.mean(), 100 * (reached & clear).mean()))
     assert clear.mean() > 0.97 and (reached & clear).mean() > (0.90 if with_base else 0.60)
+    # the step kernel above 12 columns is the run-time-sized one-thread-per-problem instance (normal equations in shared
+    # memory); the one-warp-per-problem kernel, an independent parallelisation of the same step, gives the same iterates
+    monkeypatch.setenv("KIN_IK_STEP", "warp")
+    q4, f4, dmin4 = K.inverse_kinematics_batch(m, link, joints, dev(tg), dev(q0), with_rot=True, iters=40, sscc=sscc, sdf=sdf, margin=0.02,
+                                               restarts=2, return_dmin=True)
+    monkeypatch.delenv("KIN_IK_STEP")
+    assert torch.equal(q4, q3) and torch.equal(f4, f3) and torch.equal(dmin4, dmin)
+    # position-only targets (3 rows of residual) through both step kernels
+    outs = []
+    for mode in ("warp", "thread"):
+        monkeypatch.setenv("KIN_IK_STEP", mode)
+        outs.append(K.ik_solve_device(m, link, joints, dev(tg[:512]), dev(q0[:512]), with_rot=False, iters=30, sscc=sscc, sdf=sdf, margin=0.02))
+        monkeypatch.delenv("KIN_IK_STEP")
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
 
 
 def test_staged_ik_solve_is_bitwise_the_single_launch(monkeypatch):

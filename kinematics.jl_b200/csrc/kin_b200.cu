@@ -412,6 +412,13 @@ kin::GenOptions gen_options(const KinModel *m, const KinCall *c, const DevicePro
     // (jf_smem, opt-in through KIN_JIT_JF_REGS_MAX) costs threads and measured 4.15 against 2.52 ms at 15 columns,
     // 6.21 against 2.84 at 18.
     o.jf_smem = (o.coll && h.n_dof > env_ll("KIN_JIT_JF_REGS_MAX", 32)) ? 1 : 0;
+    // phase 2b: one instance per distinct relevance mask (0, default), or one instance testing the mask at run time (1; -1: when
+    // there are more than KIN_JIT_RTMASK_MIN masks).  Dual-arm model, 13 masks, 18-column loops: the code shrinks from 15.7 k
+    // to 6.4 k instructions, the time does not follow (2^21 configurations, ms per-mask / run-time: 15 columns collision-only
+    // 2.57 / 2.60, fused 3.29 / 3.04; 18 columns 2.84 / 2.99, 3.66 / 3.67): the node barriers already make a CTA share its
+    // instruction fetches.  Kept as a knob.
+    o.rtmask = (int)env_ll("KIN_JIT_RTMASK", 0);
+    o.rtmask_min = (int)env_ll("KIN_JIT_RTMASK_MIN", 6);
     if (o.coll && (!std::getenv("KIN_JIT_BLOCK") || o.jf_smem)) {
         const size_t cta_max = (size_t)(m ? m->dev_smem : 227 * 1024), sm_total = cta_max + 1024;   // 228 KB per SM, 1 KB reserved per CTA
         auto fits = [&](int block, int minb) {

@@ -11,9 +11,9 @@ namespace kin {
 
 std::string GenOptions::key() const {
     char b[192];
-    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d I%d W%d P%d B%d F%d", precision, layout, (int)want_T, (int)want_J,
+    std::snprintf(b, sizeof b, "p%d l%d T%d J%d c%d r%d y%d k%d g%d a%d s%d w%d b%d m%d q%d y%d e%d G%d C%d I%d W%d P%d B%d F%d R%d.%d", precision, layout, (int)want_T, (int)want_J,
                   (int)coll, with_rot, rpy_jac, keep_irrelevant, (int)want_grads, (int)want_argmin, (int)stale, (int)ws, block, min_blocks, qbatch,
-                  ksync, es32, grad_mode, fd_cold, ik, warp, prims, bulk, jf_smem);
+                  ksync, es32, grad_mode, fd_cold, ik, warp, prims, bulk, jf_smem, rtmask, rtmask_min);
     return b;
 }
 
@@ -358,6 +358,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
 
     // ------------------------------------------------------------------ phase 2: one call per run of equal masks
     std::ostringstream p2;
+    bool rt_mask = false;       // phase 2b tests the relevance mask at run time (one instance) instead of one instance per mask
     if (o.coll) {
         // joint frames of the columns as the consumers of phase 2 see them
         p2 << "#ifndef KJFR_DEFINED\nconst JFrame<real> jfr[KND] = {\n";
@@ -386,17 +387,24 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
             for (unsigned mk : masks) seen |= mk == r.mask;
             if (!seen) masks.push_back(r.mask);
         }
-        p2 << "#if !KWARP\n#pragma unroll 1\nfor (int s0 = 0; s0 < KS;) {\n    int se, mi;\n";
+        rt_mask = o.rtmask == 1 || (o.rtmask < 0 && (int)masks.size() > o.rtmask_min);
+        p2 << "#if !KWARP\n#pragma unroll 1\nfor (int s0 = 0; s0 < KS;) {\n    int se, mi;\n    unsigned mk;\n";
         for (size_t r = 0; r < runs.size(); ++r) {
             size_t mi = 0;
             while (masks[mi] != runs[r].mask) ++mi;
             p2 << "    " << (r ? "else " : "") << (r + 1 < runs.size() ? "if (s0 < " + std::to_string(runs[r].se) + ") " : "") << "{ se = " << runs[r].se
-               << "; mi = " << mi << "; }\n";
+               << "; mi = " << mi << "; mk = 0x" << std::hex << runs[r].mask << std::dec << "u; }\n";
         }
-        p2 << "    const int ge = min(s0 + SPH_GROUP, se);\n    phase2a_group<real>(s0, ge, KP2AARGS);\n    switch (mi) {\n";
-        for (size_t mi = 0; mi < masks.size(); ++mi)
-            p2 << "        case " << mi << ": phase2b_group<real, KND, 0x" << std::hex << masks[mi] << std::dec << "u>(s0, ge, KP2BARGS); break;\n";
-        p2 << "        default: break;\n    }\n    s0 = ge;\n}\n#endif\n";
+        p2 << "    const int ge = min(s0 + SPH_GROUP, se);\n    phase2a_group<real>(s0, ge, KP2AARGS);\n";
+        if (rt_mask) {
+            p2 << "    (void)mi;\n    phase2b_group<real, KND, 0u>(s0, ge, KP2BARGS);\n";
+        } else {
+            p2 << "    switch (mi) {\n";
+            for (size_t mi = 0; mi < masks.size(); ++mi)
+                p2 << "        case " << mi << ": phase2b_group<real, KND, 0x" << std::hex << masks[mi] << std::dec << "u>(s0, ge, KP2BARGS); break;\n";
+            p2 << "        default: break;\n    }\n";
+        }
+        p2 << "    s0 = ge;\n}\n#endif\n";
     }
     out.phase2 = p2.str();
 
@@ -404,6 +412,7 @@ bool generate_source(const Program &p, const GenOptions &o, GenSource &out, std:
     std::ostringstream c;
     c << "#define KREAL " << (f32 ? "float" : "double") << "\n";
     if (o.fd_cold) c << "#define KIN_FD_COLD 1\n";
+    c << "#define KP2RTMASK " << (rt_mask ? 1 : 0) << "\n";
     c << "#define KJFSMEM " << ((o.jf_smem && o.coll && !o.warp && !o.ik) ? 1 : 0) << "\n";
     c << "#define KPRIMS " << o.prims << "\n#define KBULK " << ((o.bulk && o.layout == 2 && !o.warp && !o.ik) ? 1 : 0) << "\n";
     c << "#define KWANT_T " << (o.want_T ? 1 : 0) << "\n#define KWANT_J " << (o.want_J ? 1 : 0) << "\n#define KCOLL " << (o.coll ? 1 : 0)

@@ -39,6 +39,9 @@ struct GenOptions {
     int fd_cold = 0;            // 1: the rare direct-FD fallback of the series gradient is an out-of-line call
     int ksync = 0;              // 1: CTA-wide barrier after every node of phase 1 (the warps of a CTA then fetch the
                                 //    straight-line code together: one instruction-cache fill serves all of them)
+    int rtmask = 0;             // phase 2b: 1 = one instance testing the relevance mask at run time, 0 = one instance per distinct mask,
+                                //   -1 = by the number of distinct masks (more than rtmask_min: run time)
+    int rtmask_min = 6;
     int jf_smem = 0;            // 1: the joint frames of phase 2 live in the per-thread shared scratch, not in registers (opt-in, KIN_JIT_JF_REGS_MAX: measured slower)
     int bulk = 0;               // 1: tiled layout, FK / Jacobian only: outputs staged per warp and written with cp.async.bulk (TMA)
     int prims = 0;              // 1: the SDF table holds rows other than boxes (sphere / cylinder): the row loops test the kind

@@ -128,9 +128,15 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
                                               , real_ *stw, const int nvalid
 #endif
                                               , const real_ *jfs     // KJFSMEM: this thread's joint frames in the shared scratch, [6 j + i][thread]
+                                              , const unsigned rmask // KP2RTMASK: the relevance mask of this run of spheres at run time
                                               ) {
     typedef real_ real;
     constexpr int BS = KBS;
+    // One instance per distinct relevance mask (MASK: the column loop below keeps only what that mask needs) -- or (opt-in,
+    // KIN_JIT_RTMASK: for models with many distinct masks, e.g. 13 instances of an 18-column loop on a dual-arm mechanism)
+    // ONE instance that tests the mask of the run at run time: warp-uniform branches, 2.4 x less code, measured within
+    // +-8 % of the per-mask instances (kin_b200.cu: gen_options)
+    const unsigned mask_ = KP2RTMASK ? rmask : MASK;
 #if KAOS && !KWARP && !KIK
     const int lane = (int)es;
     real *stg = stw + lane;
@@ -170,7 +176,7 @@ __device__ __forceinline__ void phase2b_group(const int s0, const int ge, const 
             #pragma unroll
             for (int j = 0; j < ND; ++j) {
                 real *st = stale0 + 3 * j * BS;
-                if ((MASK >> j) & 1u) {       // joint_jacobian!, algorithm.jl:65-81
+                if ((mask_ >> j) & 1u) {      // joint_jacobian!, algorithm.jl:65-81
                     real cx, cy, cz;
 #if KJFSMEM
                     // more than 12 columns: the frames do not fit in registers; six shared loads with immediate offsets
@@ -714,9 +720,9 @@ extern "C" __global__ void __launch_bounds__(KBS, KMINB) kin_gen_kernel(const __
                 JFrame<real> jfr[KND];                        // unused: the frames were parked in the scratch by KJF_OUT
 #endif
 #if KAOS
-                #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, (size_t)lane, stw, nvalid, jfs
+                #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, (size_t)lane, stw, nvalid, jfs, mk
 #else
-                #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, es, jfs
+                #define KP2BARGS tb, rad, cent0, stale0, hand, jfr, A.grad_mode, trunc, voff, Vp0, Gp0, Ap0, es, jfs, mk
 #endif
 #include "kin_gen_phase2.inc"
 #endif

@@ -271,22 +271,29 @@ def test_dual_arm_program_and_specialised_kernel_compile(with_base, tmp_path):
     expect = {(L.SOA, L.F64): (128, 2) if not with_base else (224, 1), (L.AOS, L.F64): None,
               (L.TILED32, L.F32): (256, 2) if not with_base else (480, 1), (L.TILED32, L.F64): (256, 1) if not with_base else (224, 1)}
     for (layout, prec), shape in expect.items():
-        for jf_smem in ((False, True) if layout == L.SOA else (False,)):
+        for variant in (("default", "jf_smem", "rtmask") if layout == L.SOA else ("default",)):
+            jf_smem = variant == "jf_smem"
             c = L.KinCall()
             c.precision, c.layout, c.n, c.q = prec, layout, 1 << 20, 1
             c.n_fk_links, c.fk_links, c.T_out = len(fk), fk.ctypes.data_as(C.POINTER(C.c_int32)), 1
             c.truncation_dist = float("inf")
             c.vals_out, c.grads_out = 1, 1
-            out_dir = tmp_path / ("l%d_p%d_%d" % (layout, prec, jf_smem))
+            out_dir = tmp_path / ("l%d_p%d_%s" % (layout, prec, variant))
             out_dir.mkdir()
-            if jf_smem:               # opt-in variant: joint frames parked in the shared scratch (measured slower, kept as a knob)
-                os.environ["KIN_JIT_JF_REGS_MAX"] = "12"
+            # opt-in variants (measured, not faster, kept as knobs): joint frames parked in the shared scratch; one instance of
+            # phase 2b that tests the relevance mask at run time instead of one instance per distinct mask (13 here)
+            knob = {"jf_smem": ("KIN_JIT_JF_REGS_MAX", "12"), "rtmask": ("KIN_JIT_RTMASK", "1")}.get(variant)
+            if knob:
+                os.environ[knob[0]] = knob[1]
             try:
                 L.check(lib.kin_codegen_dump(C.byref(d), C.byref(c), 1, str(out_dir).encode()))
             finally:
-                os.environ.pop("KIN_JIT_JF_REGS_MAX", None)
+                if knob:
+                    os.environ.pop(knob[0], None)
             cfg = (out_dir / "kin_gen_config.h").read_text()
-            assert ("#define KJFSMEM %d" % jf_smem) in cfg
+            assert ("#define KJFSMEM %d" % jf_smem) in cfg and ("#define KP2RTMASK %d" % (variant == "rtmask")) in cfg
+            n_inst = (out_dir / "kin_gen_phase2.inc").read_text().count("phase2b_group<")
+            assert n_inst == (1 if variant == "rtmask" else 13)
             kbs = int(re.search(r"#define KBS (\d+)", cfg).group(1))
             minb = int(re.search(r"#define KMINB (\d+)", cfg).group(1))
             assert kbs % 32 == 0 and 32 <= kbs <= 512

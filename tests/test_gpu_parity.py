@@ -650,6 +650,16 @@ def test_specialised_kernel_on_a_dual_arm_model(layout, with_base, monkeypatch):
                 outs.append(o)
             for key in ("T", "J", "vals", "grads", "argmin"):
                 assert torch.equal(outs[0][key], outs[1][key]), (key, kw, dtype)
+            if dtype == torch.float64 and kw is combos[0] and layout == L.SOA:
+                # opt-in code shape: ONE instance of phase 2b that tests the relevance mask at run time (KIN_JIT_RTMASK)
+                monkeypatch.setenv("KIN_JIT_RTMASK", "1")
+                o = evaluate(dm, Qc, ql, N, layout=layout, fk_links=ids, jac_links=tools, with_rot=True, rpy_jac=True,
+                             collision=True, want_argmin=True, launch_info=True, **kw)
+                torch.cuda.synchronize()
+                monkeypatch.delenv("KIN_JIT_RTMASK")
+                assert o["launch"]["block"] < 0
+                for key in ("T", "J", "vals", "grads", "argmin"):
+                    assert torch.equal(outs[0][key], o[key]), (key, "rtmask")
         if dtype == torch.float64:        # the last combination (analytic gradient is an extension: FD combination re-run for the oracle)
             sub = slice(0, 400)
             b = outs[1]

@@ -4,6 +4,7 @@ mirrors the kernel.  What this pins without a GPU: link/joint id assignment, top
 constant folding of fixed chains, relevance masks, sphere pre-composition, box inversion, scratch
 (stale column) ordering."""
 import os
+import re
 
 import numpy as np
 import pytest
@@ -209,6 +210,11 @@ def test_codegen_and_nvrtc_compile_without_a_gpu(tmp_path):
         assert 100 < n_arith < 400
         assert p1.count("KST_T(") == 300 and p1.count("KST_J(") == 48
         assert (out / "kin_gen.cubin").stat().st_size > 10000
+        # the measured launch shapes of the headline kernels (profiles/sweep_jit.py) are what the library picks for Fetch: the
+        # fit-driven search of gen_options (models with a large per-thread scratch) must leave them alone
+        cfg0 = (out / "kin_gen_config.h").read_text()
+        shape = tuple(int(re.search(r"#define %s (\d+)" % k, cfg0).group(1)) for k in ("KBS", "KMINB"))
+        assert shape == ((128, 2) if fused else (128, 1)), shape
         if fused:
             p2 = (out / "kin_gen_phase2.inc").read_text()
             assert p2.count("phase2b_group<") == 4 and p2.count("phase2a_group<") == 1   # four relevance masks, one shared box search
